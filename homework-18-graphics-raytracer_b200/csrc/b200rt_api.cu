@@ -1,0 +1,468 @@
+// b200rt_api.cu — the C ABI of libb200rt.so: context, scene packing, render entry points.
+//
+// Host code in this file is built with -ffp-contract=off: the per-triangle invariants it hoists
+// (face normal, plane offset; primitives.rs:37-42, main.rs:203) and the camera basis (main.rs:85-92)
+// must have the same bits the reference computes per pair / per pixel.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b200rt.h"
+#include "hvec.h"
+#include "rt_types.h"
+
+using namespace b200rt;
+using namespace b200rt_host;
+
+struct b200rt_ctx {
+    int device = -1;
+    int sm_count = 0;
+    int sm_clock_khz = 0;
+    size_t hbm_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::string last_cuda_error;
+
+    // device scene
+    bool have_scene = false;
+    DScene scene{};
+    void* d_scene_blob = nullptr;
+    size_t scene_blob_bytes = 0;
+
+    // device scratch for the host-buffer entry points
+    void* d_out = nullptr;  size_t d_out_bytes = 0;
+    void* d_aux = nullptr;  size_t d_aux_bytes = 0;
+    DCounters* d_cnt = nullptr;
+
+    b200rt_stats stats{};
+};
+
+namespace {
+
+int cuda_fail(b200rt_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) {
+        ctx->last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+    }
+    return B200RT_ERR_CUDA;
+}
+
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+int ensure(b200rt_ctx* ctx, void** p, size_t* have, size_t need) {
+    if (*have >= need && *p) return B200RT_OK;
+    if (*p) { CU(cudaFree(*p)); *p = nullptr; *have = 0; }
+    CU(cudaMalloc(p, need));
+    *have = need;
+    return B200RT_OK;
+}
+
+// Camera::shoot hoisted (main.rs:85-92)
+void make_camera(const b200rt_camera& c, DCamera& out) {
+    V3 toward = normalize(v3(c.toward));
+    V3 right = normalize(cross(toward, v3(c.up)));
+    V3 up = normalize(cross(right, toward));
+    float t = std::tan(c.fovy / 2.0f);
+    store(out.toward, toward);
+    store(out.x, t * right);
+    store(out.y, t * up);
+    store(out.origin, v3(c.center) + toward * c.near);
+    store(out.center, v3(c.center));
+    out.near = c.near;
+}
+
+int make_params(const b200rt_params& p, uint32_t epoch_begin, uint32_t epoch_count, DParams& o) {
+    if (p.width == 0 || p.height == 0) return B200RT_ERR_INVALID;
+    if (p.depth < 0 || p.depth > B200RT_MAX_DEPTH) return B200RT_ERR_UNSUPPORTED;
+    if (p.row_count && (p.row_begin >= p.height || p.row_begin + p.row_count > p.height)) return B200RT_ERR_INVALID;
+    if (p.cast_mode > B200RT_CAST_BRUTE_EXACT) return B200RT_ERR_INVALID;
+    o.width = p.width; o.height = p.height;
+    o.row_begin = p.row_count ? p.row_begin : 0u;
+    o.row_count = p.row_count ? p.row_count : p.height;
+    o.depth = p.depth;
+    o.threshold = p.threshold;
+    o.refract_max_distance = p.refract_max_distance;
+    o.tir_retries = p.tir_retries;
+    o.focus = p.focus; o.blur = p.blur;
+    o.seed_lo = (uint32_t)p.seed; o.seed_hi = (uint32_t)(p.seed >> 32);
+    o.cast_mode = p.cast_mode;
+    o.epoch_begin = epoch_begin; o.epoch_count = epoch_count;
+    return B200RT_OK;
+}
+
+int fetch_counters(b200rt_ctx* ctx) {
+    DCounters h;
+    CU(cudaMemcpyAsync(&h, ctx->d_cnt, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.casts = h.casts;
+    ctx->stats.tri_pair_tests = h.tri_pairs;
+    ctx->stats.sph_pair_tests = h.sph_pairs;
+    ctx->stats.exact_confirms = h.confirms;
+    ctx->stats.samples = h.samples;
+    return B200RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200rt_strerror(int code) {
+    switch (code) {
+        case B200RT_OK: return "ok";
+        case B200RT_ERR_INVALID: return "invalid argument";
+        case B200RT_ERR_CUDA: return "CUDA runtime error (see b200rt_last_cuda_error)";
+        case B200RT_ERR_NO_SCENE: return "no scene uploaded";
+        case B200RT_ERR_NO_DEVICE: return "no usable CUDA device (libb200rt has no CPU fallback)";
+        case B200RT_ERR_IO: return "OBJ file could not be read or parsed";
+        case B200RT_ERR_UNSUPPORTED: return "unsupported parameter (depth > B200RT_MAX_DEPTH?)";
+        default: return "unknown error";
+    }
+}
+
+const char* b200rt_last_cuda_error(const b200rt_ctx* ctx) { return ctx ? ctx->last_cuda_error.c_str() : ""; }
+
+int b200rt_create(int device_id, b200rt_ctx** out_ctx) {
+    if (!out_ctx) return B200RT_ERR_INVALID;
+    *out_ctx = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return B200RT_ERR_NO_DEVICE;
+    if (device_id < 0 || device_id >= n) return B200RT_ERR_NO_DEVICE;
+    b200rt_ctx* ctx = new b200rt_ctx();
+    ctx->device = device_id;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) {
+        delete ctx;
+        return B200RT_ERR_NO_DEVICE;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_id);
+    ctx->sm_clock_khz = khz;
+    ctx->hbm_bytes = prop.totalGlobalMem;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_cnt, sizeof(DCounters)) != cudaSuccess ||
+        cudaMemset(ctx->d_cnt, 0, sizeof(DCounters)) != cudaSuccess) {
+        b200rt_destroy(ctx);
+        return B200RT_ERR_CUDA;
+    }
+    *out_ctx = ctx;
+    return B200RT_OK;
+}
+
+int b200rt_destroy(b200rt_ctx* ctx) {
+    if (!ctx) return B200RT_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_scene_blob) cudaFree(ctx->d_scene_blob);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->d_aux) cudaFree(ctx->d_aux);
+    if (ctx->d_cnt) cudaFree(ctx->d_cnt);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return B200RT_OK;
+}
+
+int b200rt_device_info(const b200rt_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* hbm_bytes) {
+    if (!ctx) return B200RT_ERR_INVALID;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (sm_clock_khz) *sm_clock_khz = ctx->sm_clock_khz;
+    if (hbm_bytes) *hbm_bytes = ctx->hbm_bytes;
+    return B200RT_OK;
+}
+
+int b200rt_upload_scene(b200rt_ctx* ctx, const b200rt_scene* s) {
+    if (!ctx || !s) return B200RT_ERR_INVALID;
+    if ((s->n_triangles && !s->triangles) || (s->n_spheres && !s->spheres) || (s->n_materials && !s->materials) ||
+        (s->n_lights && !s->lights))
+        return B200RT_ERR_INVALID;
+    for (uint32_t i = 0; i < s->n_triangles; ++i)
+        if (s->triangles[i].object_index >= s->n_materials) return B200RT_ERR_INVALID;
+    for (uint32_t i = 0; i < s->n_spheres; ++i)
+        if (s->spheres[i].object_index >= s->n_materials) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+
+    const uint32_t nt = s->n_triangles, ns = s->n_spheres, nm = s->n_materials, nl = s->n_lights;
+    const uint32_t nt_pad = ((nt + kTileTris - 1) / kTileTris) * kTileTris;
+
+    // ---- pack (host) ------------------------------------------------------------------------------
+    std::vector<float4> tri_exact(4 * (size_t)std::max(nt, 1u)), tri_attr(4 * (size_t)std::max(nt, 1u));
+    std::vector<float4> sph(std::max(ns, 1u));
+    std::vector<uint32_t> sph_obj(std::max(ns, 1u));
+    std::vector<DMaterial> mats(std::max(nm, 1u));
+    std::vector<DLight> lights(std::max(nl, 1u));
+    for (uint32_t i = 0; i < nt; ++i) {
+        const b200rt_triangle& t = s->triangles[i];
+        const V3 v0 = v3(t.vertices[0].position), v1 = v3(t.vertices[1].position), v2 = v3(t.vertices[2].position);
+        // Triangle::face_normal, primitives.rs:37-42, and d = n . v0, main.rs:203
+        const V3 a = v1 - v0, b = v2 - v1;
+        const V3 n = normalize(cross(a, b));
+        const float d = dot(n, v0);
+        float obj_bits;
+        std::memcpy(&obj_bits, &t.object_index, 4);
+        tri_exact[4 * (size_t)i + 0] = make_float4(n.x, n.y, n.z, d);
+        tri_exact[4 * (size_t)i + 1] = make_float4(v0.x, v0.y, v0.z, obj_bits);
+        tri_exact[4 * (size_t)i + 2] = make_float4(v1.x, v1.y, v1.z, 0.0f);
+        tri_exact[4 * (size_t)i + 3] = make_float4(v2.x, v2.y, v2.z, 0.0f);
+        const b200rt_vertex* v = t.vertices;
+        tri_attr[4 * (size_t)i + 0] = make_float4(v[0].normal[0], v[0].normal[1], v[0].normal[2], v[0].uv[0]);
+        tri_attr[4 * (size_t)i + 1] = make_float4(v[1].normal[0], v[1].normal[1], v[1].normal[2], v[0].uv[1]);
+        tri_attr[4 * (size_t)i + 2] = make_float4(v[2].normal[0], v[2].normal[1], v[2].normal[2], v[1].uv[0]);
+        tri_attr[4 * (size_t)i + 3] = make_float4(v[1].uv[1], v[2].uv[0], v[2].uv[1], 0.0f);
+    }
+    for (uint32_t j = 0; j < ns; ++j) {
+        sph[j] = make_float4(s->spheres[j].center[0], s->spheres[j].center[1], s->spheres[j].center[2], s->spheres[j].radius);
+        sph_obj[j] = s->spheres[j].object_index;
+    }
+    for (uint32_t k = 0; k < nm; ++k) {
+        const b200rt_material& m = s->materials[k];
+        DMaterial& o = mats[k];
+        std::memset(&o, 0, sizeof o);
+        std::memcpy(o.normal, m.normal, 12);
+        std::memcpy(o.diffuse, m.diffuse_color, 12);
+        o.shiness = m.shiness;
+        std::memcpy(o.specular, m.specular_color, 12);
+        o.smoothness = m.smoothness;
+        o.transparency = m.transparency;
+        o.refraction_index = m.refraction_index;
+        o.opaque_decay = m.opaque_decay;
+        o.kind = m.kind; o.diffuse_fn = m.diffuse_fn; o.normal_fn = m.normal_fn;
+        std::memcpy(o.fn_params, m.fn_params, sizeof o.fn_params);
+    }
+    for (uint32_t k = 0; k < nl; ++k) {
+        const b200rt_light& l = s->lights[k];
+        DLight& o = lights[k];
+        std::memset(&o, 0, sizeof o);
+        o.kind = l.kind; o.has_origin = l.has_origin;
+        std::memcpy(o.origin, l.origin, 12);
+        std::memcpy(o.direction, l.direction, 12);
+        o.angle = l.angle; o.softness = l.softness;
+        std::memcpy(o.color, l.color, 12);
+    }
+
+    // ---- one device blob, 256-byte aligned sections --------------------------------------------------
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    const size_t off_exact = off;  off = align(off + tri_exact.size() * sizeof(float4));
+    const size_t off_attr = off;   off = align(off + tri_attr.size() * sizeof(float4));
+    const size_t off_sph = off;    off = align(off + sph.size() * sizeof(float4));
+    const size_t off_sobj = off;   off = align(off + sph_obj.size() * sizeof(uint32_t));
+    const size_t off_mat = off;    off = align(off + mats.size() * sizeof(DMaterial));
+    const size_t off_light = off;  off = align(off + lights.size() * sizeof(DLight));
+    const size_t total = off;
+    std::vector<unsigned char> blob(total, 0);
+    std::memcpy(blob.data() + off_exact, tri_exact.data(), tri_exact.size() * sizeof(float4));
+    std::memcpy(blob.data() + off_attr, tri_attr.data(), tri_attr.size() * sizeof(float4));
+    std::memcpy(blob.data() + off_sph, sph.data(), sph.size() * sizeof(float4));
+    std::memcpy(blob.data() + off_sobj, sph_obj.data(), sph_obj.size() * sizeof(uint32_t));
+    std::memcpy(blob.data() + off_mat, mats.data(), mats.size() * sizeof(DMaterial));
+    std::memcpy(blob.data() + off_light, lights.data(), lights.size() * sizeof(DLight));
+
+    ctx->have_scene = false;
+    int rc = ensure(ctx, &ctx->d_scene_blob, &ctx->scene_blob_bytes, total);
+    if (rc != B200RT_OK) return rc;
+    CU(cudaMemcpyAsync(ctx->d_scene_blob, blob.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    unsigned char* base = static_cast<unsigned char*>(ctx->d_scene_blob);
+    DScene& d = ctx->scene;
+    d.tri_filter = nullptr;
+    d.tri_exact = reinterpret_cast<const float4*>(base + off_exact);
+    d.tri_attr = reinterpret_cast<const float4*>(base + off_attr);
+    d.sph = reinterpret_cast<const float4*>(base + off_sph);
+    d.sph_obj = reinterpret_cast<const uint32_t*>(base + off_sobj);
+    d.materials = reinterpret_cast<const DMaterial*>(base + off_mat);
+    d.lights = reinterpret_cast<const DLight*>(base + off_light);
+    d.n_tris = nt; d.n_sph = ns; d.n_lights = nl; d.n_materials = nm;
+    d.n_tris_padded = nt_pad;
+    d.origin_bound = 0.0f;
+    ctx->have_scene = true;
+    return B200RT_OK;
+}
+
+int b200rt_render_whitted_device(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
+                                 float* d_out_rgb, int32_t* d_out_prim_id, void* cuda_stream) {
+    if (!ctx || !cam || !params || !d_out_rgb) return B200RT_ERR_INVALID;
+    if (!ctx->have_scene) return B200RT_ERR_NO_SCENE;
+    DCamera dc;
+    DParams dp;
+    make_camera(*cam, dc);
+    int rc = make_params(*params, 0, 1, dp);
+    if (rc != B200RT_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CU(cudaEventRecord(ctx->ev0, st));
+    CU(launch_whitted(ctx->scene, dc, dp, d_out_rgb, d_out_prim_id, ctx->d_cnt, st));
+    CU(cudaEventRecord(ctx->ev1, st));
+    return B200RT_OK;
+}
+
+int b200rt_render_whitted(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params, float* out_rgb,
+                          int32_t* out_prim_id) {
+    if (!ctx || !cam || !params || !out_rgb) return B200RT_ERR_INVALID;
+    if (!ctx->have_scene) return B200RT_ERR_NO_SCENE;
+    CU(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)params->width * params->height;
+    int rc = ensure(ctx, &ctx->d_out, &ctx->d_out_bytes, npx * 3 * sizeof(float));
+    if (rc != B200RT_OK) return rc;
+    if (out_prim_id) {
+        rc = ensure(ctx, &ctx->d_aux, &ctx->d_aux_bytes, npx * sizeof(int32_t));
+        if (rc != B200RT_OK) return rc;
+    }
+    rc = b200rt_render_whitted_device(ctx, cam, params, (float*)ctx->d_out, out_prim_id ? (int32_t*)ctx->d_aux : nullptr,
+                                      ctx->stream);
+    if (rc != B200RT_OK) return rc;
+    // only the rendered rows are defined; copy exactly those
+    const uint32_t r0 = params->row_count ? params->row_begin : 0u;
+    const uint32_t rn = params->row_count ? params->row_count : params->height;
+    const size_t o = (size_t)r0 * params->width, cnt = (size_t)rn * params->width;
+    CU(cudaEventRecord(ctx->ev2, ctx->stream));
+    CU(cudaMemcpyAsync(out_rgb + 3 * o, (float*)ctx->d_out + 3 * o, cnt * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_prim_id)
+        CU(cudaMemcpyAsync(out_prim_id + o, (int32_t*)ctx->d_aux + o, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev3, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev0, ctx->ev1);
+    cudaEventElapsedTime(&ctx->stats.d2h_ms, ctx->ev2, ctx->ev3);
+    ctx->stats.h2d_ms = 0.0f;
+    return B200RT_OK;
+}
+
+int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
+                                     uint32_t epoch_begin, uint32_t epoch_count, float* d_accum, void* cuda_stream) {
+    if (!ctx || !cam || !params || !d_accum) return B200RT_ERR_INVALID;
+    if (!ctx->have_scene) return B200RT_ERR_NO_SCENE;
+    if (((uintptr_t)d_accum & 15u) != 0) return B200RT_ERR_INVALID;  // float4 accumulators
+    DCamera dc;
+    DParams dp;
+    make_camera(*cam, dc);
+    int rc = make_params(*params, epoch_begin, epoch_count, dp);
+    if (rc != B200RT_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CU(cudaEventRecord(ctx->ev0, st));
+    if (epoch_count) CU(launch_distributed(ctx->scene, dc, dp, d_accum, ctx->d_cnt, st));
+    CU(cudaEventRecord(ctx->ev1, st));
+    return B200RT_OK;
+}
+
+int b200rt_render_distributed(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
+                              uint32_t epoch_begin, uint32_t epoch_count, float* accum) {
+    if (!ctx || !cam || !params || !accum) return B200RT_ERR_INVALID;
+    if (!ctx->have_scene) return B200RT_ERR_NO_SCENE;
+    CU(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)params->width * params->height;
+    int rc = ensure(ctx, &ctx->d_out, &ctx->d_out_bytes, npx * 4 * sizeof(float));
+    if (rc != B200RT_OK) return rc;
+    const uint32_t r0 = params->row_count ? params->row_begin : 0u;
+    const uint32_t rn = params->row_count ? params->row_count : params->height;
+    if (params->row_count && (r0 >= params->height || r0 + rn > params->height)) return B200RT_ERR_INVALID;
+    const size_t o = (size_t)r0 * params->width, cnt = (size_t)rn * params->width;
+    // the accumulation buffer is ADDED to: it travels to the device and back
+    CU(cudaEventRecord(ctx->ev2, ctx->stream));
+    CU(cudaMemcpyAsync((float*)ctx->d_out + 4 * o, accum + 4 * o, cnt * 4 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev3, ctx->stream));
+    rc = b200rt_render_distributed_device(ctx, cam, params, epoch_begin, epoch_count, (float*)ctx->d_out, ctx->stream);
+    if (rc != B200RT_OK) return rc;
+    CU(cudaMemcpyAsync(accum + 4 * o, (float*)ctx->d_out + 4 * o, cnt * 4 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev0, ctx->ev1);
+    cudaEventElapsedTime(&ctx->stats.h2d_ms, ctx->ev2, ctx->ev3);
+    return B200RT_OK;
+}
+
+int b200rt_resolve_device(b200rt_ctx* ctx, const float* d_accum, float* d_out_rgb, size_t n_pixels, void* cuda_stream) {
+    if (!ctx || !d_accum || !d_out_rgb) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CU(launch_resolve(d_accum, d_out_rgb, n_pixels, st));
+    return B200RT_OK;
+}
+
+int b200rt_intersect_device(b200rt_ctx* ctx, const b200rt_ray* d_rays, size_t n, uint32_t cast_mode, b200rt_hit* d_hits,
+                            void* cuda_stream) {
+    if (!ctx || (n && (!d_rays || !d_hits))) return B200RT_ERR_INVALID;
+    if (!ctx->have_scene) return B200RT_ERR_NO_SCENE;
+    if (cast_mode > B200RT_CAST_BRUTE_EXACT) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CU(cudaEventRecord(ctx->ev0, st));
+    CU(launch_intersect(ctx->scene, d_rays, n, cast_mode, d_hits, ctx->d_cnt, st));
+    CU(cudaEventRecord(ctx->ev1, st));
+    return B200RT_OK;
+}
+
+int b200rt_intersect(b200rt_ctx* ctx, const b200rt_ray* rays, size_t n, uint32_t cast_mode, b200rt_hit* hits) {
+    if (!ctx || (n && (!rays || !hits))) return B200RT_ERR_INVALID;
+    if (!ctx->have_scene) return B200RT_ERR_NO_SCENE;
+    if (n == 0) return B200RT_OK;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, &ctx->d_aux, &ctx->d_aux_bytes, n * sizeof(b200rt_ray));
+    if (rc != B200RT_OK) return rc;
+    rc = ensure(ctx, &ctx->d_out, &ctx->d_out_bytes, n * sizeof(b200rt_hit));
+    if (rc != B200RT_OK) return rc;
+    CU(cudaMemcpyAsync(ctx->d_aux, rays, n * sizeof(b200rt_ray), cudaMemcpyHostToDevice, ctx->stream));
+    rc = b200rt_intersect_device(ctx, (const b200rt_ray*)ctx->d_aux, n, cast_mode, (b200rt_hit*)ctx->d_out, ctx->stream);
+    if (rc != B200RT_OK) return rc;
+    CU(cudaMemcpyAsync(hits, ctx->d_out, n * sizeof(b200rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev0, ctx->ev1);
+    return B200RT_OK;
+}
+
+int b200rt_get_stats(b200rt_ctx* ctx, b200rt_stats* out) {
+    if (!ctx || !out) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = fetch_counters(ctx);
+    if (rc != B200RT_OK) return rc;
+    // kernel_ms of a *_device call: the events were recorded on the caller's stream
+    if (cudaEventQuery(ctx->ev1) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev0, ctx->ev1);
+    *out = ctx->stats;
+    return B200RT_OK;
+}
+
+int b200rt_reset_stats(b200rt_ctx* ctx) {
+    if (!ctx) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(DCounters), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    return B200RT_OK;
+}
+
+int b200rt_measure_fp32_peak(b200rt_ctx* ctx, double* tflops, double* sm_mhz_effective) {
+    if (!ctx || !tflops) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const int threads = 256, blocks = ctx->sm_count * 8, iters = 4096;
+    int rc = ensure(ctx, &ctx->d_aux, &ctx->d_aux_bytes, (size_t)blocks * threads * sizeof(float));
+    if (rc != B200RT_OK) return rc;
+    for (int w = 0; w < 2; ++w) CU(launch_fp32_peak((float*)ctx->d_aux, blocks, threads, iters, ctx->stream));
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        CU(launch_fp32_peak((float*)ctx->d_aux, blocks, threads, iters, ctx->stream));
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        best = std::min(best, ms);
+    }
+    const double fmas = (double)blocks * threads * (double)iters * 64.0;
+    *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
+    if (sm_mhz_effective) *sm_mhz_effective = (fmas / (best * 1e-3)) / ((double)ctx->sm_count * 128.0) / 1e6;
+    return B200RT_OK;
+}
+
+}  // extern "C"

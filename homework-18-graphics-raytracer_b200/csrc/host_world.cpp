@@ -1,0 +1,405 @@
+// host_world.cpp — host-side scene construction behind the C ABI (no CUDA in this file).
+//
+// Mirrors the reference's builder surface:
+//   World::new / push_object / push_light                       main.rs:161-178
+//   ObjectProxy::push_triangle / push_sphere / push_triangles   main.rs:705-728
+//   triangle() / square()  (flat normals)                       main.rs:730-746
+//   load_obj()  (tobj: first model, fan triangulation)          main.rs:778-807
+//   the scene literal and camera of main()                      main.rs:810-1083
+// Built with -ffp-contract=off: every float here rounds exactly like the Rust code.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b200rt.h"
+#include "hvec.h"
+
+using namespace b200rt_host;
+
+struct b200rt_world {
+    std::vector<b200rt_material> materials;  // World.objects (Object = {material}), primitives.rs:8-10
+    std::vector<b200rt_triangle> triangles;  // World.triangles, global push order
+    std::vector<b200rt_sphere> spheres;      // World.spheres
+    std::vector<b200rt_light> lights;        // World.lights
+};
+
+extern "C" {
+
+b200rt_world* b200rt_world_new(void) { return new b200rt_world(); }
+void b200rt_world_free(b200rt_world* w) { delete w; }
+
+int b200rt_world_push_object(b200rt_world* w, const b200rt_material* material) {
+    if (!w || !material) return B200RT_ERR_INVALID;
+    w->materials.push_back(*material);
+    return (int)w->materials.size() - 1;  // ObjectIndex(self.objects.len() - 1), main.rs:169
+}
+
+int b200rt_world_push_triangle(b200rt_world* w, uint32_t object_index, const b200rt_vertex v[3]) {
+    if (!w || !v || object_index >= w->materials.size()) return B200RT_ERR_INVALID;
+    b200rt_triangle t;
+    t.vertices[0] = v[0];
+    t.vertices[1] = v[1];
+    t.vertices[2] = v[2];
+    t.object_index = object_index;
+    w->triangles.push_back(t);
+    return B200RT_OK;
+}
+
+int b200rt_world_push_flat_triangle(b200rt_world* w, uint32_t object_index, const float pos[3][3],
+                                    const float uv[3][2]) {
+    if (!w || !pos || !uv) return B200RT_ERR_INVALID;
+    // main.rs:731-733
+    V3 a = v3(pos[1]) - v3(pos[0]);
+    V3 b = v3(pos[2]) - v3(pos[1]);
+    V3 normal = normalize(cross(a, b));
+    b200rt_vertex v[3];
+    for (int i = 0; i < 3; ++i) {
+        std::memcpy(v[i].position, pos[i], sizeof(float) * 3);
+        store(v[i].normal, normal);
+        v[i].uv[0] = uv[i][0];
+        v[i].uv[1] = uv[i][1];
+    }
+    return b200rt_world_push_triangle(w, object_index, v);
+}
+
+int b200rt_world_push_square(b200rt_world* w, uint32_t object_index, const float pos[4][3],
+                             const float uv[4][2]) {
+    if (!w || !pos || !uv) return B200RT_ERR_INVALID;
+    // main.rs:743-744: (0,1,2) then (0,2,3)
+    static const int idx[2][3] = {{0, 1, 2}, {0, 2, 3}};
+    for (int t = 0; t < 2; ++t) {
+        float p[3][3], q[3][2];
+        for (int i = 0; i < 3; ++i) {
+            std::memcpy(p[i], pos[idx[t][i]], sizeof(float) * 3);
+            std::memcpy(q[i], uv[idx[t][i]], sizeof(float) * 2);
+        }
+        int rc = b200rt_world_push_flat_triangle(w, object_index, p, q);
+        if (rc != B200RT_OK) return rc;
+    }
+    return B200RT_OK;
+}
+
+int b200rt_world_push_sphere(b200rt_world* w, uint32_t object_index, const float center[3], float radius) {
+    if (!w || !center || object_index >= w->materials.size()) return B200RT_ERR_INVALID;
+    b200rt_sphere s;
+    std::memcpy(s.center, center, sizeof(float) * 3);
+    s.radius = radius;
+    s.object_index = object_index;
+    w->spheres.push_back(s);
+    return B200RT_OK;
+}
+
+int b200rt_world_push_light(b200rt_world* w, const b200rt_light* light) {
+    if (!w || !light) return B200RT_ERR_INVALID;
+    w->lights.push_back(*light);
+    return B200RT_OK;
+}
+
+int b200rt_world_scene(const b200rt_world* w, b200rt_scene* out) {
+    if (!w || !out) return B200RT_ERR_INVALID;
+    out->triangles = w->triangles.data();
+    out->n_triangles = (uint32_t)w->triangles.size();
+    out->spheres = w->spheres.data();
+    out->n_spheres = (uint32_t)w->spheres.size();
+    out->materials = w->materials.data();
+    out->n_materials = (uint32_t)w->materials.size();
+    out->lights = w->lights.data();
+    out->n_lights = (uint32_t)w->lights.size();
+    return B200RT_OK;
+}
+
+}  // extern "C"
+
+// ---- OBJ import -------------------------------------------------------------------------------
+// What tobj 0.1.6 does for the reference's call (main.rs:784-790): positions are one global pool,
+// a model ends when an `o`/`g` statement follows faces, only models[0] is used, faces of any arity
+// are fan-triangulated, `a`, `a/b`, `a//c`, `a/b/c` and negative (relative) indices are accepted.
+namespace {
+
+struct ObjMesh {
+    std::vector<float> positions;           // xyz...
+    std::vector<unsigned> indices;          // triangulated, 0-based, first model only
+};
+
+bool parse_obj(FILE* f, ObjMesh& mesh) {
+    char line[4096];
+    bool first_model_closed = false;
+    bool have_faces = false;
+    while (std::fgets(line, sizeof line, f)) {
+        char* p = line;
+        while (*p == ' ' || *p == '\t') ++p;
+        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) {
+            char* q = p + 1;
+            for (int k = 0; k < 3; ++k) {
+                char* end = nullptr;
+                float val = std::strtof(q, &end);  // correctly rounded, like Rust's str::parse::<f32>
+                if (end == q) return false;
+                mesh.positions.push_back(val);
+                q = end;
+            }
+        } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
+            if (first_model_closed) continue;
+            std::vector<long> corner;
+            char* q = p + 1;
+            for (;;) {
+                while (*q == ' ' || *q == '\t') ++q;
+                if (*q == '\0' || *q == '\n' || *q == '\r' || *q == '#') break;
+                char* end = nullptr;
+                long vi = std::strtol(q, &end, 10);
+                if (end == q) return false;
+                corner.push_back(vi);
+                q = end;
+                while (*q != '\0' && *q != ' ' && *q != '\t' && *q != '\n' && *q != '\r') ++q;  // skip /vt/vn
+            }
+            if (corner.size() < 3) return false;
+            const long nv = (long)(mesh.positions.size() / 3);
+            for (long& c : corner) {
+                c = c < 0 ? nv + c : c - 1;
+                if (c < 0 || c >= nv) return false;
+            }
+            for (size_t i = 1; i + 1 < corner.size(); ++i) {
+                mesh.indices.push_back((unsigned)corner[0]);
+                mesh.indices.push_back((unsigned)corner[i]);
+                mesh.indices.push_back((unsigned)corner[i + 1]);
+            }
+            have_faces = true;
+        } else if ((p[0] == 'g' || p[0] == 'o') && (p[1] == ' ' || p[1] == '\t' || p[1] == '\n' || p[1] == '\r')) {
+            if (have_faces) first_model_closed = true;
+        }
+    }
+    return have_faces;
+}
+
+// Built-in copy of the reference mesh as data: 20 unit vertices of a regular dodecahedron and its
+// 12 pentagons as 36 triangles, in the order dodecahedron.obj lists them (1-based there).
+const float kDodecaV[20][3] = {
+    {-0.57735f, -0.57735f, 0.57735f}, {0.934172f, 0.356822f, 0.0f},    {0.934172f, -0.356822f, 0.0f},
+    {-0.934172f, 0.356822f, 0.0f},    {-0.934172f, -0.356822f, 0.0f},  {0.0f, 0.934172f, 0.356822f},
+    {0.0f, 0.934172f, -0.356822f},    {0.356822f, 0.0f, -0.934172f},   {-0.356822f, 0.0f, -0.934172f},
+    {0.0f, -0.934172f, -0.356822f},   {0.0f, -0.934172f, 0.356822f},   {0.356822f, 0.0f, 0.934172f},
+    {-0.356822f, 0.0f, 0.934172f},    {0.57735f, 0.57735f, -0.57735f}, {0.57735f, 0.57735f, 0.57735f},
+    {-0.57735f, 0.57735f, -0.57735f}, {-0.57735f, 0.57735f, 0.57735f}, {0.57735f, -0.57735f, -0.57735f},
+    {0.57735f, -0.57735f, 0.57735f},  {-0.57735f, -0.57735f, -0.57735f}};
+const unsigned char kDodecaF[36][3] = {
+    {19, 3, 2},  {12, 19, 2}, {15, 12, 2}, {8, 14, 2},  {18, 8, 2},  {3, 18, 2},  {20, 5, 4},  {9, 20, 4},
+    {16, 9, 4},  {13, 17, 4}, {1, 13, 4},  {5, 1, 4},   {7, 16, 4},  {6, 7, 4},   {17, 6, 4},  {6, 15, 2},
+    {7, 6, 2},   {14, 7, 2},  {10, 18, 3}, {11, 10, 3}, {19, 11, 3}, {11, 1, 5},  {10, 11, 5}, {20, 10, 5},
+    {20, 9, 8},  {10, 20, 8}, {18, 10, 8}, {9, 16, 7},  {8, 9, 7},   {14, 8, 7},  {12, 15, 6}, {13, 12, 6},
+    {17, 13, 6}, {13, 1, 11}, {12, 13, 11}, {19, 12, 11}};
+
+int push_mesh(b200rt_world* w, uint32_t object_index, const ObjMesh& mesh, float scale_div, const float offset[3]) {
+    const float zero_uv[3][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}, {0.0f, 0.0f}};  // main.rs:797-799
+    const V3 off = v3(offset);
+    int n = 0;
+    for (size_t f = 0; f + 2 < mesh.indices.size(); f += 3) {
+        float pos[3][3];
+        for (int k = 0; k < 3; ++k) {
+            const float* src = &mesh.positions[3 * (size_t)mesh.indices[f + k]];
+            // main.rs:802: p.position / 3.0 + Vector3::new(0.7, 1.0, -0.5)
+            V3 p = v3(src) / scale_div + off;
+            store(pos[k], p);
+        }
+        int rc = b200rt_world_push_flat_triangle(w, object_index, pos, zero_uv);
+        if (rc != B200RT_OK) return rc;
+        ++n;
+    }
+    return n;
+}
+
+b200rt_material color_material(float dr, float dg, float db, float shiness, float sr, float sg, float sb,
+                               float smoothness, float refraction_index, float opaque_decay, float transparency) {
+    b200rt_material m;
+    std::memset(&m, 0, sizeof m);
+    m.kind = B200RT_MATERIAL_COLOR;
+    m.normal[0] = 0.0f; m.normal[1] = 0.0f; m.normal[2] = 1.0f;
+    m.diffuse_color[0] = dr; m.diffuse_color[1] = dg; m.diffuse_color[2] = db;
+    m.shiness = shiness;
+    m.specular_color[0] = sr; m.specular_color[1] = sg; m.specular_color[2] = sb;
+    m.smoothness = smoothness;
+    m.refraction_index = refraction_index;
+    m.opaque_decay = opaque_decay;
+    m.transparency = transparency;
+    m.diffuse_fn = B200RT_DIFFUSE_CONST;
+    m.normal_fn = B200RT_NORMAL_CONST;
+    return m;
+}
+
+struct Quad {
+    float pos[4][3];
+    float uv[4][2];
+};
+
+}  // namespace
+
+extern "C" {
+
+int b200rt_world_load_obj(b200rt_world* w, uint32_t object_index, const char* path, float scale_div,
+                          const float offset[3]) {
+    if (!w || !path || !offset || object_index >= w->materials.size()) return B200RT_ERR_INVALID;
+    FILE* f = std::fopen(path, "r");
+    if (!f) return B200RT_ERR_IO;
+    ObjMesh mesh;
+    bool ok = parse_obj(f, mesh);
+    std::fclose(f);
+    if (!ok) return B200RT_ERR_IO;
+    return push_mesh(w, object_index, mesh, scale_div, offset);
+}
+
+void b200rt_fixture_camera(b200rt_camera* cam) {
+    if (!cam) return;
+    // main.rs:1077-1083; Deg -> Rad is deg * (PI/180 computed in f64, cast to f32) in cgmath 0.16
+    cam->fovy = 60.0f * (float)(3.14159265358979323846 / 180.0);
+    cam->center[0] = 2.0f; cam->center[1] = 2.5f; cam->center[2] = 2.0f;
+    store(cam->toward, normalize(v3(-1.0f, -1.0f, -1.0f)));
+    store(cam->up, normalize(v3(0.0f, 1.0f, 0.0f)));
+    cam->near = -0.1f;
+}
+
+void b200rt_default_params(b200rt_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->width = 1280;               // main.rs:1084
+    p->height = 960;               // main.rs:1085
+    p->depth = 5;                  // main.rs:1098
+    p->threshold = 0.001f;         // main.rs:467
+    p->refract_max_distance = 100.0f;  // main.rs:505
+    p->tir_retries = 10;           // main.rs:378
+    p->focus = 3.0f;               // main.rs:1147
+    p->blur = 0.04f;               // main.rs:1148
+    p->seed = 0;
+    p->cast_mode = B200RT_CAST_TWO_PHASE;
+}
+
+int b200rt_world_fixture(b200rt_world* w, const char* obj_path) {
+    if (!w) return B200RT_ERR_INVALID;
+    const float obj_offset[3] = {0.7f, 1.0f, -0.5f};
+    int rc;
+
+    // object 0: dodecahedron, main.rs:812-825
+    b200rt_material m0 = color_material(1.0f, 1.0f, 1.0f, 0.1f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 0.0f, 0.0f);
+    int o0 = b200rt_world_push_object(w, &m0);
+    if (obj_path) {
+        rc = b200rt_world_load_obj(w, (uint32_t)o0, obj_path, 3.0f, obj_offset);
+    } else {
+        ObjMesh mesh;
+        for (int i = 0; i < 20; ++i)
+            for (int k = 0; k < 3; ++k) mesh.positions.push_back(kDodecaV[i][k]);
+        for (int f = 0; f < 36; ++f)
+            for (int k = 0; k < 3; ++k) mesh.indices.push_back((unsigned)kDodecaF[f][k] - 1u);
+        rc = push_mesh(w, (uint32_t)o0, mesh, 3.0f, obj_offset);
+    }
+    if (rc < 0) return rc;
+
+    // object 1: floor, main.rs:826-844 (uv of corner 3 really is (0,1) again in the reference)
+    b200rt_material m1 = color_material(1.0f, 0.8f, 0.6f, 0.5f, 1.0f, 1.0f, 1.0f, 0.01f, 1.0f, 0.0f, 0.0f);
+    int o1 = b200rt_world_push_object(w, &m1);
+    const Quad floor_q = {{{-2.0f, 0.0f, -2.0f}, {-2.0f, 0.0f, 2.0f}, {2.0f, 0.0f, 2.0f}, {2.0f, 0.0f, -2.0f}},
+                          {{0.0f, 0.0f}, {0.0f, 1.0f}, {1.0f, 0.0f}, {0.0f, 1.0f}}};
+    if ((rc = b200rt_world_push_square(w, (uint32_t)o1, floor_q.pos, floor_q.uv)) < 0) return rc;
+
+    // object 2: striped, bump-mapped wall, main.rs:845-877
+    b200rt_material m2 = color_material(0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 1.0f, 1.0f, 0.00001f, 1.0f, 0.0f, 0.0f);
+    m2.kind = B200RT_MATERIAL_GENERATIVE;
+    m2.diffuse_fn = B200RT_DIFFUSE_STRIPE_V;
+    m2.normal_fn = B200RT_NORMAL_SINCOS_U;
+    m2.fn_params[0] = 20.0f;
+    m2.fn_params[1] = 1.0f; m2.fn_params[2] = 1.0f; m2.fn_params[3] = 1.0f;
+    m2.fn_params[4] = 0.5f; m2.fn_params[5] = 0.5f; m2.fn_params[6] = 1.0f;
+    m2.fn_params[7] = 10.0f;
+    int o2 = b200rt_world_push_object(w, &m2);
+    const Quad wall_q = {{{-2.0f, 2.0f, -2.0f}, {-2.0f, 2.0f, 2.0f}, {-2.0f, -2.0f, 2.0f}, {-2.0f, -2.0f, -2.0f}},
+                         {{0.0f, 0.0f}, {0.0f, 1.0f}, {1.0f, 0.0f}, {1.0f, 1.0f}}};
+    if ((rc = b200rt_world_push_square(w, (uint32_t)o2, wall_q.pos, wall_q.uv)) < 0) return rc;
+
+    // objects 3 and 4: two glass slabs, main.rs:879-977.  Same six-quad box pattern:
+    //   front z=z1, back z=z0, top y=1.5, bottom y=1.0, left x=-hx, right x=+hx.
+    const float uvA[4][2] = {{0.0f, 0.0f}, {0.0f, 1.0f}, {1.0f, 0.0f}, {0.0f, 1.0f}};  // first quad of each slab
+    const float uvB[4][2] = {{0.0f, 1.0f}, {1.0f, 0.0f}, {0.0f, 1.0f}, {0.0f, 0.0f}};  // the other five
+    const float slab[2][3] = {{0.5f, 0.6f, 0.7f}, {0.3f, 0.71f, 0.81f}};               // hx, z0, z1
+    for (int s = 0; s < 2; ++s) {
+        b200rt_material mg = color_material(1.0f, 0.8f, 0.6f, 1.0f, 1.0f, 1.0f, 1.0f, 0.00001f, 1.6f, 0.1f, 1.0f);
+        int og = b200rt_world_push_object(w, &mg);
+        const float hx = slab[s][0], z0 = slab[s][1], z1 = slab[s][2];
+        const float y0 = 1.0f, y1 = 1.5f;
+        const float q0[4][3] = {{hx, y1, z1}, {-hx, y1, z1}, {-hx, y0, z1}, {hx, y0, z1}};     // main.rs:892-897 / 942-947
+        const float q1[4][3] = {{hx, y0, z0}, {-hx, y0, z0}, {-hx, y1, z0}, {hx, y1, z0}};     // main.rs:898-903 / 948-953
+        const float q2[4][3] = {{hx, y1, z0}, {-hx, y1, z0}, {-hx, y1, z1}, {hx, y1, z1}};     // main.rs:904-909 / 954-959
+        const float q3a[4][3] = {{hx, y0, z1}, {-hx, y0, z1}, {-hx, y0, z0}, {hx, y0, z0}};    // bottom
+        const float q4[4][3] = {{-hx, y1, z0}, {-hx, y0, z0}, {-hx, y0, z1}, {-hx, y1, z1}};   // left
+        const float q5[4][3] = {{hx, y0, z0}, {hx, y1, z0}, {hx, y1, z1}, {hx, y0, z1}};       // right
+        if ((rc = b200rt_world_push_square(w, (uint32_t)og, q0, uvA)) < 0) return rc;
+        if ((rc = b200rt_world_push_square(w, (uint32_t)og, q1, uvB)) < 0) return rc;
+        if ((rc = b200rt_world_push_square(w, (uint32_t)og, q2, uvB)) < 0) return rc;
+        if (s == 0) {
+            // slab 1 order: bottom (910-915), left (916-921), right (922-927)
+            if ((rc = b200rt_world_push_square(w, (uint32_t)og, q3a, uvB)) < 0) return rc;
+            if ((rc = b200rt_world_push_square(w, (uint32_t)og, q4, uvB)) < 0) return rc;
+        } else {
+            // slab 2 order: left (960-965), bottom (966-971), right (972-977)
+            if ((rc = b200rt_world_push_square(w, (uint32_t)og, q4, uvB)) < 0) return rc;
+            if ((rc = b200rt_world_push_square(w, (uint32_t)og, q3a, uvB)) < 0) return rc;
+        }
+        if ((rc = b200rt_world_push_square(w, (uint32_t)og, q5, uvB)) < 0) return rc;
+    }
+
+    // four spheres, main.rs:979-1056
+    const float inv_sqrt3 = 0.5f / std::sqrt(3.0f);
+    b200rt_material m5 = color_material(1.0f, 0.2f, 0.2f, 0.2f, 1.0f, 1.0f, 0.0f, 0.2f, 1.0f, 0.0f, 0.0f);
+    int o5 = b200rt_world_push_object(w, &m5);
+    const float c5[3] = {-0.5f, 0.5f, inv_sqrt3};
+    if ((rc = b200rt_world_push_sphere(w, (uint32_t)o5, c5, 0.5f)) < 0) return rc;
+
+    b200rt_material m6 = color_material(1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 0.001f, 1.12f, 0.3f, 0.96f);
+    int o6 = b200rt_world_push_object(w, &m6);
+    const float c6[3] = {0.5f, 0.5f, inv_sqrt3};
+    if ((rc = b200rt_world_push_sphere(w, (uint32_t)o6, c6, 0.5f)) < 0) return rc;
+
+    b200rt_material m7 = color_material(0.0f, 0.0f, 0.0f, 0.3f, 0.0f, 0.0f, 1.0f, 0.7f, 1.0f, 0.0f, 0.0f);
+    m7.kind = B200RT_MATERIAL_GENERATIVE;
+    m7.diffuse_fn = B200RT_DIFFUSE_CHECKER_UPV;
+    m7.normal_fn = B200RT_NORMAL_CONST;
+    m7.fn_params[0] = 10.0f;
+    m7.fn_params[1] = 1.0f; m7.fn_params[2] = 0.1f; m7.fn_params[3] = 0.1f;
+    m7.fn_params[4] = 0.1f; m7.fn_params[5] = 0.1f; m7.fn_params[6] = 1.0f;
+    int o7 = b200rt_world_push_object(w, &m7);
+    const float c7[3] = {0.0f, 0.5f, -1.0f / std::sqrt(3.0f)};
+    if ((rc = b200rt_world_push_sphere(w, (uint32_t)o7, c7, 0.5f)) < 0) return rc;
+
+    b200rt_material m8 = color_material(0.5f, 1.0f, 0.2f, 0.5f, 1.0f, 1.0f, 1.0f, 0.01f, 1.0f, 0.0f, 0.0f);
+    int o8 = b200rt_world_push_object(w, &m8);
+    const float c8[3] = {0.0f, 0.5f + std::sqrt(2.0f / 3.0f), 0.0f};
+    if ((rc = b200rt_world_push_sphere(w, (uint32_t)o8, c8, 0.5f)) < 0) return rc;
+
+    // three lights, main.rs:1058-1075
+    b200rt_light l0;
+    std::memset(&l0, 0, sizeof l0);
+    l0.kind = B200RT_LIGHT_DIRECTIONAL;
+    l0.has_origin = 0;
+    store(l0.direction, normalize(v3(-1.0f, -1.0f, 0.0f)));
+    l0.color[0] = 1.0f; l0.color[1] = 0.98f; l0.color[2] = 0.95f;
+    b200rt_world_push_light(w, &l0);
+
+    b200rt_light l1;
+    std::memset(&l1, 0, sizeof l1);
+    l1.kind = B200RT_LIGHT_SPOT;
+    l1.has_origin = 1;
+    l1.origin[0] = 0.0f; l1.origin[1] = 10.0f; l1.origin[2] = 0.0f;
+    store(l1.direction, normalize(v3(0.0f, -1.0f, -0.0f)));
+    l1.angle = 60.0f * (float)(3.14159265358979323846 / 180.0);
+    l1.softness = 1.0f;
+    l1.color[0] = 1.0f * 1.0f; l1.color[1] = 0.5f * 1.0f; l1.color[2] = 0.9f * 1.0f;
+    b200rt_world_push_light(w, &l1);
+
+    b200rt_light l2;
+    std::memset(&l2, 0, sizeof l2);
+    l2.kind = B200RT_LIGHT_POINT;
+    l2.has_origin = 1;
+    l2.origin[0] = 0.0f; l2.origin[1] = 0.1f; l2.origin[2] = 0.0f;
+    l2.color[0] = 0.8f; l2.color[1] = 0.8f; l2.color[2] = 1.0f;
+    b200rt_world_push_light(w, &l2);
+    return B200RT_OK;
+}
+
+}  // extern "C"

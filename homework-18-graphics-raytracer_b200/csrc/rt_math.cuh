@@ -1,0 +1,114 @@
+// rt_math.cuh — device f32 math in the reference's evaluation order.
+//
+// This translation unit is compiled with -fmad=false: nvcc never contracts a*b+c, so every
+// expression below rounds exactly like rustc's (and the oracle's) non-fused IEEE f32 code.
+// Division and sqrt use the default -prec-div=true / -prec-sqrt=true (correctly rounded).
+// The only fused arithmetic in the library is written explicitly with __fmaf_rn in the filter
+// stage of the two-phase cast (rt_cast.cuh), whose results never reach an output.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace b200rt {
+
+struct f3 { float x, y, z; };
+struct f2 { float x, y; };
+
+#define RT_DI __device__ __forceinline__
+
+RT_DI f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+RT_DI f3 mk3(const float* p) { return mk3(p[0], p[1], p[2]); }
+RT_DI f3 mk3(float4 v) { return mk3(v.x, v.y, v.z); }
+RT_DI f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_DI f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_DI f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+RT_DI f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+RT_DI f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+RT_DI f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }  // LinSrgb * LinSrgb
+RT_DI f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+// cgmath 0.16 Vector3::dot = mul_element_wise().sum() = (x + y) + z
+RT_DI float dot(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+RT_DI f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RT_DI float magnitude(f3 a) { return sqrtf(dot(a, a)); }
+RT_DI f3 normalize(f3 a) { return a * (1.0f / magnitude(a)); }  // InnerSpace::normalize_to
+RT_DI float distance(f3 a, f3 b) { return magnitude(b - a); }   // MetricSpace for Point3
+
+constexpr float kF32Epsilon = 1.1920929e-7f;       // std::f32::EPSILON
+constexpr float kPi = 3.14159265358979323846f;     // std::f32::consts::PI
+
+// approx 0.1 ulps_eq! with cgmath's defaults (epsilon = f32::EPSILON, max_ulps = 4)
+RT_DI float signum(float v) { return isnan(v) ? v : (signbit(v) ? -1.0f : 1.0f); }
+RT_DI bool ulps_eq(float a, float b) {
+    if (fabsf(a - b) <= kF32Epsilon) return true;
+    if (signum(a) != signum(b)) return false;
+    long long diff = (long long)__float_as_int(a) - (long long)__float_as_int(b);
+    if (diff < 0) diff = -diff;
+    return diff <= 4;
+}
+
+struct quat { float s; f3 v; };
+// cgmath Quaternion::from_arc(src, dst, None)
+RT_DI quat from_arc(f3 src, f3 dst) {
+    float mag_avg = sqrtf(dot(src, src) * dot(dst, dst));
+    float d = dot(src, dst);
+    quat q;
+    if (ulps_eq(d, mag_avg)) {
+        q.s = 1.0f; q.v = mk3(0.0f, 0.0f, 0.0f);
+    } else if (ulps_eq(d, -mag_avg)) {
+        f3 v = cross(mk3(1.0f, 0.0f, 0.0f), src);
+        if (ulps_eq(v.x, 0.0f) && ulps_eq(v.y, 0.0f) && ulps_eq(v.z, 0.0f)) v = cross(mk3(0.0f, 1.0f, 0.0f), src);
+        f3 axis = normalize(v);
+        // from_axis_angle(axis, pi): sin_cos(pi/2 in f32) = (1.0, -4.371139e-8)
+        q.s = -4.371139e-8f; q.v = axis * 1.0f;
+    } else {
+        float qs = mag_avg + d;
+        f3 qv = cross(src, dst);
+        float inv = 1.0f / sqrtf(qs * qs + dot(qv, qv));
+        q.s = qs * inv; q.v = qv * inv;
+    }
+    return q;
+}
+// cgmath Quaternion * Vector3
+RT_DI f3 rotate(quat q, f3 vec) {
+    f3 tmp = cross(q.v, vec) + (vec * q.s);
+    return (cross(q.v, tmp) * 2.0f) + vec;
+}
+
+// f32::is_normal
+RT_DI bool is_normal_f32(float f) {
+    uint32_t e = (__float_as_uint(f) >> 23) & 0xffu;
+    return e != 0u && e != 0xffu;
+}
+
+// ---- Philox4x32-10 sample stream: counter (x, y, epoch, block), key (seed_lo, seed_hi) ---------
+struct Rng {
+    uint32_t k0, k1, x, y, epoch, draws;
+    uint32_t b[4];
+};
+RT_DI void philox_block(Rng& r, uint32_t block) {
+    uint32_t c0 = r.x, c1 = r.y, c2 = r.epoch, c3 = block;
+    uint32_t k0 = r.k0, k1 = r.k1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    r.b[0] = c0; r.b[1] = c1; r.b[2] = c2; r.b[3] = c3;
+}
+RT_DI void rng_init(Rng& r, uint32_t seed_lo, uint32_t seed_hi, uint32_t y, uint32_t x, uint32_t epoch) {
+    r.k0 = seed_lo; r.k1 = seed_hi; r.x = x; r.y = y; r.epoch = epoch; r.draws = 0;
+}
+RT_DI float rng_uniform(Rng& r) {
+    if ((r.draws & 3u) == 0u) philox_block(r, r.draws >> 2);
+    uint32_t w = r.draws & 3u;
+    uint32_t v = w == 0 ? r.b[0] : (w == 1 ? r.b[1] : (w == 2 ? r.b[2] : r.b[3]));
+    r.draws++;
+    return (float)(v >> 8) * 5.9604644775390625e-8f;
+}
+RT_DI float rng_range(Rng& r, float low, float high) { return low + (high - low) * rng_uniform(r); }
+
+}  // namespace b200rt

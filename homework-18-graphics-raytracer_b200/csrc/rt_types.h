@@ -1,0 +1,96 @@
+// rt_types.h — device-resident scene layout shared by the host packer (b200rt_api.cu) and the
+// kernels (rt_kernels.cu).  All records are 16-byte float4 so every load is a 128-bit LDG/LDS.
+//
+// HBM layout (see DESIGN.md "Data layout"):
+//   tri_filter[4*i + 0..3]  {n.xyz, d}  {m0.xyz, c0}  {m1.xyz, c1}  {m2.xyz, c2}
+//        n = unit face normal, d = n.v0 (both bit-identical to the reference's per-pair values),
+//        m_k = n x e_k, c_k = m_k.v_k - eps_k : edge planes with the conservative slack folded in.
+//        Read by the branch-free FMA filter for EVERY ray x triangle pair (64 B/pair, smem-staged).
+//   tri_exact[4*i + 0..3]   {n.xyz, d}  {v0.xyz, object}  {v1.xyz, 0}  {v2.xyz, 0}
+//        Read only for pairs that survive the filter (exact reference-order confirm).
+//   tri_attr[4*i + 0..3]    {n0.xyz, uv0.x} {n1.xyz, uv0.y} {n2.xyz, uv1.x} {uv1.y, uv2.x, uv2.y, 0}
+//        Read once per cast, for the winning triangle only (normal / uv interpolation).
+//   sph[j]                  {c.xyz, r}     sph_obj[j] = object index
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200rt.h"
+
+namespace b200rt {
+
+struct DMaterial {  // ColorMaterial / GenerativeMaterial, materials.rs:20-31, 70-83
+    float normal[3];
+    float diffuse[3];
+    float shiness;
+    float specular[3];
+    float smoothness;
+    float transparency;
+    float refraction_index;
+    float opaque_decay;
+    uint32_t kind, diffuse_fn, normal_fn;
+    float fn_params[8];
+    float pad;
+};
+
+struct DLight {  // lights.rs:6-30
+    uint32_t kind, has_origin;
+    float origin[3];
+    float direction[3];
+    float angle, softness;
+    float color[3];
+    float pad;
+};
+
+struct DScene {
+    const float4* tri_filter;
+    const float4* tri_exact;
+    const float4* tri_attr;
+    const float4* sph;
+    const uint32_t* sph_obj;
+    const DMaterial* materials;
+    const DLight* lights;
+    uint32_t n_tris, n_sph, n_lights, n_materials;
+    uint32_t n_tris_padded;  // tri_filter is padded to a multiple of kTileTris with never-hit records
+    float origin_bound;      // filter slack was derived for ray origins with |o|_inf <= origin_bound
+};
+
+// Camera::shoot hoisted per frame (main.rs:85-92): computed on the host with the same libm tanf
+// and the same non-fused f32 expression order as the reference.
+struct DCamera {
+    float toward[3];
+    float x[3];       // tan(fovy/2) * right
+    float y[3];       // tan(fovy/2) * up
+    float origin[3];  // center + toward * near
+    float center[3];
+    float near;
+};
+
+struct DParams {
+    uint32_t width, height, row_begin, row_count;
+    int32_t depth;
+    float threshold, refract_max_distance;
+    uint32_t tir_retries;
+    float focus, blur;
+    uint32_t seed_lo, seed_hi;
+    uint32_t cast_mode;
+    uint32_t epoch_begin, epoch_count;
+};
+
+struct DCounters {  // device-side statistics, one 64-bit atomic per CTA at kernel end
+    unsigned long long casts, tri_pairs, sph_pairs, confirms, samples;
+};
+
+constexpr int kTileTris = 64;  // triangles per shared-memory tile (64 x 64 B = 4 KB)
+
+// launchers (rt_kernels.cu)
+cudaError_t launch_whitted(const DScene& sc, const DCamera& cam, const DParams& p, float* d_rgb, int32_t* d_prim,
+                           DCounters* d_cnt, cudaStream_t stream);
+cudaError_t launch_distributed(const DScene& sc, const DCamera& cam, const DParams& p, float* d_accum,
+                               DCounters* d_cnt, cudaStream_t stream);
+cudaError_t launch_intersect(const DScene& sc, const b200rt_ray* d_rays, size_t n, uint32_t cast_mode,
+                             b200rt_hit* d_hits, DCounters* d_cnt, cudaStream_t stream);
+cudaError_t launch_resolve(const float* d_accum, float* d_rgb, size_t n_pixels, cudaStream_t stream);
+cudaError_t launch_fp32_peak(float* d_sink, int blocks, int threads, int iters, cudaStream_t stream);
+
+}  // namespace b200rt
