@@ -116,7 +116,7 @@ EXPORTED_SYMBOLS = [
     "b200rt_create", "b200rt_destroy", "b200rt_strerror", "b200rt_last_cuda_error", "b200rt_device_info",
     "b200rt_upload_scene", "b200rt_render_whitted", "b200rt_render_whitted_device", "b200rt_render_distributed",
     "b200rt_render_distributed_device", "b200rt_resolve_device", "b200rt_intersect", "b200rt_intersect_device",
-    "b200rt_get_stats", "b200rt_reset_stats", "b200rt_measure_fp32_peak", "b200rt_world_new", "b200rt_world_free",
+    "b200rt_get_stats", "b200rt_reset_stats", "b200rt_measure_fp32_peak", "b200rt_filter_bench", "b200rt_pipe_bench", "b200rt_world_new", "b200rt_world_free",
     "b200rt_world_push_object", "b200rt_world_push_triangle", "b200rt_world_push_flat_triangle",
     "b200rt_world_push_square", "b200rt_world_push_sphere", "b200rt_world_push_light", "b200rt_world_load_obj",
     "b200rt_world_scene", "b200rt_world_fixture", "b200rt_fixture_camera", "b200rt_default_params",
@@ -154,6 +154,8 @@ def load_library() -> C.CDLL:
         "b200rt_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "b200rt_reset_stats": (C.c_int, [vp]),
         "b200rt_measure_fp32_peak": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "b200rt_filter_bench": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
+        "b200rt_pipe_bench": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
         "b200rt_world_new": (vp, []),
         "b200rt_world_free": (None, [vp]),
         "b200rt_world_push_object": (C.c_int, [vp, C.POINTER(Material)]),
@@ -446,6 +448,18 @@ class Context:
 
     def reset_stats(self) -> None:
         _check(self._lib.b200rt_reset_stats(self._h), "reset_stats", self)
+
+    def filter_bench(self, variant: int, blocks_per_sm: int = 4, iters: int = 256):
+        """K2 micro-benchmark of the filter loop; returns (kernel_ms, pair_tests)."""
+        ms, pairs = C.c_float(), C.c_uint64()
+        _check(self._lib.b200rt_filter_bench(self._h, variant, blocks_per_sm, iters, C.byref(ms), C.byref(pairs)),
+               "filter_bench", self)
+        return ms.value, pairs.value
+
+    def pipe_bench(self, variant: int):
+        ms, ipc = C.c_float(), C.c_double()
+        _check(self._lib.b200rt_pipe_bench(self._h, variant, C.byref(ms), C.byref(ipc)), "pipe_bench", self)
+        return ms.value, ipc.value
 
     def measure_fp32_peak(self):
         t, mhz = C.c_double(), C.c_double()

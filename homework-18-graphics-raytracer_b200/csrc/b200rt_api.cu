@@ -34,6 +34,13 @@ struct b200rt_ctx {
     void* d_scene_blob = nullptr;
     size_t scene_blob_bytes = 0;
 
+    // host copy of the exact records (for re-deriving the filter records when the origin bound grows)
+    std::vector<float4> h_tri_exact;
+    std::vector<float4> h_sph;
+    float scene_radius = 0.0f;   // max |vertex|, max |centre| + r
+    float max_edge = 0.0f;
+    void* d_filter = nullptr;  size_t d_filter_bytes = 0;
+
     // device scratch for the host-buffer entry points
     void* d_out = nullptr;  size_t d_out_bytes = 0;
     void* d_aux = nullptr;  size_t d_aux_bytes = 0;
@@ -63,6 +70,70 @@ int ensure(b200rt_ctx* ctx, void** p, size_t* have, size_t need) {
     CU(cudaMalloc(p, need));
     *have = need;
     return B200RT_OK;
+}
+
+// Filter records of the two-phase cast (rt_cast.cuh): unit edge planes in f64, slack B folded into w_k.
+// Layout [tile][k][lane] float4 with triangles a = 64*tile + lane, b = a + 32 interleaved.
+int pack_filter(b200rt_ctx* ctx, float origin_bound) {
+    const uint32_t nt = ctx->scene.n_tris;
+    const uint32_t n_tiles = ctx->scene.n_tris_padded / kTileTris;
+    const double u = 5.9604644775390625e-8;   // 2^-24
+    const double S = 2.0 * ((double)origin_bound + (double)ctx->scene_radius + (double)ctx->max_edge);
+    const double A = 64.0 * u * S, B = 128.0 * u * S;
+    std::vector<float4> rec((size_t)std::max(n_tiles, 1u) * 256, make_float4(0.f, 0.f, 0.f, 0.f));
+    auto up = [](double v) { float f = (float)v; if ((double)f < v) f = std::nextafter(f, INFINITY); return f; };
+    for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+        for (uint32_t lane = 0; lane < 32; ++lane) {
+            float vals[2][16];
+            for (int h = 0; h < 2; ++h) {
+                for (int q = 0; q < 16; ++q) vals[h][q] = 0.0f;   // all-zero record: n.dir = 0 -> always a candidate
+                const uint32_t idx = tile * kTileTris + (uint32_t)h * 32u + lane;
+                if (idx >= nt) continue;
+                const float4* ex = &ctx->h_tri_exact[4 * (size_t)idx];
+                const double n[3] = {ex[0].x, ex[0].y, ex[0].z};
+                const double v[3][3] = {{ex[1].x, ex[1].y, ex[1].z}, {ex[2].x, ex[2].y, ex[2].z}, {ex[3].x, ex[3].y, ex[3].z}};
+                // edge k and its anchor vertex, in the order of main.rs:219-221
+                const int ea[3] = {2, 0, 1}, eb[3] = {1, 2, 0};   // e_k = v[ea] - v[eb], anchor v[eb]
+                float out[16];
+                out[0] = ex[0].x; out[1] = ex[0].y; out[2] = ex[0].z; out[3] = ex[0].w;
+                bool ok = std::isfinite(ex[0].x) && std::isfinite(ex[0].y) && std::isfinite(ex[0].z) && std::isfinite(ex[0].w);
+                for (int k = 0; k < 3 && ok; ++k) {
+                    const double e[3] = {v[ea[k]][0] - v[eb[k]][0], v[ea[k]][1] - v[eb[k]][1], v[ea[k]][2] - v[eb[k]][2]};
+                    const double M[3] = {n[1] * e[2] - n[2] * e[1], n[2] * e[0] - n[0] * e[2], n[0] * e[1] - n[1] * e[0]};
+                    const double len = std::sqrt(M[0] * M[0] + M[1] * M[1] + M[2] * M[2]);
+                    if (!(len > 0.0) || !std::isfinite(len)) { ok = false; break; }
+                    const double m[3] = {M[0] / len, M[1] / len, M[2] / len};
+                    const double c = m[0] * v[eb[k]][0] + m[1] * v[eb[k]][1] + m[2] * v[eb[k]][2];
+                    out[4 + 4 * k + 0] = (float)m[0]; out[4 + 4 * k + 1] = (float)m[1]; out[4 + 4 * k + 2] = (float)m[2];
+                    out[4 + 4 * k + 3] = up(-c + B);
+                }
+                if (ok) for (int q = 0; q < 16; ++q) vals[h][q] = out[q];
+            }
+            // interleave {a,b}: entry q -> float2; two entries per float4
+            for (int k = 0; k < 8; ++k)
+                rec[((size_t)tile * 8 + k) * 32 + lane] =
+                    make_float4(vals[0][2 * k], vals[1][2 * k], vals[0][2 * k + 1], vals[1][2 * k + 1]);
+        }
+    }
+    CU(cudaDeviceSynchronize());   // a kernel of an earlier launch may still read the old records
+    int rc = ensure(ctx, &ctx->d_filter, &ctx->d_filter_bytes, rec.size() * sizeof(float4));
+    if (rc != B200RT_OK) return rc;
+    CU(cudaMemcpyAsync(ctx->d_filter, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->scene.tri_filter = reinterpret_cast<const float4*>(ctx->d_filter);
+    ctx->scene.origin_bound = origin_bound;
+    ctx->scene.filter_A = up(A);
+    ctx->scene.filter_g = 3.814697265625e-6f;   // 2^-18
+    return B200RT_OK;
+}
+
+// Rays leave the camera from center + toward*near (- lens offsets): make sure the filter's origin bound covers it.
+int ensure_origin_bound(b200rt_ctx* ctx, const b200rt_camera& cam, const b200rt_params& p) {
+    const double c = std::sqrt((double)cam.center[0] * cam.center[0] + (double)cam.center[1] * cam.center[1] +
+                               (double)cam.center[2] * cam.center[2]);
+    const double need = c + std::fabs((double)cam.near) * 2.0 + 16.0 * std::fabs((double)p.blur) + 1.0;
+    if (need <= (double)ctx->scene.origin_bound) return B200RT_OK;
+    return pack_filter(ctx, (float)(2.0 * need));
 }
 
 // Camera::shoot hoisted (main.rs:85-92)
@@ -164,6 +235,7 @@ int b200rt_destroy(b200rt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d_scene_blob) cudaFree(ctx->d_scene_blob);
+    if (ctx->d_filter) cudaFree(ctx->d_filter);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_aux) cudaFree(ctx->d_aux);
     if (ctx->d_cnt) cudaFree(ctx->d_cnt);
@@ -287,7 +359,30 @@ int b200rt_upload_scene(b200rt_ctx* ctx, const b200rt_scene* s) {
     d.lights = reinterpret_cast<const DLight*>(base + off_light);
     d.n_tris = nt; d.n_sph = ns; d.n_lights = nl; d.n_materials = nm;
     d.n_tris_padded = nt_pad;
-    d.origin_bound = 0.0f;
+    // bounds for the filter slack
+    double rad = 0.0, edge = 0.0;
+    for (uint32_t i = 0; i < nt; ++i) {
+        const float4* ex = &tri_exact[4 * (size_t)i];
+        for (int k = 1; k <= 3; ++k) {
+            const double r2 = (double)ex[k].x * ex[k].x + (double)ex[k].y * ex[k].y + (double)ex[k].z * ex[k].z;
+            if (std::isfinite(r2)) rad = std::max(rad, std::sqrt(r2));
+            const float4 a = ex[k], b = ex[k == 3 ? 1 : k + 1];
+            const double e2 = ((double)a.x - b.x) * ((double)a.x - b.x) + ((double)a.y - b.y) * ((double)a.y - b.y) +
+                              ((double)a.z - b.z) * ((double)a.z - b.z);
+            if (std::isfinite(e2)) edge = std::max(edge, std::sqrt(e2));
+        }
+    }
+    for (uint32_t j = 0; j < ns; ++j) {
+        const double r2 = (double)sph[j].x * sph[j].x + (double)sph[j].y * sph[j].y + (double)sph[j].z * sph[j].z;
+        if (std::isfinite(r2) && std::isfinite(sph[j].w)) rad = std::max(rad, std::sqrt(r2) + std::fabs((double)sph[j].w));
+    }
+    ctx->scene_radius = (float)rad;
+    ctx->max_edge = (float)edge;
+    ctx->h_tri_exact = tri_exact;
+    ctx->h_sph = sph;
+    // every secondary ray starts on a primitive, i.e. within scene_radius (+ rounding); cameras further out re-pack
+    rc = pack_filter(ctx, (float)(4.0 * rad + 8.0));
+    if (rc != B200RT_OK) return rc;
     ctx->have_scene = true;
     return B200RT_OK;
 }
@@ -302,7 +397,9 @@ int b200rt_render_whitted_device(b200rt_ctx* ctx, const b200rt_camera* cam, cons
     int rc = make_params(*params, 0, 1, dp);
     if (rc != B200RT_OK) return rc;
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    rc = ensure_origin_bound(ctx, *cam, *params);
+    if (rc != B200RT_OK) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the CUDA default stream
     CU(cudaEventRecord(ctx->ev0, st));
     CU(launch_whitted(ctx->scene, dc, dp, d_out_rgb, d_out_prim_id, ctx->d_cnt, st));
     CU(cudaEventRecord(ctx->ev1, st));
@@ -351,7 +448,9 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
     int rc = make_params(*params, epoch_begin, epoch_count, dp);
     if (rc != B200RT_OK) return rc;
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    rc = ensure_origin_bound(ctx, *cam, *params);
+    if (rc != B200RT_OK) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the CUDA default stream
     CU(cudaEventRecord(ctx->ev0, st));
     if (epoch_count) CU(launch_distributed(ctx->scene, dc, dp, d_accum, ctx->d_cnt, st));
     CU(cudaEventRecord(ctx->ev1, st));
@@ -386,7 +485,7 @@ int b200rt_render_distributed(b200rt_ctx* ctx, const b200rt_camera* cam, const b
 int b200rt_resolve_device(b200rt_ctx* ctx, const float* d_accum, float* d_out_rgb, size_t n_pixels, void* cuda_stream) {
     if (!ctx || !d_accum || !d_out_rgb) return B200RT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the CUDA default stream
     CU(launch_resolve(d_accum, d_out_rgb, n_pixels, st));
     return B200RT_OK;
 }
@@ -397,7 +496,7 @@ int b200rt_intersect_device(b200rt_ctx* ctx, const b200rt_ray* d_rays, size_t n,
     if (!ctx->have_scene) return B200RT_ERR_NO_SCENE;
     if (cast_mode > B200RT_CAST_BRUTE_EXACT) return B200RT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the CUDA default stream
     CU(cudaEventRecord(ctx->ev0, st));
     CU(launch_intersect(ctx->scene, d_rays, n, cast_mode, d_hits, ctx->d_cnt, st));
     CU(cudaEventRecord(ctx->ev1, st));
@@ -439,6 +538,81 @@ int b200rt_reset_stats(b200rt_ctx* ctx) {
     CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(DCounters), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    return B200RT_OK;
+}
+
+int b200rt_filter_bench(b200rt_ctx* ctx, int variant, int blocks_per_sm, int iters, float* kernel_ms, uint64_t* pair_tests) {
+    if (!ctx || !kernel_ms || !pair_tests || blocks_per_sm <= 0 || iters <= 0) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * blocks_per_sm;
+    const size_t n_rays = (size_t)blocks * 256 * 4;
+    // synthetic tile: an 8x8 patch of small triangles in the z=0 plane; rays start above it pointing down
+    std::vector<float4> recs(4 * 64), rays(2 * n_rays);
+    for (int i = 0; i < 64; ++i) {
+        const float cx = (float)(i % 8) * 0.25f, cy = (float)(i / 8) * 0.25f;
+        recs[4 * i + 0] = make_float4(0.f, 0.f, 1.f, 0.f);
+        recs[4 * i + 1] = make_float4(1.f, 0.f, 0.f, -cx);
+        recs[4 * i + 2] = make_float4(0.f, 1.f, 0.f, -cy);
+        recs[4 * i + 3] = make_float4(-0.70710678f, -0.70710678f, 0.f, 0.70710678f * (cx + cy + 0.25f));
+    }
+    uint32_t s = 12345u;
+    auto rnd = [&s]() { s = s * 1664525u + 1013904223u; return (float)(s >> 8) * (1.0f / 16777216.0f); };
+    for (size_t i = 0; i < n_rays; ++i) {
+        float dx = rnd() - 0.5f, dy = rnd() - 0.5f, dz = -1.0f;
+        const float inv = 1.0f / std::sqrt(dx * dx + dy * dy + dz * dz);
+        rays[2 * i] = make_float4(rnd() * 2.f, rnd() * 2.f, 1.0f + rnd(), 0.f);
+        rays[2 * i + 1] = make_float4(dx * inv, dy * inv, dz * inv, 0.f);
+    }
+    const size_t rec_bytes = recs.size() * sizeof(float4), ray_bytes = rays.size() * sizeof(float4);
+    const size_t out_bytes = (size_t)blocks * 256 * sizeof(uint32_t);
+    int rc = ensure(ctx, &ctx->d_aux, &ctx->d_aux_bytes, rec_bytes + ray_bytes);
+    if (rc != B200RT_OK) return rc;
+    rc = ensure(ctx, &ctx->d_out, &ctx->d_out_bytes, out_bytes);
+    if (rc != B200RT_OK) return rc;
+    float4* d_recs = (float4*)ctx->d_aux;
+    float4* d_rays = d_recs + recs.size();
+    CU(cudaMemcpyAsync(d_recs, recs.data(), rec_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_rays, rays.data(), ray_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long pairs = 0;
+    const float A = 2e-6f, B = 4e-6f, g = 2.44140625e-4f;
+    CU(launch_filter_bench(variant, d_recs, d_rays, (uint32_t*)ctx->d_out, blocks, iters, A, B, g, ctx->stream, &pairs));
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        CU(launch_filter_bench(variant, d_recs, d_rays, (uint32_t*)ctx->d_out, blocks, iters, A, B, g, ctx->stream, &pairs));
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        best = std::min(best, ms);
+    }
+    *kernel_ms = best;
+    *pair_tests = pairs;
+    return B200RT_OK;
+}
+
+int b200rt_pipe_bench(b200rt_ctx* ctx, int variant, float* kernel_ms, double* inst_per_clk_per_smsp) {
+    if (!ctx || !kernel_ms || !inst_per_clk_per_smsp) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, iters = 2048;
+    int rc = ensure(ctx, &ctx->d_aux, &ctx->d_aux_bytes, (size_t)blocks * 256 * sizeof(float));
+    if (rc != B200RT_OK) return rc;
+    CU(launch_pipe_bench(variant, (float*)ctx->d_aux, blocks, iters, ctx->stream));
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        CU(launch_pipe_bench(variant, (float*)ctx->d_aux, blocks, iters, ctx->stream));
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        best = std::min(best, ms);
+    }
+    *kernel_ms = best;
+    // 64 "main" instructions per thread per iteration; warps = blocks*8
+    const double warp_insts = (double)blocks * 8.0 * iters * 64.0;
+    const double clocks = best * 1e-3 * (double)ctx->sm_clock_khz * 1e3;
+    *inst_per_clk_per_smsp = warp_insts / clocks / ((double)ctx->sm_count * 4.0);
     return B200RT_OK;
 }
 

@@ -3,17 +3,33 @@
 // Two implementations with identical results (bit-identical prim id, face, t, position):
 //
 //   cast_brute_exact   every ray x primitive pair goes through the exact test, written in the
-//                      reference's operation order with non-fused IEEE arithmetic.
-//   cast_two_phase     phase 1: a branch-free FMA "plane + 3 edge planes" filter over the packed
-//                      64-byte tri_filter records staged in shared memory produces a 64-bit
-//                      candidate mask per 64-triangle tile (the FP32-roofline loop: 20 FFMA-pipe
-//                      instructions per pair).  The filter is conservative: its slack (folded into
-//                      the edge-plane offsets at upload) exceeds the worst-case rounding gap between
-//                      the fused filter and the reference's formula, so it never rejects a pair the
-//                      exact test would accept.
-//                      phase 2: the few surviving candidates (typically 1-4 of 64) are confirmed in
-//                      increasing index order by the same exact test as cast_brute_exact, which keeps
-//                      the reference's "later primitive wins ties, spheres after triangles" rule.
+//                      reference's operation order with non-fused IEEE arithmetic (validation path).
+//
+//   warp_cast          the production path, a WARP-COLLECTIVE two-phase cast:
+//     phase 1 (filter)  lanes hold TRIANGLES, the warp loops over its active RAYS.  Each lane keeps one
+//                       packed pair of triangle records (tri a = 64*tile + lane, tri b = a + 32) in
+//                       registers: 16 float2 = the plane {n, d} and three unit edge planes {m_k, w_k}.
+//                       Every lane's ray is staged once in a 1 KB per-warp shared-memory slot; for each
+//                       active ray j the warp reads it back as a broadcast and evaluates, with Blackwell's
+//                       packed FFMA2 (two triangles per instruction, the ray as scalar-broadcast operand):
+//                           nd = n.dir   num = d - n.o   t = num * rcp(nd)   p = o + t dir
+//                           e_k = m_k.p + w_k            (signed in-plane distance to edge k, + slack)
+//                           keep = min(e0,e1,e2,t) + A|rcp(nd)| >= 0   or   |nd| < g
+//                       Two __ballot_sync give ray j's 64-bit candidate mask, kept by lane j.
+//                       Idle lanes (finished pixels, other recursion branches) still work as triangle
+//                       lanes, so SIMT divergence in the tracer never wastes filter throughput, and for
+//                       scenes of <= 64 triangles the records never leave the register file.
+//     phase 2 (confirm) each lane walks its own ray's candidates in increasing primitive index through the
+//                       exact test — the same code as cast_brute_exact — which preserves the reference's
+//                       "later primitive wins exact ties, spheres after triangles" rule (main.rs:229-233,
+//                       298-302) and its NaN behaviour.
+//
+// The filter is CONSERVATIVE: it may keep a pair the exact test rejects, never the converse.  Bound
+// (u = 2^-24, S = O + Vmax + Emax: ray-origin bound + largest vertex norm + longest edge):
+//   |t_filter - t_ref| <= (u(14 O + 11 V + 6 E)) / |nd| + 5u T      for |nd| >= 8u
+//   |e_filter - e_ref| <= |t_filter - t_ref| + u(6 O + 19 V + 30 E)
+// so A = 64u*2S and B = 128u*2S (folded into w_k) leave a > 4x margin; pairs with |nd| < g = 2^-18 and
+// rays that violate the assumptions (|o| > O, |dir|^2 far from 1, non-finite) skip the filter.
 #pragma once
 #include "rt_math.cuh"
 #include "rt_types.h"
@@ -22,6 +38,8 @@ namespace b200rt {
 
 enum : uint32_t { kFront = 0u, kBack = 1u, kBoth = 2u };
 RT_DI uint32_t face_invert(uint32_t f) { return f == kFront ? kBack : (f == kBack ? kFront : kBoth); }  // main.rs:59-66
+
+constexpr unsigned kFullMask = 0xffffffffu;
 
 struct DRay {  // main.rs:69-81
     f3 o, d;
@@ -47,6 +65,10 @@ struct Best {
     f3 pos;
     float a0, a1, a2;  // edge areas of the winning triangle (barycentric numerators, main.rs:218-222)
 };
+
+RT_DI void best_init(Best& b) {
+    b.prim = -1; b.bf = 0; b.t = 0.0f; b.pos = mk3(0.f, 0.f, 0.f); b.a0 = b.a1 = b.a2 = 0.0f;
+}
 
 // exclusion criteria, main.rs:190-200 / 286-296
 RT_DI bool excluded(const DRay& r, int32_t prim, bool bf) {
@@ -98,7 +120,7 @@ RT_DI void sphere_exact_test(float4 s, int32_t prim, const DRay& r, Best& best) 
 }
 
 // Winner-only work: barycentric normal / uv (main.rs:235-252) or sphere normal / uv (main.rs:305-313)
-RT_DI void finalize_hit(const DScene& sc, const DRay& r, const Best& best, DHit& h) {
+RT_DN void finalize_hit(const DScene& sc, const Best& best, DHit& h) {
     h.prim = best.prim;
     if (best.prim < 0) return;
     h.face = best.bf;
@@ -132,51 +154,133 @@ RT_DI void finalize_hit(const DScene& sc, const DRay& r, const Best& best, DHit&
 // ---- brute-force exact cast (validation path, B200RT_CAST_BRUTE_EXACT) -------------------------
 RT_DI void cast_brute_exact(const DScene& sc, const DRay& r, DHit& h) {
     Best best;
-    best.prim = -1; best.bf = 0; best.t = 0.0f; best.pos = mk3(0.f, 0.f, 0.f); best.a0 = best.a1 = best.a2 = 0.0f;
+    best_init(best);
+#pragma unroll 1
     for (uint32_t i = 0; i < sc.n_tris; ++i) tri_exact_test(sc.tri_exact + 4 * (size_t)i, (int32_t)i, r, best);
+#pragma unroll 1
     for (uint32_t j = 0; j < sc.n_sph; ++j) sphere_exact_test(sc.sph[j], (int32_t)(sc.n_tris + j), r, best);
-    finalize_hit(sc, r, best, h);
+    finalize_hit(sc, best, h);
 }
 
-// ---- two-phase cast -------------------------------------------------------------------------------
-// Filter math for one pair (all explicit FMAs; 20 FFMA-pipe + 1 MUFU + 2 FMNMX3 + 1 SHF):
-//   nd  = n.d                      num = d - n.o                t = num * rcp(nd)
-//   p   = o + t*d                  e_k = m_k.p - c_k            (c_k already holds -slack)
-//   cul = cull_eps - s*nd          (s = +1 front rays, -1 back rays, 0 both)
-//   keep = min(e0, e1, e2, t + t_eps, cul) >= 0                 (NaN keeps: min() drops NaN operands
-//                                                                only if another operand is not NaN;
-//                                                                an all-NaN/Inf pair is caught by the
-//                                                                |nd| guard folded into `cul`)
-// The reject bit is the sign bit of that min, funnel-shifted into the tile mask.
-struct FilterRay {
-    float ox, oy, oz, dx, dy, dz;
-    float s;         // cull sign
+// ---- warp-collective two-phase cast ---------------------------------------------------------------
+RT_DI float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU.RCP, rel. error <= 2^-23
+    return r;
+}
+RT_DI float2 pk(float a, float b) { return make_float2(a, b); }
+RT_DI float2 bc2(float a) { return make_float2(a, a); }      // becomes a scalar-broadcast FFMA2 operand (R.F32)
+
+// One lane's packed pair of filter records (triangles a | b in the .x | .y halves): 32 registers.
+struct TriPair {
+    float2 nx, ny, nz, d;
+    float2 m0x, m0y, m0z, w0;
+    float2 m1x, m1y, m1z, w1;
+    float2 m2x, m2y, m2z, w2;
 };
 
-RT_DI float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
+// tri_filter layout: [tile][k = 0..7][lane] float4, so each of the 8 loads is one coalesced 512 B request.
+RT_DI void load_tripair(const float4* __restrict__ tri_filter, uint32_t tile, uint32_t lane, TriPair& c) {
+    const float4* base = tri_filter + (size_t)tile * 256 + lane;
+    const float4 q0 = base[0], q1 = base[32], q2 = base[64], q3 = base[96], q4 = base[128], q5 = base[160],
+                 q6 = base[192], q7 = base[224];
+    c.nx = pk(q0.x, q0.y); c.ny = pk(q0.z, q0.w); c.nz = pk(q1.x, q1.y); c.d = pk(q1.z, q1.w);
+    c.m0x = pk(q2.x, q2.y); c.m0y = pk(q2.z, q2.w); c.m0z = pk(q3.x, q3.y); c.w0 = pk(q3.z, q3.w);
+    c.m1x = pk(q4.x, q4.y); c.m1y = pk(q4.z, q4.w); c.m1z = pk(q5.x, q5.y); c.w1 = pk(q5.z, q5.w);
+    c.m2x = pk(q6.x, q6.y); c.m2y = pk(q6.z, q6.w); c.m2z = pk(q7.x, q7.y); c.w2 = pk(q7.z, q7.w);
+}
 
-template <int kCount>
-RT_DI void filter_tile(const float4* __restrict__ tile, const FilterRay& fr, float t_eps, float cull_eps,
-                       uint32_t& rej_lo, uint32_t& rej_hi) {
-    // tile: kCount records of 4 float4 in shared memory; all lanes read the same address (broadcast).
-    uint32_t lo = 0u, hi = 0u;
-#pragma unroll 8
-    for (int i = 0; i < kCount; ++i) {
-        const float4 q0 = tile[4 * i + 0], q1 = tile[4 * i + 1], q2 = tile[4 * i + 2], q3 = tile[4 * i + 3];
-        const float nd = __fmaf_rn(q0.z, fr.dz, __fmaf_rn(q0.y, fr.dy, q0.x * fr.dx));
-        const float num = __fmaf_rn(-q0.z, fr.oz, __fmaf_rn(-q0.y, fr.oy, __fmaf_rn(-q0.x, fr.ox, q0.w)));
-        const float t = num * __frcp_rn(nd);
-        const float px = __fmaf_rn(t, fr.dx, fr.ox), py = __fmaf_rn(t, fr.dy, fr.oy), pz = __fmaf_rn(t, fr.dz, fr.oz);
-        const float e0 = __fmaf_rn(q1.z, pz, __fmaf_rn(q1.y, py, __fmaf_rn(q1.x, px, -q1.w)));
-        const float e1 = __fmaf_rn(q2.z, pz, __fmaf_rn(q2.y, py, __fmaf_rn(q2.x, px, -q2.w)));
-        const float e2 = __fmaf_rn(q3.z, pz, __fmaf_rn(q3.y, py, __fmaf_rn(q3.x, px, -q3.w)));
-        const float cul = __fmaf_rn(-fr.s, nd, cull_eps);
-        const float m = fminf(min3f(e0, e1, e2), fminf(t + t_eps, cul));
-        // reject iff m < 0 (sign bit set and not -0/NaN-with-sign issues: handled below)
-        const uint32_t sgn = __float_as_uint(m);
-        if (i < 32) lo = __funnelshift_l(sgn, lo, 1); else hi = __funnelshift_l(sgn, hi, 1);
+// Filter of this lane's two triangles against one (warp-uniform) ray.  Returns keep flags.
+RT_DI void filter_pair(const TriPair& c, float ox, float oy, float oz, float dx, float dy, float dz, float A, float g,
+                       bool& keep_a, bool& keep_b) {
+    const float2 nd = __ffma2_rn(c.nz, bc2(dz), __ffma2_rn(c.ny, bc2(dy), __fmul2_rn(c.nx, bc2(dx))));
+    const float2 num = __ffma2_rn(c.nz, bc2(-oz), __ffma2_rn(c.ny, bc2(-oy), __ffma2_rn(c.nx, bc2(-ox), c.d)));
+    const float2 r = pk(rcp_approx(nd.x), rcp_approx(nd.y));
+    const float2 t = __fmul2_rn(num, r);
+    const float2 px = __ffma2_rn(t, bc2(dx), bc2(ox));
+    const float2 py = __ffma2_rn(t, bc2(dy), bc2(oy));
+    const float2 pz = __ffma2_rn(t, bc2(dz), bc2(oz));
+    const float2 e0 = __ffma2_rn(c.m0z, pz, __ffma2_rn(c.m0y, py, __ffma2_rn(c.m0x, px, c.w0)));
+    const float2 e1 = __ffma2_rn(c.m1z, pz, __ffma2_rn(c.m1y, py, __ffma2_rn(c.m1x, px, c.w1)));
+    const float2 e2 = __ffma2_rn(c.m2z, pz, __ffma2_rn(c.m2y, py, __ffma2_rn(c.m2x, px, c.w2)));
+    const float ma = fminf(fminf(fminf(e0.x, e1.x), e2.x), t.x);
+    const float mb = fminf(fminf(fminf(e0.y, e1.y), e2.y), t.y);
+    const float2 ms = __ffma2_rn(bc2(A), pk(fabsf(r.x), fabsf(r.y)), pk(ma, mb));
+    keep_a = (ms.x >= 0.0f) | (fabsf(nd.x) < g);
+    keep_b = (ms.y >= 0.0f) | (fabsf(nd.y) < g);
+}
+
+struct CastStats {
+    unsigned long long casts, confirms, filter_steps;
+};
+
+// Warp-collective cast: EVERY lane of the warp must call it (converged).  `active` lanes carry a ray.
+// s_rays: this warp's 32 x 2 float4 staging slot in shared memory.  tile0: the lane's records of tile 0,
+// loaded once per kernel (scenes of <= 64 triangles never reload them).
+RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPair& tile0, uint32_t lane, bool active,
+                     const DRay& ray, DHit& hit, CastStats& cs) {
+    const unsigned act = __ballot_sync(kFullMask, active);
+    Best best;
+    best_init(best);
+    if (act == 0u) { hit.prim = -1; return; }
+    // stage the rays
+    s_rays[2 * lane + 0] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.0f);
+    s_rays[2 * lane + 1] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f);
+    // rays outside the filter's assumptions go through every pair exactly
+    const float oo = ray.o.x * ray.o.x + ray.o.y * ray.o.y + ray.o.z * ray.o.z;
+    const float dd = ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z;
+    const bool trust = (oo <= sc.origin_bound * sc.origin_bound) && (fabsf(dd - 1.0f) <= 1e-3f);  // false for NaN/Inf
+    __syncwarp();
+    const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
+    for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+        TriPair c;
+        if (tile == 0) c = tile0; else load_tripair(sc.tri_filter, tile, lane, c);
+        uint32_t m_lo = 0u, m_hi = 0u;
+        // two rays per iteration: two independent FFMA2 dependency chains in flight per warp
+        unsigned m = act;
+        while (m) {
+            const uint32_t j0 = (uint32_t)__ffs((int)m) - 1u;
+            m &= m - 1u;
+            const bool two = m != 0u;
+            const uint32_t j1 = two ? (uint32_t)__ffs((int)m) - 1u : j0;
+            m &= m - 1u;
+            const float4 ro0 = s_rays[2 * j0 + 0], rd0 = s_rays[2 * j0 + 1];   // broadcast reads
+            const float4 ro1 = s_rays[2 * j1 + 0], rd1 = s_rays[2 * j1 + 1];
+            bool ka0, kb0, ka1, kb1;
+            filter_pair(c, ro0.x, ro0.y, ro0.z, rd0.x, rd0.y, rd0.z, sc.filter_A, sc.filter_g, ka0, kb0);
+            filter_pair(c, ro1.x, ro1.y, ro1.z, rd1.x, rd1.y, rd1.z, sc.filter_A, sc.filter_g, ka1, kb1);
+            const unsigned ba0 = __ballot_sync(kFullMask, ka0), bb0 = __ballot_sync(kFullMask, kb0);
+            const unsigned ba1 = __ballot_sync(kFullMask, ka1), bb1 = __ballot_sync(kFullMask, kb1);
+            if (lane == j0) { m_lo = ba0; m_hi = bb0; }
+            if (two && lane == j1) { m_lo = ba1; m_hi = bb1; }
+        }
+        if (active) {
+            const uint32_t base = tile * kTileTris;
+            const uint32_t left = sc.n_tris - base;                      // >= 1
+            const uint32_t v_lo = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
+            const uint32_t v_hi = left >= 64u ? 0xffffffffu : (left > 32u ? ((1u << (left - 32u)) - 1u) : 0u);
+            const uint32_t c_lo = trust ? (m_lo & v_lo) : v_lo;
+            const uint32_t c_hi = trust ? (m_hi & v_hi) : v_hi;
+            unsigned long long cand = ((unsigned long long)c_hi << 32) | (unsigned long long)c_lo;
+            cs.confirms += (unsigned long long)__popcll(cand);
+#pragma unroll 1
+            while (cand) {                                                // increasing primitive index
+                const uint32_t i = (uint32_t)__ffsll((long long)cand) - 1u;
+                cand &= cand - 1ull;
+                tri_exact_test(sc.tri_exact + 4 * (size_t)(base + i), (int32_t)(base + i), ray, best);
+            }
+        }
+        if (lane == 0u) cs.filter_steps += (unsigned long long)__popc(act);
     }
-    rej_lo = lo; rej_hi = hi;
+    __syncwarp();   // staging slot is free for the next cast
+    if (active) {
+#pragma unroll 1
+        for (uint32_t j = 0; j < sc.n_sph; ++j) sphere_exact_test(sc.sph[j], (int32_t)(sc.n_tris + j), ray, best);
+        finalize_hit(sc, best, hit);
+        cs.casts += 1ull;
+    } else {
+        hit.prim = -1;
+    }
 }
 
 }  // namespace b200rt

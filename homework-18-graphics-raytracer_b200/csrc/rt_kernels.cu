@@ -1,12 +1,18 @@
 // rt_kernels.cu — sm_100a kernels of the render core.  Compiled with -fmad=false (see rt_math.cuh).
 //
 // The reference's recursion (ray_trace main.rs:466-519, distributed_ray_trace main.rs:521-614,
-// get_shade 407-464, get_refract 343-405) is flattened into one per-thread state machine whose
-// every iteration is   prepare -> ONE World::cast -> consume.   All lanes of a warp therefore meet
-// at a single cast site regardless of which recursion branch they are in; the divergent part is
-// only the (short) prepare/consume code.  Whitted recursion uses an explicit per-thread stack of
-// pending rays carrying {depth, contribution, throughput}: ray_trace's result is linear in its
-// children (main.rs:516-518), so a child's value is added as throughput * value.
+// get_shade 407-464, get_refract 343-405) is flattened into a WARP-UNIFORM phase machine:
+//
+//     for (;;) {  prepare(phase)  ->  ONE warp-collective World::cast  ->  consume(phase)  }
+//
+// `phase` is the same for all 32 lanes of a warp (path cast / shadow cast of light i / refraction
+// step ...); a lane takes part in a phase through per-lane flags (alive, sh_on, rf_on, b_on).  So
+// the divergent part of a ray tracer — which recursion branch each pixel is in — never splits the
+// warp across different code: every instruction of a phase is issued once for all participating
+// lanes, and there is a single (inlined) cast site whose filter stage is always 32 lanes wide
+// (rt_cast.cuh).  Whitted recursion keeps an explicit per-thread stack of pending rays carrying
+// {depth, contribution, throughput}: ray_trace's result is linear in its children
+// (main.rs:516-518), so a child's value is added as throughput * value.
 #include <cuda_runtime.h>
 
 #include "rt_cast.cuh"
@@ -17,23 +23,22 @@ namespace b200rt {
 
 enum : int { kModeWhitted = 0, kModeDistributed = 1 };
 
-enum : int {
-    ST_EXIT = 0,       // thread has no more samples
-    ST_DONE,           // current sample finished: accumulate it, start the next one (lane refill)
-    ST_POP,            // whitted: take the next pending ray
-    ST_TRACE,          // cast of a path ray in flight
-    ST_LIGHTS,         // get_shade: find the next light that needs a shadow cast
-    ST_SHADOW,         // shadow cast in flight
-    ST_AFTER_SHADE,    // get_shade finished
-    ST_REFR_IN,        // get_refract: first inside cast in flight
-    ST_REFR_TIR,       // get_refract: total-internal-reflection cast
-    ST_AFTER_REFRACT,  // get_refract finished
-    ST_LEVEL,          // distributed: top of distributed_ray_trace for the current hit
-    ST_BOUNCE,         // distributed: reflected (diffuse / glossy) cast in flight
-    ST_BOUNCE_REFR,    // distributed: escape-ray cast in flight
+enum : int {          // warp-uniform phases
+    P_START = 0,      // open the next sample (distributed: next epoch of the pixel; whitted: the pixel)
+    P_POP,            // whitted: every lane takes its next pending ray
+    P_LEVEL,          // distributed: top of distributed_ray_trace for each lane's current hit
+    P_PATH,           // cast in flight: a path ray (primary / popped / bounce)
+    P_SHADE_NEXT,     // get_shade: advance to the next light that some lane has to test
+    P_SHADOW,         // cast in flight: shadow rays of light `li`
+    P_AFTER_SHADE,    // get_shade done for all participating lanes
+    P_REFR_ENTER,     // get_refract: refract into the medium
+    P_REFR_IN,        // cast in flight: first inside ray
+    P_REFR_TIR,       // cast in flight: a total-internal-reflection bounce
+    P_AFTER_REFRACT,  // get_refract done
+    P_EXIT
 };
 
-// what the distributed tracer does with a finished get_shade
+// what a lane does with its finished get_shade in the distributed tracer
 enum : int { SH_FINAL = 0, SH_NEXT_MIX, SH_NEXT_REFR };
 
 struct Pending {  // one stack entry of the flattened Whitted recursion
@@ -45,9 +50,21 @@ struct Pending {  // one stack entry of the flattened Whitted recursion
     f3 throughput;
 };
 
-RT_DI void cast_any(const DScene& sc, const DRay& r, uint32_t cast_mode, DHit& h) {
-    (void)cast_mode;
-    cast_brute_exact(sc, r, h);
+RT_DI void zero_tripair(TriPair& c) {
+    const float2 z = make_float2(0.f, 0.f);
+    c.nx = c.ny = c.nz = c.d = c.m0x = c.m0y = c.m0z = c.w0 = c.m1x = c.m1y = c.m1z = c.w1 = c.m2x = c.m2y = c.m2z = c.w2 = z;
+}
+
+// One World::cast for every active lane of the warp.  Warp-collective: all 32 lanes call it converged.
+template <int CAST>
+RT_DI void cast_warp(const DScene& sc, float4* s_rays, const TriPair& tile0, uint32_t lane, bool active, const DRay& r,
+                     DHit& h, CastStats& cs) {
+    if (CAST == B200RT_CAST_BRUTE_EXACT) {
+        h.prim = -1;
+        if (active) { cast_brute_exact(sc, r, h); cs.casts += 1ull; }
+    } else {
+        warp_cast(sc, s_rays, tile0, lane, active, r, h, cs);
+    }
 }
 
 // Camera::shoot per pixel (main.rs:91, 1094-1096) from the hoisted basis
@@ -56,7 +73,11 @@ RT_DI void clip_of(uint32_t x, uint32_t y, const DParams& p, float& cx, float& c
     cx = ((float)x - (float)p.width / 2.0f) / (float)p.height;    // main.rs:1095
 }
 
-template <int MODE>
+RT_DI void set_hit(DHit& h, f3& h_dir, f3& h_dir_orig, uint32_t& h_rayface, const DHit& hc, const DRay& ray) {
+    h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face;
+}
+
+template <int MODE, int CAST>
 __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCamera cam, const DParams p,
                                                     float* __restrict__ out, int32_t* __restrict__ prim_out,
                                                     DCounters* __restrict__ cnt) {
@@ -70,7 +91,14 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
     const bool in_image = px < p.width && py_local < rows;
     const uint32_t py = p.row_begin + py_local;
 
-    unsigned long long n_casts = 0ull, n_samples = 0ull;
+    unsigned long long n_samples = 0ull;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.filter_steps = 0ull;
+    __shared__ float4 s_rays_all[4][64];               // per-warp ray staging slot of the transposed filter
+    float4* s_rays = s_rays_all[warp];
+    TriPair tile0;                                     // this lane's two triangles of tile 0: register resident
+    if (CAST != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
+    else zero_tripair(tile0);
 
     const f3 cam_toward = mk3(cam.toward), cam_x = mk3(cam.x), cam_y = mk3(cam.y);
     float clip_x = 0.0f, clip_y = 0.0f;
@@ -78,17 +106,21 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
     const f3 pinhole_dir = normalize(clip_x * cam_x + clip_y * cam_y + cam_toward);   // main.rs:91 / 110
 
     const float TH = p.threshold;
-    const uint32_t n_epochs = MODE == kModeDistributed ? p.epoch_count : 1u;
+    const uint32_t n_epochs = MODE == kModeDistributed ? p.epoch_count : 1u;   // warp-uniform
     f3 px_sum = mk3(0.0f, 0.0f, 0.0f);
     float px_count = 0.0f;
     int32_t primary_id = -1;
 
-    // ---- per-sample state (one sample = one Whitted pixel or one stochastic epoch of the pixel) ----
-    Pending stack[B200RT_MAX_DEPTH + 1];
+    // ---- warp-uniform control ----------------------------------------------------------------------------
+    int phase = P_START;
+    uint32_t li = 0;                  // light index of the running get_shade
+    uint32_t next_sample = 0;
+    bool path_is_primary = true;
+
+    // ---- per-lane state ------------------------------------------------------------------------------------
+    Pending stack[MODE == kModeWhitted ? B200RT_MAX_DEPTH + 1 : 1];
     int sp = 0;
-    int st = ST_DONE;
-    uint32_t next_sample = 0;             // samples started so far
-    const uint32_t n_samples_total = in_image ? n_epochs : 0u;
+    bool alive = false;               // the lane has a current node / hit in flight
     bool sample_open = false;
     DRay ray;
     ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.face = kFront; ray.ex_prim = -1; ray.ex_face = kFront;
@@ -98,163 +130,169 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
     float contribution = 1.0f;
     bool first_cast = true;
 
-    // current hit (the `hit` of ray_trace / distributed_ray_trace / get_shade / get_refract)
-    DHit h;
+    DHit h;                           // the `hit` of ray_trace / distributed_ray_trace / get_shade / get_refract
     h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = mk3(0.f, 0.f, 0.f); h.normal = mk3(0.f, 0.f, 1.f);
     h.uv.x = h.uv.y = 0.f;
-    f3 h_dir = mk3(0.f, 0.f, 1.f);       // hit.ray.direction (replaced by scatter_hit in the distributed tracer)
-    f3 h_dir_orig = h_dir;               // direction before scatter_hit (view direction of the BRDF probes)
-    uint32_t h_rayface = kFront;         // hit.ray.face_direction
+    f3 h_dir = mk3(0.f, 0.f, 1.f);    // hit.ray.direction (replaced by scatter_hit in the distributed tracer)
+    f3 h_dir_orig = h_dir;            // direction before scatter_hit (view direction of the BRDF probes)
+    uint32_t h_rayface = kFront;      // hit.ray.face_direction
     MatEval mat;
     mat.normal_ts = mk3(0.f, 0.f, 1.f); mat.diffuse = mat.specular = mk3(0.f, 0.f, 0.f);
     mat.shiness = mat.smoothness = mat.transparency = mat.opaque_decay = 0.f; mat.refraction_index = 1.f;
 
-    // get_shade state
+    // get_shade
+    bool sh_on = false, sh_need = false;
     f3 nadj = mk3(0.f, 0.f, 1.f), shade = mk3(0.f, 0.f, 0.f);
-    uint32_t li = 0;
     DirLight L;
     L.has_origin = false; L.origin = L.dir = L.color = mk3(0.f, 0.f, 0.f);
     int shade_purpose = SH_FINAL;
-    // get_refract state
-    DHit hi = h;                          // hit_inside
+    // get_refract
+    bool rf_on = false, rf_lane = false, refr_ok = false;
+    DHit hi = h;                      // hit_inside
     f3 hi_dir = h_dir; uint32_t hi_rayface = kBack;
-    float rf_k = 1.0f, rf_travel = 0.0f; uint32_t rf_retry = 0; bool refr_ok = false;
+    float rf_k = 1.0f, rf_travel = 0.0f; uint32_t rf_retry = 0;
     DRay escape_ray = ray;
     // whitted per-node values
-    float shade_c = 0.f; bool do_refl = false; float refl_c = 0.f, refr_c = 0.f;
+    float shade_c = 0.f, refl_c = 0.f, refr_c = 0.f; bool do_refl = false;
     // distributed per-level values
     Rng rng; rng.draws = 0; rng.k0 = rng.k1 = rng.x = rng.y = rng.epoch = 0; rng.b[0] = rng.b[1] = rng.b[2] = rng.b[3] = 0;
     f3 pend_factor = mk3(0.f, 0.f, 0.f);  // BRDF probe value (mix branch) or decay^distance (refraction branch)
     f3 a_shade = mk3(0.f, 0.f, 0.f); bool a_known = false;
-    int bounce_type = 0;                  // 0 = diffuse probe, 1 = specular probe (RayType, main.rs:532)
+    int ray_type = 0;                 // RayType (main.rs:532): 0 diffuse, 1 reflection, 2 refraction
+    bool b_on = false;                // lane casts a bounce ray this level
 
-    {
-        for (;;) {
-            // ================================ prepare ===========================================
-            bool need_cast = (st == ST_TRACE);
-            while (!need_cast && st != ST_EXIT) {
-                switch (st) {
-                case ST_DONE: {
-                    // close the finished sample ...
-                    if (sample_open) {
-                        if (MODE == kModeWhitted) {
-                            px_sum = acc;
-                            n_samples += 1ull;
-                        } else if (is_normal_f32(acc.x) && is_normal_f32(acc.y) && is_normal_f32(acc.z)) {  // main.rs:1157-1160
-                            px_sum = px_sum + acc;                                         // photon.rs:30
-                            px_count += 1.0f;                                              // photon.rs:31
-                            n_samples += 1ull;
-                        }
-                        sample_open = false;
-                    }
-                    // ... and open the next one (no warp-wide wait between samples)
-                    if (next_sample >= n_samples_total) { st = ST_EXIT; break; }
-                    sample_open = true;
-                    acc = mk3(0.0f, 0.0f, 0.0f); T = mk3(1.0f, 1.0f, 1.0f);
-                    depth = p.depth; contribution = 1.0f; sp = 0; a_known = false;
+    for (;;) {
+        // =========================================== prepare ===========================================
+        bool active = false;          // this lane carries a ray into the cast below
+        bool need_cast = false;       // warp-uniform
+        while (!need_cast && phase != P_EXIT) {
+            switch (phase) {
+            case P_START: {
+                // close the sample that just finished ...
+                if (sample_open) {
                     if (MODE == kModeWhitted) {
+                        px_sum = acc;
+                        n_samples += 1ull;
+                    } else if (is_normal_f32(acc.x) && is_normal_f32(acc.y) && is_normal_f32(acc.z)) {   // main.rs:1157-1160
+                        px_sum = px_sum + acc;                                         // photon.rs:30
+                        px_count += 1.0f;                                              // photon.rs:31
+                        n_samples += 1ull;
+                    }
+                    sample_open = false;
+                }
+                if (next_sample >= n_epochs) { phase = P_EXIT; break; }
+                // ... and open the next one, in lockstep for the whole warp
+                sample_open = in_image;
+                acc = mk3(0.0f, 0.0f, 0.0f); T = mk3(1.0f, 1.0f, 1.0f);
+                depth = p.depth; contribution = 1.0f; sp = 0; a_known = false; alive = false;
+                if (MODE == kModeWhitted) {
+                    if (in_image) {
                         Pending e;
                         e.o = mk3(cam.origin); e.d = pinhole_dir; e.faces = kFront | (kFront << 2); e.ex_prim = -1;
                         e.depth = p.depth; e.contribution = 1.0f; e.throughput = mk3(1.0f, 1.0f, 1.0f);
                         stack[sp++] = e;
-                        st = ST_POP;
-                    } else {
-                        // Camera::shoot_focus, main.rs:101-127 (Box-Muller on two stream uniforms)
-                        rng_init(rng, p.seed_lo, p.seed_hi, py, px, p.epoch_begin + next_sample);
-                        const float u1 = 1.0f - rng_uniform(rng);
-                        const float u2 = rng_uniform(rng);
-                        const float radius = sqrtf(-2.0f * logf(u1));
-                        const float ang = 2.0f * kPi * u2;
-                        const float xoffset = p.blur * (radius * cosf(ang));
-                        const float yoffset = p.blur * (radius * sinf(ang));
-                        ray.d = normalize(pinhole_dir * p.focus + cam_x * xoffset + cam_y * yoffset);        // main.rs:115-117
-                        ray.o = mk3(cam.center) + normalize(cam_toward) * cam.near - (cam_x * xoffset + cam_y * yoffset);  // :118-120
-                        ray.face = kFront; ray.ex_prim = -1; ray.ex_face = kFront;
-                        st = ST_TRACE; need_cast = true;
                     }
-                    next_sample += 1;
-                    break;
+                    phase = P_POP;
+                } else {
+                    // Camera::shoot_focus, main.rs:101-127 (Box-Muller on two stream uniforms)
+                    rng_init(rng, p.seed_lo, p.seed_hi, py, px, p.epoch_begin + next_sample);
+                    const float u1 = 1.0f - rng_uniform(rng);
+                    const float u2 = rng_uniform(rng);
+                    const float radius = sqrtf(-2.0f * logf(u1));
+                    const float ang = 2.0f * kPi * u2;
+                    const float xoffset = p.blur * (radius * cosf(ang));
+                    const float yoffset = p.blur * (radius * sinf(ang));
+                    ray.d = normalize(pinhole_dir * p.focus + cam_x * xoffset + cam_y * yoffset);        // main.rs:115-117
+                    ray.o = mk3(cam.center) + normalize(cam_toward) * cam.near - (cam_x * xoffset + cam_y * yoffset);  // :118-120
+                    ray.face = kFront; ray.ex_prim = -1; ray.ex_face = kFront;
+                    active = in_image; path_is_primary = true;
+                    phase = P_PATH; need_cast = true;
                 }
-                case ST_POP: {
-                    if (sp == 0) { st = ST_DONE; break; }
+                next_sample += 1;
+                break;
+            }
+            case P_POP: {      // whitted: main.rs:466-471 for the next pending ray of every lane
+                alive = false;
+                while (sp > 0) {
                     const Pending e = stack[--sp];
+                    if (e.contribution < TH) continue;                                  // main.rs:469
                     depth = e.depth; contribution = e.contribution; T = e.throughput;
-                    if (contribution < TH) break;                                          // main.rs:469
                     ray.o = e.o; ray.d = e.d; ray.face = e.faces & 3u; ray.ex_face = (e.faces >> 2) & 3u; ray.ex_prim = e.ex_prim;
-                    st = ST_TRACE; need_cast = true;
+                    alive = true;
                     break;
                 }
-                case ST_LIGHTS: {                                                          // main.rs:413-433
-                    bool found = false;
-                    while (li < sc.n_lights) {
-                        if (approx_light(sc.lights[li], h.pos, L)) {
-                            const float cosine = -dot(L.dir, nadj);                        // main.rs:420
-                            if (!(cosine <= 0.0f)) { found = true; break; }
-                        }
-                        ++li;
-                    }
-                    if (found) {
-                        ray.o = h.pos; ray.d = -L.dir; ray.face = kBack; ray.ex_prim = h.prim; ray.ex_face = kBack;
-                        st = ST_SHADOW; need_cast = true;
+                if (!__any_sync(kFullMask, alive)) { phase = P_START; break; }
+                active = alive; path_is_primary = false;
+                phase = P_PATH; need_cast = true;
+                break;
+            }
+            case P_LEVEL: {    // distributed: main.rs:521-554 for each lane's current hit
+                sh_on = false; b_on = false; rf_on = false; rf_lane = false;
+                if (alive) {
+                    if (depth <= 0) {
+                        if (a_known) { acc = acc + T * a_shade; alive = false; }      // main.rs:525-527 (shade already known)
+                        else { sh_on = true; shade_purpose = SH_FINAL; }             // depth 0 at the primary hit
                     } else {
-                        st = ST_AFTER_SHADE;
+                        const float w0 = (1.0f - mat.shiness) * (1.0f - mat.transparency);
+                        const float w1 = mat.shiness * (1.0f - mat.transparency);
+                        const float w2 = mat.transparency;
+                        // weighted_select, main.rs:652-666
+                        const float wsum = (w0 + w1) + w2;
+                        const float rsel = rng_range(rng, 0.0f, wsum);
+                        float accum = 0.0f;
+                        accum += w0;
+                        if (rsel < accum) ray_type = 0;
+                        else { accum += w1; ray_type = rsel < accum ? 1 : 2; }
+                        // scatter_hit, main.rs:539-554
+                        const f3 base_dir = ray_type == 0 ? -h.normal : h_dir;
+                        const float exponent = ray_type == 0 ? 1.0f : mat.smoothness;
+                        const float phi = acosf(powf(1.0f - rng_range(rng, 0.0f, 1.0f), exponent));
+                        const float theta = rng_range(rng, -kPi, kPi);
+                        const quat from_z = from_arc(mk3(0.0f, 0.0f, 1.0f), normalize(base_dir));
+                        const f3 new_dir = rotate(from_z, mk3(sinf(phi) * cosf(theta), sinf(phi) * sinf(theta), cosf(phi)));
+                        h_dir_orig = h_dir;
+                        h_dir = new_dir;                                               // main.rs:552
+                        const float cosine = -dot(h.normal, h_dir);                    // main.rs:559 / 578 / 597
+                        if (cosine <= 0.0f) alive = false;                             // black
+                        else if (ray_type == 2) { rf_on = true; rf_lane = true; }
+                        else b_on = true;
                     }
-                    break;
                 }
-                case ST_AFTER_SHADE: {
-                    if (MODE == kModeWhitted) {
-                        // main.rs:488-490 / 516: depth<=0 returns the unweighted shade
-                        const f3 term = depth <= 0 ? shade : shade * shade_c;
-                        acc = acc + T * term;
-                        if (depth <= 0) { st = ST_POP; break; }
-                        refl_c = mat.shiness * (1.0f - mat.transparency);                  // main.rs:493
-                        do_refl = contribution * refl_c >= TH;                             // main.rs:495
-                        refr_c = mat.transparency;                                         // main.rs:502
-                        refr_ok = false;
-                        if (contribution * refr_c > TH) {                                  // main.rs:504
-                            rf_k = mat.refraction_index;                                   // main.rs:354
-                            f3 rin;
-                            if (refract_dir(h.normal, h_dir, rf_k, rin)) {                 // main.rs:355-359
-                                ray.o = h.pos; ray.d = normalize(rin); ray.face = kBack; ray.ex_prim = h.prim; ray.ex_face = kFront;
-                                st = ST_REFR_IN; need_cast = true;
-                                break;
-                            }
-                        }
-                        st = ST_AFTER_REFRACT;
+                if (!__any_sync(kFullMask, alive)) { phase = P_START; break; }
+                phase = P_REFR_ENTER;
+                break;
+            }
+            case P_REFR_ENTER: {   // main.rs:354-368
+                refr_ok = false;
+                if (rf_on) {
+                    rf_k = mat.refraction_index;
+                    f3 rin;
+                    if (refract_dir(h.normal, h_dir, rf_k, rin)) {
+                        ray.o = h.pos; ray.d = normalize(rin); ray.face = kBack; ray.ex_prim = h.prim; ray.ex_face = kFront;
                     } else {
-                        if (shade_purpose == SH_FINAL) {
-                            acc = acc + T * shade;
-                            st = ST_DONE;
-                        } else if (shade_purpose == SH_NEXT_MIX) {
-                            // mix(get_shade(next), x*probe, 0.5) = a + (x*probe - a)*0.5   (main.rs:571, 590)
-                            acc = acc + T * (shade - shade * 0.5f);
-                            T = T * (pend_factor * 0.5f);
-                            a_shade = shade; a_known = true; depth -= 1;
-                            st = ST_LEVEL;
-                        } else {
-                            // (x + get_shade(next)) * decay^distance   (main.rs:605)
-                            acc = acc + T * (shade * pend_factor.x);
-                            T = T * pend_factor.x;
-                            a_shade = shade; a_known = true; depth -= 1;
-                            st = ST_LEVEL;
-                        }
+                        rf_on = false;                                                 // Trapped
                     }
-                    break;
                 }
-                case ST_REFR_TIR: {                                                        // main.rs:379-381
-                    ray = make_reflect(hi.pos, hi.normal, hi_dir, hi_rayface, hi.prim, hi.face);
-                    need_cast = true;
-                    break;
-                }
-                case ST_AFTER_REFRACT: {
-                    if (MODE == kModeWhitted) {
-                        // push refraction first so the reflection subtree is evaluated (and summed) first,
-                        // like `shade*sc + reflection*rc + refraction*tc` (main.rs:516-518)
+                if (__any_sync(kFullMask, rf_on)) { active = rf_on; phase = P_REFR_IN; need_cast = true; }
+                else phase = P_AFTER_REFRACT;
+                break;
+            }
+            case P_REFR_TIR: {     // main.rs:379-381
+                if (rf_on) ray = make_reflect(hi.pos, hi.normal, hi_dir, hi_rayface, hi.prim, hi.face);
+                active = rf_on;
+                need_cast = true;
+                break;
+            }
+            case P_AFTER_REFRACT: {
+                if (MODE == kModeWhitted) {
+                    // push refraction first so the reflection subtree is evaluated (and summed) first,
+                    // like `shade*sc + reflection*rc + refraction*tc` (main.rs:516-518)
+                    if (alive) {
                         if (refr_ok) {
                             Pending e;
                             e.o = escape_ray.o; e.d = escape_ray.d; e.faces = escape_ray.face | (escape_ray.ex_face << 2);
                             e.ex_prim = escape_ray.ex_prim; e.depth = depth - 1; e.contribution = contribution * refr_c;
-                            e.throughput = T * (powf(mat.opaque_decay, rf_travel) * refr_c);  // main.rs:508, 518
+                            e.throughput = T * (powf(mat.opaque_decay, rf_travel) * refr_c);   // main.rs:508, 518
                             stack[sp++] = e;
                         }
                         if (do_refl) {
@@ -264,88 +302,144 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
                             e.depth = depth - 1; e.contribution = contribution * refl_c; e.throughput = T * refl_c;
                             stack[sp++] = e;
                         }
-                        st = ST_POP;
-                    } else {
-                        if (refr_ok) { ray = escape_ray; st = ST_BOUNCE_REFR; need_cast = true; }  // main.rs:603
-                        else st = ST_DONE;                                                 // main.rs:610
                     }
-                    break;
-                }
-                case ST_LEVEL: {                                                           // main.rs:521-537
-                    if (depth <= 0) {
-                        if (a_known) { acc = acc + T * a_shade; st = ST_DONE; }
-                        else { nadj = adjust_normal(mat, h.normal); shade = mk3(0.f, 0.f, 0.f); li = 0; shade_purpose = SH_FINAL; st = ST_LIGHTS; }
-                        break;
-                    }
-                    const float w0 = (1.0f - mat.shiness) * (1.0f - mat.transparency);
-                    const float w1 = mat.shiness * (1.0f - mat.transparency);
-                    const float w2 = mat.transparency;
-                    // weighted_select, main.rs:652-666
-                    const float wsum = (w0 + w1) + w2;
-                    const float rsel = rng_range(rng, 0.0f, wsum);
-                    int type = 2;
-                    { float accum = 0.0f; accum += w0; if (rsel < accum) type = 0; else { accum += w1; if (rsel < accum) type = 1; else { accum += w2; type = 2; } } }
-                    // scatter_hit, main.rs:539-554
-                    const f3 base_dir = type == 0 ? -h.normal : h_dir;
-                    const float exponent = type == 0 ? 1.0f : mat.smoothness;
-                    const float phi = acosf(powf(1.0f - rng_range(rng, 0.0f, 1.0f), exponent));
-                    const float theta = rng_range(rng, -kPi, kPi);
-                    const quat from_z = from_arc(mk3(0.0f, 0.0f, 1.0f), normalize(base_dir));
-                    const f3 new_dir = rotate(from_z, mk3(sinf(phi) * cosf(theta), sinf(phi) * sinf(theta), cosf(phi)));
-                    h_dir_orig = h_dir;
-                    h_dir = new_dir;                                                       // main.rs:552
-                    const float cosine = -dot(h.normal, h_dir);                            // main.rs:559 / 578 / 597
-                    if (cosine <= 0.0f) { st = ST_DONE; break; }
-                    if (type != 2) {
-                        ray = make_reflect(h.pos, h.normal, h_dir, h_rayface, h.prim, h.face);  // main.rs:563 / 582
-                        bounce_type = type;
-                        st = ST_BOUNCE; need_cast = true;
-                    } else {
-                        rf_k = mat.refraction_index;
-                        refr_ok = false;
-                        f3 rin;
-                        if (refract_dir(h.normal, h_dir, rf_k, rin)) {
-                            ray.o = h.pos; ray.d = normalize(rin); ray.face = kBack; ray.ex_prim = h.prim; ray.ex_face = kFront;
-                            st = ST_REFR_IN; need_cast = true;
-                        } else {
-                            st = ST_DONE;                                                  // Trapped -> black
-                        }
-                    }
-                    break;
-                }
-                default: st = ST_DONE; break;
-                }
-            }
-            if (st == ST_EXIT) break;
-
-            // ================================ cast ==============================================
-            DHit hc;
-            cast_any(sc, ray, p.cast_mode, hc);
-            n_casts += 1ull;
-            const bool hit = hc.prim >= 0;
-
-            // ================================ consume ===========================================
-            switch (st) {
-            case ST_TRACE: {
-                if (first_cast) { primary_id = hc.prim; first_cast = false; }
-                if (!hit) { st = MODE == kModeWhitted ? ST_POP : ST_DONE; break; }        // main.rs:473-476 / 1154
-                h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face;
-                mat = material_approx(sc.materials, h.object, h.uv);                       // main.rs:478 / 529
-                if (MODE == kModeWhitted) {
-                    shade_c = (1.0f - mat.shiness) * (1.0f - mat.transparency);            // main.rs:480
-                    shade = mk3(0.0f, 0.0f, 0.0f);
-                    if (contribution * shade_c >= TH) {                                    // main.rs:482
-                        nadj = adjust_normal(mat, h.normal); li = 0; st = ST_LIGHTS;       // main.rs:410
-                    } else {
-                        st = ST_AFTER_SHADE;
-                    }
+                    phase = P_POP;
                 } else {
-                    a_known = false;
-                    st = ST_LEVEL;
+                    if (rf_lane) {
+                        if (refr_ok) { ray = escape_ray; b_on = true; }                 // main.rs:603
+                        else alive = false;                                            // main.rs:610
+                    } else if (b_on) {
+                        ray = make_reflect(h.pos, h.normal, h_dir, h_rayface, h.prim, h.face);   // main.rs:563 / 582
+                    }
+                    if (__any_sync(kFullMask, b_on)) { active = b_on; path_is_primary = false; phase = P_PATH; need_cast = true; }
+                    else if (__any_sync(kFullMask, sh_on)) {       // only depth-0 primary hits left
+                        if (sh_on) { nadj = adjust_normal(mat, h.normal); shade = mk3(0.f, 0.f, 0.f); }
+                        li = 0; phase = P_SHADE_NEXT;
+                    } else phase = P_LEVEL;                        // every lane died this level
                 }
                 break;
             }
-            case ST_SHADOW: {                                                              // main.rs:435-461
+            case P_SHADE_NEXT: {   // main.rs:413-433: the next light some lane has to test
+                bool found = false;
+                while (li < sc.n_lights) {
+                    sh_need = false;
+                    if (sh_on && approx_light(sc.lights[li], h.pos, L)) {
+                        const float cosine = -dot(L.dir, nadj);                        // main.rs:420
+                        sh_need = !(cosine <= 0.0f);
+                    }
+                    if (__any_sync(kFullMask, sh_need)) { found = true; break; }
+                    ++li;
+                }
+                if (found) {
+                    if (sh_need) { ray.o = h.pos; ray.d = -L.dir; ray.face = kBack; ray.ex_prim = h.prim; ray.ex_face = kBack; }
+                    active = sh_need;
+                    phase = P_SHADOW; need_cast = true;
+                } else {
+                    phase = P_AFTER_SHADE;
+                }
+                break;
+            }
+            case P_AFTER_SHADE: {
+                if (MODE == kModeWhitted) {
+                    rf_on = false; do_refl = false; refr_ok = false;
+                    if (alive) {
+                        // main.rs:488-490 / 516: depth<=0 returns the unweighted shade
+                        const f3 term = depth <= 0 ? shade : shade * shade_c;
+                        acc = acc + T * term;
+                        if (depth <= 0) alive = false;
+                        else {
+                            refl_c = mat.shiness * (1.0f - mat.transparency);          // main.rs:493
+                            do_refl = contribution * refl_c >= TH;                     // main.rs:495
+                            refr_c = mat.transparency;                                 // main.rs:502
+                            rf_on = contribution * refr_c > TH;                        // main.rs:504
+                        }
+                    }
+                    phase = P_REFR_ENTER;
+                } else {
+                    if (sh_on) {
+                        if (shade_purpose == SH_FINAL) {
+                            acc = acc + T * shade;
+                            alive = false;
+                        } else if (shade_purpose == SH_NEXT_MIX) {
+                            // mix(get_shade(next), x*probe, 0.5) = a + (x*probe - a)*0.5   (main.rs:571, 590)
+                            acc = acc + T * (shade - shade * 0.5f);
+                            T = T * (pend_factor * 0.5f);
+                            a_shade = shade; a_known = true; depth -= 1;
+                        } else {
+                            // (x + get_shade(next)) * decay^distance   (main.rs:605)
+                            acc = acc + T * (shade * pend_factor.x);
+                            T = T * pend_factor.x;
+                            a_shade = shade; a_known = true; depth -= 1;
+                        }
+                        sh_on = false;
+                    }
+                    phase = P_LEVEL;
+                }
+                break;
+            }
+            default: phase = P_EXIT; break;
+            }
+        }
+        if (phase == P_EXIT) break;
+
+        // ============================================ cast =============================================
+        DHit hc;
+        cast_warp<CAST>(sc, s_rays, tile0, lane, active, ray, hc, cs);
+        const bool hit = hc.prim >= 0;
+
+        // =========================================== consume ===========================================
+        switch (phase) {
+        case P_PATH: {
+            if (MODE == kModeWhitted) {
+                sh_on = false;
+                if (active) {
+                    if (first_cast) { primary_id = hc.prim; first_cast = false; }
+                    if (!hit) alive = false;                                           // main.rs:473-476
+                    else {
+                        set_hit(h, h_dir, h_dir_orig, h_rayface, hc, ray);
+                        mat = material_approx(sc.materials, h.object, h.uv);           // main.rs:478
+                        shade_c = (1.0f - mat.shiness) * (1.0f - mat.transparency);    // main.rs:480
+                        shade = mk3(0.0f, 0.0f, 0.0f);
+                        if (contribution * shade_c >= TH) { sh_on = true; nadj = adjust_normal(mat, h.normal); }  // main.rs:482, 410
+                    }
+                }
+                li = 0; phase = P_SHADE_NEXT;
+            } else if (path_is_primary) {
+                alive = active && hit;                                                 // main.rs:1150-1155
+                if (active && first_cast) { primary_id = hc.prim; first_cast = false; }
+                if (alive) {
+                    set_hit(h, h_dir, h_dir_orig, h_rayface, hc, ray);
+                    mat = material_approx(sc.materials, h.object, h.uv);               // main.rs:529
+                    a_known = false;
+                }
+                phase = P_LEVEL;
+            } else {
+                // bounce: main.rs:564-574 / 583-593 / 603-608
+                if (active) {
+                    b_on = false;
+                    if (!hit) {
+                        if (ray_type == 2) alive = false;                              // main.rs:606-608
+                        else { sh_on = true; shade_purpose = SH_FINAL; }               // get_shade(&scattered_hit)
+                    } else {
+                        // probe / decay of the CURRENT material, before the hit is replaced
+                        if (ray_type == 2) { pend_factor.x = powf(mat.opaque_decay, rf_travel); shade_purpose = SH_NEXT_REFR; }
+                        else {
+                            pend_factor = ray_type == 0 ? get_diffuse(mat, h.normal, ray.d)                    // main.rs:566-570
+                                                        : get_specular(mat, h.normal, -h_dir_orig, ray.d);     // main.rs:585-589
+                            shade_purpose = SH_NEXT_MIX;
+                        }
+                        set_hit(h, h_dir, h_dir_orig, h_rayface, hc, ray);
+                        mat = material_approx(sc.materials, h.object, h.uv);
+                        sh_on = true;
+                    }
+                }
+                if (sh_on) { nadj = adjust_normal(mat, h.normal); shade = mk3(0.f, 0.f, 0.f); }
+                li = 0; phase = P_SHADE_NEXT;
+            }
+            break;
+        }
+        case P_SHADOW: {                                                               // main.rs:435-461
+            if (active) {
                 bool occluded = false;
                 if (hit) {
                     if (L.has_origin) {
@@ -358,70 +452,48 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
                 }
                 if (!occluded) {
                     const f3 view = -h_dir, ldir = -L.dir;
-                    const f3 diffuse = get_diffuse(mat, nadj, ldir) * L.color;             // main.rs:458
-                    const f3 specular = get_specular(mat, nadj, view, ldir) * L.color;     // main.rs:459
+                    const f3 diffuse = get_diffuse(mat, nadj, ldir) * L.color;         // main.rs:458
+                    const f3 specular = get_specular(mat, nadj, view, ldir) * L.color; // main.rs:459
                     shade = shade + diffuse * (1.0f - mat.shiness) + specular * mat.shiness;  // main.rs:461
                 }
-                ++li;
-                st = ST_LIGHTS;
-                break;
             }
-            case ST_REFR_IN:
-            case ST_REFR_TIR: {                                                            // main.rs:371-388
-                if (!hit) { refr_ok = false; st = ST_AFTER_REFRACT; break; }               // Infinite
-                const f3 prev = st == ST_REFR_IN ? h.pos : hi.pos;
-                hi = hc; hi_dir = ray.d; hi_rayface = ray.face;
-                if (st == ST_REFR_IN) { rf_travel = distance(hi.pos, prev); rf_retry = 0; }   // main.rs:375
-                else { rf_travel += distance(prev, hi.pos); rf_retry += 1; }               // main.rs:385, 387
-                f3 rout;
-                const bool have_out = refract_dir(hi.normal, hi_dir, 1.0f / rf_k, rout);   // main.rs:376 / 386
-                if (!have_out && rf_travel <= p.refract_max_distance && rf_retry < p.tir_retries) {  // main.rs:378
-                    st = ST_REFR_TIR;
-                } else if (!have_out) {
-                    refr_ok = false; st = ST_AFTER_REFRACT;                                // Trapped
-                } else {
-                    refr_ok = true;                                                        // main.rs:392-402
-                    escape_ray.o = hi.pos; escape_ray.d = normalize(rout); escape_ray.face = kFront;
-                    escape_ray.ex_prim = hi.prim; escape_ray.ex_face = kBack;
-                    st = ST_AFTER_REFRACT;
-                }
-                break;
-            }
-            case ST_BOUNCE: {                                                              // main.rs:564-574 / 583-593
-                if (!hit) {
-                    // get_shade(&scattered_hit): same hit, view direction = -scattered direction
-                    nadj = adjust_normal(mat, h.normal); shade = mk3(0.f, 0.f, 0.f); li = 0;
-                    shade_purpose = SH_FINAL; st = ST_LIGHTS;
-                    break;
-                }
-                // probe of the CURRENT material, evaluated before the hit is replaced (main.rs:566-570 / 585-589)
-                pend_factor = bounce_type == 0 ? get_diffuse(mat, h.normal, ray.d)
-                                                 : get_specular(mat, h.normal, -h_dir_orig, ray.d);
-                h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face;
-                mat = material_approx(sc.materials, h.object, h.uv);
-                nadj = adjust_normal(mat, h.normal); shade = mk3(0.f, 0.f, 0.f); li = 0;
-                shade_purpose = SH_NEXT_MIX; st = ST_LIGHTS;
-                break;
-            }
-            case ST_BOUNCE_REFR: {                                                         // main.rs:603-608
-                if (!hit) { st = ST_DONE; break; }
-                pend_factor.x = powf(mat.opaque_decay, rf_travel);
-                h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face;
-                mat = material_approx(sc.materials, h.object, h.uv);
-                nadj = adjust_normal(mat, h.normal); shade = mk3(0.f, 0.f, 0.f); li = 0;
-                shade_purpose = SH_NEXT_REFR; st = ST_LIGHTS;
-                break;
-            }
-            default: st = ST_DONE; break;
-            }
+            ++li;
+            phase = P_SHADE_NEXT;
+            break;
         }
-
+        case P_REFR_IN:
+        case P_REFR_TIR: {                                                             // main.rs:371-388
+            if (active) {
+                if (!hit) { refr_ok = false; rf_on = false; }                          // Infinite
+                else {
+                    const f3 prev = phase == P_REFR_IN ? h.pos : hi.pos;
+                    hi = hc; hi_dir = ray.d; hi_rayface = ray.face;
+                    if (phase == P_REFR_IN) { rf_travel = distance(hi.pos, prev); rf_retry = 0; }   // main.rs:375
+                    else { rf_travel += distance(prev, hi.pos); rf_retry += 1; }       // main.rs:385, 387
+                    f3 rout;
+                    const bool have_out = refract_dir(hi.normal, hi_dir, 1.0f / rf_k, rout);   // main.rs:376 / 386
+                    if (!have_out && rf_travel <= p.refract_max_distance && rf_retry < p.tir_retries) {   // main.rs:378
+                        // stays rf_on: another internal reflection
+                    } else if (!have_out) {
+                        refr_ok = false; rf_on = false;                                // Trapped
+                    } else {
+                        refr_ok = true; rf_on = false;                                 // main.rs:392-402
+                        escape_ray.o = hi.pos; escape_ray.d = normalize(rout); escape_ray.face = kFront;
+                        escape_ray.ex_prim = hi.prim; escape_ray.ex_face = kBack;
+                    }
+                }
+            }
+            phase = __any_sync(kFullMask, rf_on) ? P_REFR_TIR : P_AFTER_REFRACT;
+            break;
+        }
+        default: phase = P_EXIT; break;
+        }
     }
 
     if (in_image) {
         const size_t at = (size_t)py * p.width + px;
         if (MODE == kModeWhitted) {
-            out[3 * at + 0] = 0.0f + px_sum.x;                                             // main.rs:1107
+            out[3 * at + 0] = 0.0f + px_sum.x;                                         // main.rs:1107
             out[3 * at + 1] = 0.0f + px_sum.y;
             out[3 * at + 2] = 0.0f + px_sum.z;
             if (prim_out) prim_out[at] = primary_id;
@@ -435,35 +507,49 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
 
     // statistics: warp reduce, one atomic per warp
     if (cnt) {
+        unsigned long long n_casts = cs.casts, n_conf = cs.confirms;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             n_casts += __shfl_xor_sync(0xffffffffu, n_casts, o);
+            n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
             n_samples += __shfl_xor_sync(0xffffffffu, n_samples, o);
         }
         if (lane == 0) {
             atomicAdd(&cnt->casts, n_casts);
             atomicAdd(&cnt->tri_pairs, n_casts * sc.n_tris);
             atomicAdd(&cnt->sph_pairs, n_casts * sc.n_sph);
+            atomicAdd(&cnt->confirms, n_conf);
             atomicAdd(&cnt->samples, n_samples);
         }
     }
 }
 
-// World::cast for a batch of rays (b200rt_intersect)
+// World::cast for a batch of rays (b200rt_intersect): one ray per lane, warp-collective two-phase cast.
+// This is K2, the intersection kernel on its own.
+template <int CAST>
 __global__ void __launch_bounds__(128) intersect_kernel(const DScene sc, const b200rt_ray* __restrict__ rays, size_t n,
-                                                        uint32_t cast_mode, b200rt_hit* __restrict__ hits,
-                                                        DCounters* __restrict__ cnt) {
+                                                        b200rt_hit* __restrict__ hits, DCounters* __restrict__ cnt) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long n_casts = 0ull;
-    if (i < n) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    __shared__ float4 s_rays_all[4][64];
+    float4* s_rays = s_rays_all[warp];
+    TriPair tile0;
+    if (CAST != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
+    else zero_tripair(tile0);
+    CastStats cs;
+    cs.casts = cs.confirms = cs.filter_steps = 0ull;
+    const bool active = i < n;
+    DRay r;
+    r.o = mk3(0.f, 0.f, 0.f); r.d = mk3(0.f, 0.f, 1.f); r.face = kFront; r.ex_prim = -1; r.ex_face = kFront;
+    if (active) {
         const b200rt_ray in = rays[i];
-        DRay r;
         r.o = mk3(in.origin); r.d = mk3(in.direction); r.face = in.face_direction;
         r.ex_prim = in.exclude_prim; r.ex_face = in.exclude_face;
-        DHit h;
-        h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
-        cast_any(sc, r, cast_mode, h);
-        n_casts = 1ull;
+    }
+    DHit h;
+    h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
+    cast_warp<CAST>(sc, s_rays, tile0, lane, active, r, h, cs);
+    if (active) {
         b200rt_hit o;
         o.prim_id = h.prim;
         const bool hit = h.prim >= 0;
@@ -476,12 +562,17 @@ __global__ void __launch_bounds__(128) intersect_kernel(const DScene sc, const b
         hits[i] = o;
     }
     if (cnt) {
+        unsigned long long n_casts = cs.casts, n_conf = cs.confirms;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n_casts += __shfl_xor_sync(0xffffffffu, n_casts, o);
-        if ((threadIdx.x & 31u) == 0u && n_casts) {
+        for (int o = 16; o > 0; o >>= 1) {
+            n_casts += __shfl_xor_sync(0xffffffffu, n_casts, o);
+            n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+        }
+        if (lane == 0u && n_casts) {
             atomicAdd(&cnt->casts, n_casts);
             atomicAdd(&cnt->tri_pairs, n_casts * sc.n_tris);
             atomicAdd(&cnt->sph_pairs, n_casts * sc.n_sph);
+            atomicAdd(&cnt->confirms, n_conf);
         }
     }
 }
@@ -520,13 +611,19 @@ static inline uint32_t grid_tiles(const DParams& p) {
 
 cudaError_t launch_whitted(const DScene& sc, const DCamera& cam, const DParams& p, float* d_rgb, int32_t* d_prim,
                            DCounters* d_cnt, cudaStream_t stream) {
-    trace_kernel<kModeWhitted><<<grid_tiles(p), 128, 0, stream>>>(sc, cam, p, d_rgb, d_prim, d_cnt);
+    if (p.cast_mode == B200RT_CAST_BRUTE_EXACT)
+        trace_kernel<kModeWhitted, B200RT_CAST_BRUTE_EXACT><<<grid_tiles(p), 128, 0, stream>>>(sc, cam, p, d_rgb, d_prim, d_cnt);
+    else
+        trace_kernel<kModeWhitted, B200RT_CAST_TWO_PHASE><<<grid_tiles(p), 128, 0, stream>>>(sc, cam, p, d_rgb, d_prim, d_cnt);
     return cudaGetLastError();
 }
 
 cudaError_t launch_distributed(const DScene& sc, const DCamera& cam, const DParams& p, float* d_accum,
                                DCounters* d_cnt, cudaStream_t stream) {
-    trace_kernel<kModeDistributed><<<grid_tiles(p), 128, 0, stream>>>(sc, cam, p, d_accum, nullptr, d_cnt);
+    if (p.cast_mode == B200RT_CAST_BRUTE_EXACT)
+        trace_kernel<kModeDistributed, B200RT_CAST_BRUTE_EXACT><<<grid_tiles(p), 128, 0, stream>>>(sc, cam, p, d_accum, nullptr, d_cnt);
+    else
+        trace_kernel<kModeDistributed, B200RT_CAST_TWO_PHASE><<<grid_tiles(p), 128, 0, stream>>>(sc, cam, p, d_accum, nullptr, d_cnt);
     return cudaGetLastError();
 }
 
@@ -534,7 +631,10 @@ cudaError_t launch_intersect(const DScene& sc, const b200rt_ray* d_rays, size_t 
                              b200rt_hit* d_hits, DCounters* d_cnt, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + 127) / 128);
-    intersect_kernel<<<blocks, 128, 0, stream>>>(sc, d_rays, n, cast_mode, d_hits, d_cnt);
+    if (cast_mode == B200RT_CAST_BRUTE_EXACT)
+        intersect_kernel<B200RT_CAST_BRUTE_EXACT><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_cnt);
+    else
+        intersect_kernel<B200RT_CAST_TWO_PHASE><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_cnt);
     return cudaGetLastError();
 }
 

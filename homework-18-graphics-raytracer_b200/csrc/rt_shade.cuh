@@ -10,7 +10,7 @@ struct MatEval {
     float shiness, smoothness, transparency, refraction_index, opaque_decay;
 };
 
-RT_DI MatEval material_approx(const DMaterial* __restrict__ mats, uint32_t object, f2 uv) {
+RT_DN MatEval material_approx(const DMaterial* __restrict__ mats, uint32_t object, f2 uv) {
     const DMaterial& m = mats[object];
     MatEval e;
     e.normal_ts = mk3(m.normal);
@@ -51,7 +51,7 @@ RT_DI f3 get_diffuse(const MatEval& m, f3 n, f3 l) {
     return mk3(0.0f, 0.0f, 0.0f);
 }
 // materials.rs:55-66
-RT_DI f3 get_specular(const MatEval& m, f3 n, f3 view, f3 l) {
+RT_DN f3 get_specular(const MatEval& m, f3 n, f3 view, f3 l) {
     const float cosine = dot(l, n);
     if (cosine <= 0.0f) return mk3(0.0f, 0.0f, 0.0f);
     const f3 reflected_ray = 2.0f * cosine * n - l;
@@ -67,7 +67,7 @@ struct DirLight {  // lights.rs:6-11
 };
 
 // lights.rs:48-93
-RT_DI bool approx_light(const DLight& L, f3 position, DirLight& out) {
+RT_DN bool approx_light(const DLight& L, f3 position, DirLight& out) {
     if (L.kind == B200RT_LIGHT_DIRECTIONAL) {
         out.has_origin = L.has_origin != 0u;
         out.origin = mk3(L.origin);
@@ -101,7 +101,7 @@ RT_DI bool approx_light(const DLight& L, f3 position, DirLight& out) {
 }
 
 // main.rs:328-341 (normal = hit.at.normal, l = hit.ray.direction)
-RT_DI DRay make_reflect(f3 pos, f3 normal, f3 l, uint32_t ray_face, int32_t prim, uint32_t hit_face) {
+RT_DN DRay make_reflect(f3 pos, f3 normal, f3 l, uint32_t ray_face, int32_t prim, uint32_t hit_face) {
     DRay r;
     const f3 reflected = l - 2.0f * dot(l, normal) * normal;
     r.o = pos;
@@ -113,7 +113,7 @@ RT_DI DRay make_reflect(f3 pos, f3 normal, f3 l, uint32_t ray_face, int32_t prim
 }
 
 // closure main.rs:344-352
-RT_DI bool refract_dir(f3 n, f3 l, float k, f3& out) {
+RT_DN bool refract_dir(f3 n, f3 l, float k, f3& out) {
     const float c = -dot(l, n);
     if (k * k >= 1.0f - c * c) {
         const f3 x = (l + n * c) / k - n * sqrtf(1.0f - (1.0f - c * c) / (k * k));

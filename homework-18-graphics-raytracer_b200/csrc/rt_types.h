@@ -2,10 +2,14 @@
 // kernels (rt_kernels.cu).  All records are 16-byte float4 so every load is a 128-bit LDG/LDS.
 //
 // HBM layout (see DESIGN.md "Data layout"):
-//   tri_filter[4*i + 0..3]  {n.xyz, d}  {m0.xyz, c0}  {m1.xyz, c1}  {m2.xyz, c2}
-//        n = unit face normal, d = n.v0 (both bit-identical to the reference's per-pair values),
-//        m_k = n x e_k, c_k = m_k.v_k - eps_k : edge planes with the conservative slack folded in.
-//        Read by the branch-free FMA filter for EVERY ray x triangle pair (64 B/pair, smem-staged).
+//   tri_filter[(tile*8 + k)*32 + lane]   k = 0..7, one float4 each: the packed record PAIR of triangles
+//        a = 64*tile + lane and b = a + 32, interleaved {a,b} so each 64-bit half-pair is an FFMA2 operand:
+//          k0 {nx_a,nx_b, ny_a,ny_b}  k1 {nz_a,nz_b, d_a,d_b}
+//          k2 {m0x, m0y}  k3 {m0z, w0}   k4,k5 edge 1   k6,k7 edge 2          (each entry an {a,b} pair)
+//        n = unit face normal, d = n.v0 (the reference's per-pair values, bit-identical); m_k = unit
+//        in-plane normal of edge k (n x e_k normalised, computed in f64), w_k = -(m_k.v_k) + B with the
+//        conservative slack B folded in.  Read by the warp-transposed FFMA2 filter: 8 coalesced 512 B
+//        loads per warp per tile, and not at all after kernel start for scenes of <= 64 triangles.
 //   tri_exact[4*i + 0..3]   {n.xyz, d}  {v0.xyz, object}  {v1.xyz, 0}  {v2.xyz, 0}
 //        Read only for pairs that survive the filter (exact reference-order confirm).
 //   tri_attr[4*i + 0..3]    {n0.xyz, uv0.x} {n1.xyz, uv0.y} {n2.xyz, uv1.x} {uv1.y, uv2.x, uv2.y, 0}
@@ -51,8 +55,10 @@ struct DScene {
     const DMaterial* materials;
     const DLight* lights;
     uint32_t n_tris, n_sph, n_lights, n_materials;
-    uint32_t n_tris_padded;  // tri_filter is padded to a multiple of kTileTris with never-hit records
-    float origin_bound;      // filter slack was derived for ray origins with |o|_inf <= origin_bound
+    uint32_t n_tris_padded;  // tri_filter is padded to a multiple of kTileTris (padding is masked off)
+    float origin_bound;      // filter slack was derived for ray origins with |o| <= origin_bound
+    float filter_A;          // slack per unit |1/(n.dir)|   (64u * 2S)
+    float filter_g;          // |n.dir| below this always passes the filter (2^-18)
 };
 
 // Camera::shoot hoisted per frame (main.rs:85-92): computed on the host with the same libm tanf
@@ -91,6 +97,9 @@ cudaError_t launch_distributed(const DScene& sc, const DCamera& cam, const DPara
 cudaError_t launch_intersect(const DScene& sc, const b200rt_ray* d_rays, size_t n, uint32_t cast_mode,
                              b200rt_hit* d_hits, DCounters* d_cnt, cudaStream_t stream);
 cudaError_t launch_resolve(const float* d_accum, float* d_rgb, size_t n_pixels, cudaStream_t stream);
+cudaError_t launch_filter_bench(int variant, const float4* d_recs, const float4* d_rays, uint32_t* d_out, int blocks,
+                                int iters, float A, float B, float g, cudaStream_t stream, unsigned long long* pairs);
+cudaError_t launch_pipe_bench(int variant, float* d_sink, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_fp32_peak(float* d_sink, int blocks, int threads, int iters, cudaStream_t stream);
 
 }  // namespace b200rt

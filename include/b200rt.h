@@ -11,7 +11,8 @@
  *   - every entry point returns int: 0 = B200RT_OK, negative = error (b200rt_strerror()).
  *     The reference panics instead (main.rs:785, 767-775); no exception crosses this boundary.
  *   - caller owns every host buffer; the library owns device memory.  `*_device` variants take
- *     device pointers that the caller (e.g. a torch tensor) owns.
+ *     device pointers that the caller (e.g. a torch tensor) owns and enqueue on `cuda_stream`
+ *     (a cudaStream_t; NULL = the CUDA default stream) without synchronising.
  *   - one context per host thread and per GPU.  Multi-GPU = one process (context) per GPU; rows
  *     or epochs are sharded by the caller through b200rt_params.row_begin/row_count and the
  *     epoch_begin/epoch_count arguments.
@@ -221,6 +222,15 @@ int b200rt_reset_stats(b200rt_ctx* ctx);
 /* FP32-pipe calibration: runs a dependent-free FFMA loop on every SM and returns the measured
  * TFLOP/s (2 flop per FFMA lane) — the live denominator bench.py reports beside the nominal one. */
 int b200rt_measure_fp32_peak(b200rt_ctx* ctx, double* tflops, double* sm_mhz_effective);
+
+/* K2 micro-benchmark: the ray x triangle filter loop of the two-phase cast in isolation (one 64-triangle
+ * shared-memory tile, `iters` passes per ray).  variant 0 = scalar FFMA, 1 = FFMA2 over triangle pairs,
+ * 2 / 3 = FFMA2 over ray pairs with 2 / 4 rays per thread.  Returns the kernel time and pair-test count. */
+int b200rt_filter_bench(b200rt_ctx* ctx, int variant, int blocks_per_sm, int iters, float* kernel_ms,
+                        uint64_t* pair_tests);
+
+/* Pipe calibration loops (dev tool): returns warp-instructions per clock per SM sub-partition at sm_mhz. */
+int b200rt_pipe_bench(b200rt_ctx* ctx, int variant, float* kernel_ms, double* inst_per_clk_per_smsp);
 
 /* ---- host-side scene construction (World builder; no GPU needed) --------------------------- */
 /* Mirrors World::new / push_object / ObjectProxy::push_triangle(s) / push_sphere / push_light
