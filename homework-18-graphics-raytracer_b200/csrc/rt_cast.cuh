@@ -120,7 +120,7 @@ RT_DI void sphere_exact_test(float4 s, int32_t prim, const DRay& r, Best& best) 
 }
 
 // Winner-only work: barycentric normal / uv (main.rs:235-252) or sphere normal / uv (main.rs:305-313)
-RT_DN void finalize_hit(const DScene& sc, const Best& best, DHit& h) {
+RT_DI void finalize_hit(const DScene& sc, const Best& best, DHit& h) {
     h.prim = best.prim;
     if (best.prim < 0) return;
     h.face = best.bf;
@@ -146,8 +146,8 @@ RT_DN void finalize_hit(const DScene& sc, const Best& best, DHit& h) {
         h.object = sc.sph_obj[j];
         const f3 tmp = normalize(best.pos - mk3(s));                              // main.rs:306
         h.normal = best.bf ? -tmp : tmp;
-        h.uv.x = acosf(h.normal.y) / kPi;                                         // main.rs:311
-        h.uv.y = atan2f(h.normal.z, h.normal.x) / (kPi * 2.0f) + 0.5f;            // main.rs:312
+        h.uv.x = nl_acosf(h.normal.y) / kPi;                                         // main.rs:311
+        h.uv.y = nl_atan2f(h.normal.z, h.normal.x) / (kPi * 2.0f) + 0.5f;            // main.rs:312
     }
 }
 

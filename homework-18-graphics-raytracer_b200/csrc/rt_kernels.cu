@@ -77,8 +77,12 @@ RT_DI void set_hit(DHit& h, f3& h_dir, f3& h_dir_orig, uint32_t& h_rayface, cons
     h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face;
 }
 
+#ifndef B200RT_TRACE_MIN_BLOCKS
+#define B200RT_TRACE_MIN_BLOCKS 4
+#endif
+
 template <int MODE, int CAST>
-__global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCamera cam, const DParams p,
+__global__ void __launch_bounds__(128, B200RT_TRACE_MIN_BLOCKS) trace_kernel(const DScene sc, const DCamera cam, const DParams p,
                                                     float* __restrict__ out, int32_t* __restrict__ prim_out,
                                                     DCounters* __restrict__ cnt) {
     // pixel mapping: CTA = 16x8 pixel tile, warp = 8x4 pixels (coherent primary rays)
@@ -158,6 +162,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
     Rng rng; rng.draws = 0; rng.k0 = rng.k1 = rng.x = rng.y = rng.epoch = 0; rng.b[0] = rng.b[1] = rng.b[2] = rng.b[3] = 0;
     f3 pend_factor = mk3(0.f, 0.f, 0.f);  // BRDF probe value (mix branch) or decay^distance (refraction branch)
     f3 a_shade = mk3(0.f, 0.f, 0.f); bool a_known = false;
+    bool shade_init = false;          // warp-uniform: get_shade starts at the next P_SHADE_NEXT
+    bool probe_pending = false;
     int ray_type = 0;                 // RayType (main.rs:532): 0 diffuse, 1 reflection, 2 refraction
     bool b_on = false;                // lane casts a bounce ray this level
 
@@ -198,10 +204,11 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
                     rng_init(rng, p.seed_lo, p.seed_hi, py, px, p.epoch_begin + next_sample);
                     const float u1 = 1.0f - rng_uniform(rng);
                     const float u2 = rng_uniform(rng);
-                    const float radius = sqrtf(-2.0f * logf(u1));
+                    const float radius = sqrtf(-2.0f * nl_logf(u1));
                     const float ang = 2.0f * kPi * u2;
-                    const float xoffset = p.blur * (radius * cosf(ang));
-                    const float yoffset = p.blur * (radius * sinf(ang));
+                    const float2 sca = nl_sincosf(ang);
+                    const float xoffset = p.blur * (radius * sca.y);
+                    const float yoffset = p.blur * (radius * sca.x);
                     ray.d = normalize(pinhole_dir * p.focus + cam_x * xoffset + cam_y * yoffset);        // main.rs:115-117
                     ray.o = mk3(cam.center) + normalize(cam_toward) * cam.near - (cam_x * xoffset + cam_y * yoffset);  // :118-120
                     ray.face = kFront; ray.ex_prim = -1; ray.ex_face = kFront;
@@ -246,10 +253,11 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
                         // scatter_hit, main.rs:539-554
                         const f3 base_dir = ray_type == 0 ? -h.normal : h_dir;
                         const float exponent = ray_type == 0 ? 1.0f : mat.smoothness;
-                        const float phi = acosf(powf(1.0f - rng_range(rng, 0.0f, 1.0f), exponent));
+                        const float phi = nl_acosf(nl_powf(1.0f - rng_range(rng, 0.0f, 1.0f), exponent));
                         const float theta = rng_range(rng, -kPi, kPi);
                         const quat from_z = from_arc(mk3(0.0f, 0.0f, 1.0f), normalize(base_dir));
-                        const f3 new_dir = rotate(from_z, mk3(sinf(phi) * cosf(theta), sinf(phi) * sinf(theta), cosf(phi)));
+                        const float2 scp = nl_sincosf(phi), sct = nl_sincosf(theta);
+                        const f3 new_dir = rotate(from_z, mk3(scp.x * sct.y, scp.x * sct.x, scp.y));
                         h_dir_orig = h_dir;
                         h_dir = new_dir;                                               // main.rs:552
                         const float cosine = -dot(h.normal, h_dir);                    // main.rs:559 / 578 / 597
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
                             Pending e;
                             e.o = escape_ray.o; e.d = escape_ray.d; e.faces = escape_ray.face | (escape_ray.ex_face << 2);
                             e.ex_prim = escape_ray.ex_prim; e.depth = depth - 1; e.contribution = contribution * refr_c;
-                            e.throughput = T * (powf(mat.opaque_decay, rf_travel) * refr_c);   // main.rs:508, 518
+                            e.throughput = T * (nl_powf(mat.opaque_decay, rf_travel) * refr_c);   // main.rs:508, 518
                             stack[sp++] = e;
                         }
                         if (do_refl) {
@@ -313,13 +321,17 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
                     }
                     if (__any_sync(kFullMask, b_on)) { active = b_on; path_is_primary = false; phase = P_PATH; need_cast = true; }
                     else if (__any_sync(kFullMask, sh_on)) {       // only depth-0 primary hits left
-                        if (sh_on) { nadj = adjust_normal(mat, h.normal); shade = mk3(0.f, 0.f, 0.f); }
-                        li = 0; phase = P_SHADE_NEXT;
+                        shade_init = true; li = 0; phase = P_SHADE_NEXT;
                     } else phase = P_LEVEL;                        // every lane died this level
                 }
                 break;
             }
             case P_SHADE_NEXT: {   // main.rs:413-433: the next light some lane has to test
+                if (shade_init) {      // get_shade entry, main.rs:408-412
+                    shade = mk3(0.0f, 0.0f, 0.0f);      // lanes that skip get_shade contribute black (main.rs:485)
+                    if (sh_on) nadj = adjust_normal(mat, h.normal);
+                    shade_init = false;
+                }
                 bool found = false;
                 while (li < sc.n_lights) {
                     sh_need = false;
@@ -399,42 +411,45 @@ __global__ void __launch_bounds__(128) trace_kernel(const DScene sc, const DCame
                         set_hit(h, h_dir, h_dir_orig, h_rayface, hc, ray);
                         mat = material_approx(sc.materials, h.object, h.uv);           // main.rs:478
                         shade_c = (1.0f - mat.shiness) * (1.0f - mat.transparency);    // main.rs:480
-                        shade = mk3(0.0f, 0.0f, 0.0f);
-                        if (contribution * shade_c >= TH) { sh_on = true; nadj = adjust_normal(mat, h.normal); }  // main.rs:482, 410
+                        if (contribution * shade_c >= TH) sh_on = true;                // main.rs:482
                     }
                 }
-                li = 0; phase = P_SHADE_NEXT;
-            } else if (path_is_primary) {
-                alive = active && hit;                                                 // main.rs:1150-1155
-                if (active && first_cast) { primary_id = hc.prim; first_cast = false; }
-                if (alive) {
-                    set_hit(h, h_dir, h_dir_orig, h_rayface, hc, ray);
-                    mat = material_approx(sc.materials, h.object, h.uv);               // main.rs:529
-                    a_known = false;
-                }
-                phase = P_LEVEL;
+                shade_init = true; li = 0; phase = P_SHADE_NEXT;
             } else {
-                // bounce: main.rs:564-574 / 583-593 / 603-608
-                if (active) {
+                // distributed: primary (main.rs:1150-1155) or bounce (main.rs:564-574 / 583-593 / 603-608)
+                bool new_hit = false;
+                if (path_is_primary) {
+                    alive = active && hit;
+                    if (active && first_cast) { primary_id = hc.prim; first_cast = false; }
+                    new_hit = alive;
+                    a_known = false;
+                } else if (active) {
                     b_on = false;
                     if (!hit) {
                         if (ray_type == 2) alive = false;                              // main.rs:606-608
                         else { sh_on = true; shade_purpose = SH_FINAL; }               // get_shade(&scattered_hit)
                     } else {
                         // probe / decay of the CURRENT material, before the hit is replaced
-                        if (ray_type == 2) { pend_factor.x = powf(mat.opaque_decay, rf_travel); shade_purpose = SH_NEXT_REFR; }
+                        if (ray_type == 2) { pend_factor.x = nl_powf(mat.opaque_decay, rf_travel); shade_purpose = SH_NEXT_REFR; }
                         else {
-                            pend_factor = ray_type == 0 ? get_diffuse(mat, h.normal, ray.d)                    // main.rs:566-570
-                                                        : get_specular(mat, h.normal, -h_dir_orig, ray.d);     // main.rs:585-589
+                            // get_diffuse (main.rs:566-570) or get_specular (main.rs:585-589) of the probe
+                            probe_pending = true;
                             shade_purpose = SH_NEXT_MIX;
                         }
-                        set_hit(h, h_dir, h_dir_orig, h_rayface, hc, ray);
-                        mat = material_approx(sc.materials, h.object, h.uv);
-                        sh_on = true;
+                        new_hit = true; sh_on = true;
                     }
                 }
-                if (sh_on) { nadj = adjust_normal(mat, h.normal); shade = mk3(0.f, 0.f, 0.f); }
-                li = 0; phase = P_SHADE_NEXT;
+                if (probe_pending) {
+                    pend_factor = ray_type == 0 ? get_diffuse(mat, h.normal, ray.d)
+                                                : get_specular(mat, h.normal, -h_dir_orig, ray.d);
+                    probe_pending = false;
+                }
+                if (new_hit) {
+                    set_hit(h, h_dir, h_dir_orig, h_rayface, hc, ray);
+                    mat = material_approx(sc.materials, h.object, h.uv);               // main.rs:529
+                }
+                if (path_is_primary) phase = P_LEVEL;
+                else { shade_init = true; li = 0; phase = P_SHADE_NEXT; }
             }
             break;
         }

@@ -37,6 +37,13 @@ RT_DI float magnitude(f3 a) { return sqrtf(dot(a, a)); }
 RT_DN f3 normalize(f3 a) { return a * (1.0f / magnitude(a)); }  // InnerSpace::normalize_to
 RT_DI float distance(f3 a, f3 b) { return magnitude(b - a); }   // MetricSpace for Point3
 
+// libm entry points: one out-of-line copy each (scalar register ABI, no stack traffic)
+RT_DN float nl_powf(float a, float b) { return powf(a, b); }
+RT_DN float nl_acosf(float a) { return acosf(a); }
+RT_DN float nl_atan2f(float a, float b) { return atan2f(a, b); }
+RT_DN float nl_logf(float a) { return logf(a); }
+RT_DN float2 nl_sincosf(float a) { float2 r; r.x = sinf(a); r.y = cosf(a); return r; }
+
 constexpr float kF32Epsilon = 1.1920929e-7f;       // std::f32::EPSILON
 constexpr float kPi = 3.14159265358979323846f;     // std::f32::consts::PI
 

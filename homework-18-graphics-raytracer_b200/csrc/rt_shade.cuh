@@ -10,7 +10,7 @@ struct MatEval {
     float shiness, smoothness, transparency, refraction_index, opaque_decay;
 };
 
-RT_DN MatEval material_approx(const DMaterial* __restrict__ mats, uint32_t object, f2 uv) {
+RT_DI MatEval material_approx(const DMaterial* __restrict__ mats, uint32_t object, f2 uv) {
     const DMaterial& m = mats[object];
     MatEval e;
     e.normal_ts = mk3(m.normal);
@@ -33,7 +33,8 @@ RT_DN MatEval material_approx(const DMaterial* __restrict__ mats, uint32_t objec
         }
         if (m.normal_fn == B200RT_NORMAL_SINCOS_U) {
             const float angle = uv.x * p[7] * 2.0f * kPi;                                // main.rs:856
-            f3 v = mk3(sinf(angle), 0.0f, cosf(angle));
+            const float2 sc2 = nl_sincosf(angle);
+            f3 v = mk3(sc2.x, 0.0f, sc2.y);
             if (dot(v, mk3(0.0f, 0.0f, 1.0f)) <= 0.0f) v = -v;                           // main.rs:858-862
             e.normal_ts = v;
         }
@@ -51,13 +52,13 @@ RT_DI f3 get_diffuse(const MatEval& m, f3 n, f3 l) {
     return mk3(0.0f, 0.0f, 0.0f);
 }
 // materials.rs:55-66
-RT_DN f3 get_specular(const MatEval& m, f3 n, f3 view, f3 l) {
+RT_DI f3 get_specular(const MatEval& m, f3 n, f3 view, f3 l) {
     const float cosine = dot(l, n);
     if (cosine <= 0.0f) return mk3(0.0f, 0.0f, 0.0f);
     const f3 reflected_ray = 2.0f * cosine * n - l;
     const float specular = 1.0f / (m.smoothness + kF32Epsilon);
     const float energy_conserving = (specular + 8.0f) / (8.0f * kPi);
-    const float amount = powf(fmaxf(dot(reflected_ray, view), 0.0f), specular) * energy_conserving;
+    const float amount = nl_powf(fmaxf(dot(reflected_ray, view), 0.0f), specular) * energy_conserving;
     return m.specular * amount;
 }
 
@@ -67,7 +68,7 @@ struct DirLight {  // lights.rs:6-11
 };
 
 // lights.rs:48-93
-RT_DN bool approx_light(const DLight& L, f3 position, DirLight& out) {
+RT_DI bool approx_light(const DLight& L, f3 position, DirLight& out) {
     if (L.kind == B200RT_LIGHT_DIRECTIONAL) {
         out.has_origin = L.has_origin != 0u;
         out.origin = mk3(L.origin);
@@ -79,9 +80,9 @@ RT_DN bool approx_light(const DLight& L, f3 position, DirLight& out) {
     const f3 offset = position - origin;
     if (L.kind == B200RT_LIGHT_SPOT) {
         const f3 sd = mk3(L.direction);
-        const float angle = fabsf(atan2f(magnitude(cross(sd, offset)), dot(sd, offset)));  // Vector3::angle
+        const float angle = fabsf(nl_atan2f(magnitude(cross(sd, offset)), dot(sd, offset)));  // Vector3::angle
         if (angle > L.angle) return false;
-        const float angular = powf(1.0f - angle / L.angle, L.softness + kF32Epsilon);
+        const float angular = nl_powf(1.0f - angle / L.angle, L.softness + kF32Epsilon);
         const float dist_att = 1.0f / (magnitude(offset) + kF32Epsilon);
         out.has_origin = true;
         out.origin = origin;
@@ -101,7 +102,7 @@ RT_DN bool approx_light(const DLight& L, f3 position, DirLight& out) {
 }
 
 // main.rs:328-341 (normal = hit.at.normal, l = hit.ray.direction)
-RT_DN DRay make_reflect(f3 pos, f3 normal, f3 l, uint32_t ray_face, int32_t prim, uint32_t hit_face) {
+RT_DI DRay make_reflect(f3 pos, f3 normal, f3 l, uint32_t ray_face, int32_t prim, uint32_t hit_face) {
     DRay r;
     const f3 reflected = l - 2.0f * dot(l, normal) * normal;
     r.o = pos;
@@ -113,7 +114,7 @@ RT_DN DRay make_reflect(f3 pos, f3 normal, f3 l, uint32_t ray_face, int32_t prim
 }
 
 // closure main.rs:344-352
-RT_DN bool refract_dir(f3 n, f3 l, float k, f3& out) {
+RT_DI bool refract_dir(f3 n, f3 l, float k, f3& out) {
     const float c = -dot(l, n);
     if (k * k >= 1.0f - c * c) {
         const f3 x = (l + n * c) / k - n * sqrtf(1.0f - (1.0f - c * c) / (k * k));
