@@ -106,9 +106,10 @@ class ClockSampler:
 
 def shard(total: int, rank: int, world: int):
     """Contiguous split [g*T/G, (g+1)*T/G)."""
-    b = (rank * total) // world
-    e = ((rank + 1) * total) // world
-    return b, e - b
+    import __graft_entry__ as ge
+    ge.load_package()
+    from b200rt.sharding import shard_range
+    return shard_range(total, rank, world)
 
 
 # --------------------------------------------------------------------------------------------------------

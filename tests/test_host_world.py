@@ -1,0 +1,129 @@
+"""Host-side scene construction (World / ObjectProxy / triangle() / square() / load_obj; main.rs:161-178,
+705-746, 778-807) and the scene literal of main() (main.rs:810-1075)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+def tri_array(b200rt, scene):
+    raw = C.string_at(scene.triangles, C.sizeof(b200rt.Triangle) * scene.n_triangles)
+    return np.frombuffer(raw, dtype=np.float32).reshape(scene.n_triangles, 25)
+
+
+def test_fixture_scene_census(b200rt, fixture_world):
+    s = fixture_world.scene()
+    assert (s.n_triangles, s.n_spheres, s.n_materials, s.n_lights) == (64, 4, 9, 3)
+    t = tri_array(b200rt, s)
+    obj = t[:, 24].view(np.uint32)
+    assert obj[:36].tolist() == [0] * 36                 # dodecahedron
+    assert obj[36:38].tolist() == [1, 1]                 # floor
+    assert obj[38:40].tolist() == [2, 2]                 # wall
+    assert obj[40:52].tolist() == [3] * 12 and obj[52:64].tolist() == [4] * 12     # glass slabs
+    assert [s.spheres[i].object_index for i in range(4)] == [5, 6, 7, 8]
+    np.testing.assert_allclose(list(s.spheres[0].center), [-0.5, 0.5, 0.5 / np.sqrt(np.float32(3))], rtol=1e-7)
+    np.testing.assert_allclose(list(s.spheres[3].center), [0.0, 0.5 + np.sqrt(np.float32(2) / np.float32(3)), 0.0], rtol=1e-7)
+    m = s.materials
+    assert m[2].kind == b200rt.MATERIAL_GENERATIVE and m[2].diffuse_fn == b200rt.DIFFUSE_STRIPE_V
+    assert m[2].normal_fn == b200rt.NORMAL_SINCOS_U and m[2].fn_params[0] == 20.0 and m[2].fn_params[7] == 10.0
+    assert m[7].diffuse_fn == b200rt.DIFFUSE_CHECKER_UPV and list(m[7].specular_color) == [0, 0, 1]
+    assert m[3].refraction_index == pytest.approx(1.6) and m[3].transparency == 1.0 and m[6].transparency == pytest.approx(0.96)
+    assert [s.lights[i].kind for i in range(3)] == [b200rt.LIGHT_DIRECTIONAL, b200rt.LIGHT_SPOT, b200rt.LIGHT_POINT]
+    assert s.lights[0].has_origin == 0 and s.lights[1].angle == pytest.approx(np.pi / 3, rel=1e-6)
+    # the floor quad repeats uv (0,1) on its 4th corner, as the reference does (main.rs:843)
+    assert t[37, 22:24].tolist() == [0.0, 1.0]
+
+
+def test_flat_normals_and_square_order(b200rt):
+    w = b200rt.World()
+    o = w.push_object(b200rt.color_material())
+    o.push_square([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], [[0, 0], [1, 0], [1, 1], [0, 1]])
+    t = tri_array(b200rt, w.scene())
+    assert t.shape[0] == 2
+    # square() = triangle(0,1,2), triangle(0,2,3)  (main.rs:741-746)
+    assert t[0, [0, 1, 8, 9, 16, 17]].tolist() == [0, 0, 1, 0, 1, 1]
+    assert t[1, [0, 1, 8, 9, 16, 17]].tolist() == [0, 0, 1, 1, 0, 1]
+    # triangle(): normal = normalize((v1-v0) x (v2-v1)) on all three vertices (main.rs:731-738)
+    for k in range(2):
+        for v in range(3):
+            assert t[k, 8 * v + 3: 8 * v + 6].tolist() == [0, 0, 1]
+    assert t[1, 22:24].tolist() == [0, 1]
+
+
+def test_push_order_defines_primitive_ids(b200rt, oracle):
+    """PrimitiveIndex::Triangle(i) / Sphere(i) index GLOBAL push-order arrays (main.rs:706-720)."""
+    w = b200rt.World()
+    a = w.push_object(b200rt.color_material())
+    b = w.push_object(b200rt.color_material())
+    b.push_sphere([0, 0, -10], 1.0)
+    a.push_flat_triangle([[-1, -1, -5], [1, -1, -5], [0, 1, -5]])
+    b.push_flat_triangle([[-1, -1, -3], [1, -1, -3], [0, 1, -3]])
+    s = w.scene()
+    assert [s.triangles[i].object_index for i in range(2)] == [0, 1]
+    rays = np.zeros(1, dtype=b200rt.RAY_DTYPE)
+    rays["origin"] = [0, 0, 0]; rays["direction"] = [0, 0, -1]; rays["exclude_prim"] = -1
+    h = oracle.intersect(s, rays)
+    assert h["prim_id"][0] == 1 and h["object_index"][0] == 1 and h["distance"][0] == 3.0
+    rays["exclude_prim"] = 1; rays["exclude_face"] = b200rt.FACE_BOTH
+    assert oracle.intersect(s, rays)["prim_id"][0] == 0
+    rays["origin"] = [5, 5, 0]
+    assert oracle.intersect(s, rays)["prim_id"][0] == -1
+
+
+OBJ_TEXT = """# comment
+o first
+v 0 0 0
+v 1 0 0
+v 1 1 0
+v 0 1 0
+vt 0 0
+vn 0 0 1
+f 1/1/1 2/1/1 3/1/1 4/1/1
+f -4//1 -3//1 -2//1
+g second
+v 5 5 5
+f 1 2 5
+"""
+
+
+def test_obj_import(b200rt, tmp_path):
+    """tobj behaviours load_obj relies on (main.rs:784-790): first model only, fan triangulation, a/b/c forms,
+    negative indices; plus the reference's fixed transform p/3 + (0.7, 1.0, -0.5) (main.rs:802) and uv = (0,0)."""
+    path = tmp_path / "t.obj"
+    path.write_text(OBJ_TEXT)
+    w = b200rt.World()
+    o = w.push_object(b200rt.color_material())
+    n = o.load_obj(str(path))
+    assert n == 3                                             # quad -> 2 triangles, + 1; the `g second` face is ignored
+    t = tri_array(b200rt, w.scene())
+    f32 = np.float32
+    exp0 = [f32(0) / f32(3) + f32(0.7), f32(0) / f32(3) + f32(1.0), f32(0) / f32(3) + f32(-0.5)]
+    assert t[0, 0:3].tolist() == [float(v) for v in exp0]
+    exp1 = [f32(1) / f32(3) + f32(0.7), f32(1.0), f32(-0.5)]
+    assert t[0, 8:11].tolist() == [float(v) for v in exp1]
+    assert t[1, 16:19].tolist() == [float(f32(0.7)), float(f32(1) / f32(3) + f32(1.0)), float(f32(-0.5))]   # fan: (0,2,3)
+    assert np.all(t[:, [6, 7, 14, 15, 22, 23]] == 0)          # uv = (0,0), main.rs:797-799
+    assert np.array_equal(t[2, [0, 1, 2]], t[0, [0, 1, 2]])    # -4 resolves to vertex 1
+    # no transform
+    w2 = b200rt.World()
+    o2 = w2.push_object(b200rt.color_material())
+    assert o2.load_obj(str(path), scale_div=1.0, offset=(0, 0, 0)) == 3
+    assert tri_array(b200rt, w2.scene())[0, 8:11].tolist() == [1, 0, 0]
+
+
+def test_obj_errors(b200rt, tmp_path):
+    w = b200rt.World()
+    o = w.push_object(b200rt.color_material())
+    with pytest.raises(b200rt.B200rtError) as e:               # the reference asserts / panics here (main.rs:785)
+        o.load_obj(str(tmp_path / "missing.obj"))
+    assert e.value.code == b200rt.ERR_IO
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nf 1 2 3\n")                        # index out of range
+    with pytest.raises(b200rt.B200rtError):
+        o.load_obj(str(bad))
+    empty = tmp_path / "empty.obj"
+    empty.write_text("# nothing\n")
+    with pytest.raises(b200rt.B200rtError):
+        o.load_obj(str(empty))
+    lib = b200rt.load_library()
+    assert lib.b200rt_world_push_sphere(w._h, 99, (C.c_float * 3)(0, 0, 0), 1.0) == b200rt.ERR_INVALID   # unknown object
