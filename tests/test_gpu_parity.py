@@ -24,8 +24,12 @@ def check_whitted(b200rt, oracle, ctx, world, params, cam=None):
     r0 = params.row_begin if params.row_count else 0
     r1 = r0 + (params.row_count if params.row_count else params.height)
     assert np.array_equal(prim[r0:r1], o_prim[r0:r1]), f"{int((prim[r0:r1] != o_prim[r0:r1]).sum())} hit ids differ"
-    err = rel_err(rgb[r0:r1], o_rgb[r0:r1])
-    assert np.isfinite(rgb[r0:r1]).all()
+    # the reference itself yields NaN on isolated pixels (e.g. one on the glass sphere at 3840x2160): they must
+    # be reproduced at the same positions; everything else is compared numerically
+    fin_g, fin_o = np.isfinite(rgb[r0:r1]), np.isfinite(o_rgb[r0:r1])
+    assert np.array_equal(fin_g, fin_o), f"{int((fin_g != fin_o).sum())} non-finite channel positions differ"
+    assert (~fin_o).sum() <= max(24, 1e-4 * fin_o.size)
+    err = np.where(fin_o, rel_err(np.where(fin_g, rgb[r0:r1], 0), np.where(fin_o, o_rgb[r0:r1], 0)), 0.0)
     assert err.max() <= REL_TOL, f"max rel err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
     return rgb, prim, cnt
 
