@@ -22,6 +22,8 @@ INCLUDE = os.path.join(ROOT, "include")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_COMMON = ["-O3", "-lineinfo", "-std=c++17", "-I", INCLUDE, "-I", CSRC]
+if os.environ.get("B200RT_DIST_THREADS"):        # tuning knob: CTA size of the lockstep (distributed) tracer
+    NVCC_COMMON.append("-DB200RT_DIST_THREADS=" + os.environ["B200RT_DIST_THREADS"])
 if os.environ.get("B200RT_TRACE_MIN_BLOCKS"):   # tuning knob: resident CTAs per SM the tracer is compiled for
     NVCC_COMMON.append("-DB200RT_TRACE_MIN_BLOCKS=" + os.environ["B200RT_TRACE_MIN_BLOCKS"])
 

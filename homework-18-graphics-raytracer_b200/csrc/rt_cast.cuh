@@ -223,9 +223,15 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
     Best best;
     best_init(best);
     if (act == 0u) { hit.prim = -1; return; }
-    // stage the rays
-    s_rays[2 * lane + 0] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.0f);
-    s_rays[2 * lane + 1] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f);
+    // stage the rays COMPACTED: the k-th active lane writes slot k, so the filter loop below is a plain counted
+    // loop over slots (no find-first-set / mask bookkeeping per iteration)
+    const uint32_t n_act = (uint32_t)__popc(act);
+    const uint32_t rank = (uint32_t)__popc(act & ((1u << lane) - 1u));
+    if (active) {
+        s_rays[2 * rank + 0] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.0f);
+        s_rays[2 * rank + 1] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f);
+    }
+    const uint32_t my_slot = active ? rank : 0xffffffffu;
     // rays outside the filter's assumptions go through every pair exactly
     const float oo = ray.o.x * ray.o.x + ray.o.y * ray.o.y + ray.o.z * ray.o.z;
     const float dd = ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z;
@@ -237,22 +243,18 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
         if (tile == 0) c = tile0; else load_tripair(sc.tri_filter, tile, lane, c);
         uint32_t m_lo = 0u, m_hi = 0u;
         // two rays per iteration: two independent FFMA2 dependency chains in flight per warp
-        unsigned m = act;
-        while (m) {
-            const uint32_t j0 = (uint32_t)__ffs((int)m) - 1u;
-            m &= m - 1u;
-            const bool two = m != 0u;
-            const uint32_t j1 = two ? (uint32_t)__ffs((int)m) - 1u : j0;
-            m &= m - 1u;
-            const float4 ro0 = s_rays[2 * j0 + 0], rd0 = s_rays[2 * j0 + 1];   // broadcast reads
-            const float4 ro1 = s_rays[2 * j1 + 0], rd1 = s_rays[2 * j1 + 1];
+#pragma unroll 1
+        for (uint32_t i0 = 0; i0 < n_act; i0 += 2u) {
+            const uint32_t i1 = min(i0 + 1u, n_act - 1u);               // odd count: the last ray is done twice
+            const float4 ro0 = s_rays[2 * i0 + 0], rd0 = s_rays[2 * i0 + 1];   // broadcast reads
+            const float4 ro1 = s_rays[2 * i1 + 0], rd1 = s_rays[2 * i1 + 1];
             bool ka0, kb0, ka1, kb1;
             filter_pair(c, ro0.x, ro0.y, ro0.z, rd0.x, rd0.y, rd0.z, sc.filter_A, sc.filter_g, ka0, kb0);
             filter_pair(c, ro1.x, ro1.y, ro1.z, rd1.x, rd1.y, rd1.z, sc.filter_A, sc.filter_g, ka1, kb1);
             const unsigned ba0 = __ballot_sync(kFullMask, ka0), bb0 = __ballot_sync(kFullMask, kb0);
             const unsigned ba1 = __ballot_sync(kFullMask, ka1), bb1 = __ballot_sync(kFullMask, kb1);
-            if (lane == j0) { m_lo = ba0; m_hi = bb0; }
-            if (two && lane == j1) { m_lo = ba1; m_hi = bb1; }
+            if (my_slot == i0) { m_lo = ba0; m_hi = bb0; }
+            if (my_slot == i1) { m_lo = ba1; m_hi = bb1; }
         }
         if (active) {
             const uint32_t base = tile * kTileTris;
@@ -275,7 +277,20 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
     __syncwarp();   // staging slot is free for the next cast
     if (active) {
 #pragma unroll 1
-        for (uint32_t j = 0; j < sc.n_sph; ++j) sphere_exact_test(sc.sph[j], (int32_t)(sc.n_tris + j), ray, best);
+        for (uint32_t j = 0; j < sc.n_sph; ++j) {
+            const float4 s4 = sc.sph[j];
+            // conservative pre-filter of main.rs:265-268 (fused arithmetic): squared line-sphere distance
+            // |disp|^2 |dir|^2 - (disp.dir)^2 against r^2 with a 64u (r^2 + |disp|^2) slack (both sides' rounding is
+            // <= 13u of that); NaNs fall through to the exact test
+            const float ex = s4.x - ray.o.x, ey = s4.y - ray.o.y, ez = s4.z - ray.o.z;
+            const float b = __fmaf_rn(ez, ray.d.z, __fmaf_rn(ey, ray.d.y, ex * ray.d.x));
+            const float e2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex));
+            const float r2 = s4.w * s4.w;
+            const float d2 = __fmaf_rn(-b, b, e2 * dd);
+            const float bound = __fmaf_rn(3.8146973e-6f, r2 + e2, r2);
+            if (trust && d2 > bound) continue;
+            sphere_exact_test(s4, (int32_t)(sc.n_tris + j), ray, best);
+        }
         finalize_hit(sc, best, hit);
         cs.casts += 1ull;
     } else {

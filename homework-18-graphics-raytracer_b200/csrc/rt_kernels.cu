@@ -80,25 +80,48 @@ RT_DI void set_hit(DHit& h, f3& h_dir, f3& h_dir_orig, uint32_t& h_rayface, cons
 #ifndef B200RT_TRACE_MIN_BLOCKS
 #define B200RT_TRACE_MIN_BLOCKS 4
 #endif
+// Launch shape per tracer (measured on B200, profiles/README.md):
+//  * distributed: 256-thread CTAs, two per SM, whose 8 warps share the phase (CTA-uniform phase machine,
+//    __syncthreads_or for every phase transition).  The SM then executes one phase's code at a time: the
+//    instruction-cache hit rate goes from 71 % to 93 % and the kernel is 1.36x faster, barrier included
+//    (128x4: 164 ms, 256x2: 154 ms, 512x1: 169 ms on C4 x 8 epochs; warp-uniform 128x4: 210 ms).
+//  * whitted: 128-thread CTAs with warp-uniform phases; its recursion trees differ too much between warps
+//    for a per-phase CTA barrier to pay (2.7 ms -> 3.7 ms at C2 when forced into lockstep).
+template <int MODE> struct TraceCfg;
+template <> struct TraceCfg<0> { static constexpr int kThreads = 128; static constexpr bool kLockstep = false; static constexpr int kMinBlocks = B200RT_TRACE_MIN_BLOCKS; };
+#ifndef B200RT_DIST_THREADS
+#define B200RT_DIST_THREADS 256
+#endif
+template <> struct TraceCfg<1> { static constexpr int kThreads = B200RT_DIST_THREADS; static constexpr bool kLockstep = true;  static constexpr int kMinBlocks = 512 / B200RT_DIST_THREADS; };
+
+template <bool LOCKSTEP>
+RT_DI bool phase_any(bool x) {
+    if (LOCKSTEP) return __syncthreads_or(x ? 1 : 0) != 0;
+    return __any_sync(kFullMask, x) != 0;
+}
+#define PHASE_ANY(x) phase_any<TraceCfg<MODE>::kLockstep>(x)
 
 template <int MODE, int CAST>
-__global__ void __launch_bounds__(128, B200RT_TRACE_MIN_BLOCKS) trace_kernel(const DScene sc, const DCamera cam, const DParams p,
+__global__ void __launch_bounds__(TraceCfg<MODE>::kThreads, TraceCfg<MODE>::kMinBlocks) trace_kernel(const DScene sc, const DCamera cam, const DParams p,
                                                     float* __restrict__ out, int32_t* __restrict__ prim_out,
                                                     DCounters* __restrict__ cnt) {
-    // pixel mapping: CTA = 16x8 pixel tile, warp = 8x4 pixels (coherent primary rays)
+    // pixel mapping: CTA = kTileW x kTileH pixel tile, warp = 8x4 pixels (coherent primary rays)
+    constexpr int kTraceWarps = TraceCfg<MODE>::kThreads / 32;
+    constexpr uint32_t kTileW = kTraceWarps >= 16 ? 32u : 16u;
+    constexpr uint32_t kTileH = (uint32_t)TraceCfg<MODE>::kThreads / kTileW;
     const uint32_t rows = p.row_count ? p.row_count : p.height;
-    const uint32_t tiles_x = (p.width + 15u) / 16u;
+    const uint32_t tiles_x = (p.width + kTileW - 1u) / kTileW;
     const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t px = tile_x * 16u + (warp & 1u) * 8u + (lane & 7u);
-    const uint32_t py_local = tile_y * 8u + (warp >> 1) * 4u + (lane >> 3);
+    const uint32_t px = tile_x * kTileW + (warp % (kTileW / 8u)) * 8u + (lane & 7u);
+    const uint32_t py_local = tile_y * kTileH + (warp / (kTileW / 8u)) * 4u + (lane >> 3);
     const bool in_image = px < p.width && py_local < rows;
     const uint32_t py = p.row_begin + py_local;
 
     unsigned long long n_samples = 0ull;
     CastStats cs;
     cs.casts = cs.confirms = cs.filter_steps = 0ull;
-    __shared__ float4 s_rays_all[4][64];               // per-warp ray staging slot of the transposed filter
+    __shared__ float4 s_rays_all[kTraceWarps][64];     // per-warp ray staging slot of the transposed filter
     float4* s_rays = s_rays_all[warp];
     TriPair tile0;                                     // this lane's two triangles of tile 0: register resident
     if (CAST != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
@@ -228,7 +251,7 @@ __global__ void __launch_bounds__(128, B200RT_TRACE_MIN_BLOCKS) trace_kernel(con
                     alive = true;
                     break;
                 }
-                if (!__any_sync(kFullMask, alive)) { phase = P_START; break; }
+                if (!PHASE_ANY(alive)) { phase = P_START; break; }
                 active = alive; path_is_primary = false;
                 phase = P_PATH; need_cast = true;
                 break;
@@ -266,7 +289,7 @@ __global__ void __launch_bounds__(128, B200RT_TRACE_MIN_BLOCKS) trace_kernel(con
                         else b_on = true;
                     }
                 }
-                if (!__any_sync(kFullMask, alive)) { phase = P_START; break; }
+                if (!PHASE_ANY(alive)) { phase = P_START; break; }
                 phase = P_REFR_ENTER;
                 break;
             }
@@ -281,7 +304,7 @@ __global__ void __launch_bounds__(128, B200RT_TRACE_MIN_BLOCKS) trace_kernel(con
                         rf_on = false;                                                 // Trapped
                     }
                 }
-                if (__any_sync(kFullMask, rf_on)) { active = rf_on; phase = P_REFR_IN; need_cast = true; }
+                if (PHASE_ANY(rf_on)) { active = rf_on; phase = P_REFR_IN; need_cast = true; }
                 else phase = P_AFTER_REFRACT;
                 break;
             }
@@ -319,8 +342,8 @@ __global__ void __launch_bounds__(128, B200RT_TRACE_MIN_BLOCKS) trace_kernel(con
                     } else if (b_on) {
                         ray = make_reflect(h.pos, h.normal, h_dir, h_rayface, h.prim, h.face);   // main.rs:563 / 582
                     }
-                    if (__any_sync(kFullMask, b_on)) { active = b_on; path_is_primary = false; phase = P_PATH; need_cast = true; }
-                    else if (__any_sync(kFullMask, sh_on)) {       // only depth-0 primary hits left
+                    if (PHASE_ANY(b_on)) { active = b_on; path_is_primary = false; phase = P_PATH; need_cast = true; }
+                    else if (PHASE_ANY(sh_on)) {       // only depth-0 primary hits left
                         shade_init = true; li = 0; phase = P_SHADE_NEXT;
                     } else phase = P_LEVEL;                        // every lane died this level
                 }
@@ -339,7 +362,7 @@ __global__ void __launch_bounds__(128, B200RT_TRACE_MIN_BLOCKS) trace_kernel(con
                         const float cosine = -dot(L.dir, nadj);                        // main.rs:420
                         sh_need = !(cosine <= 0.0f);
                     }
-                    if (__any_sync(kFullMask, sh_need)) { found = true; break; }
+                    if (PHASE_ANY(sh_need)) { found = true; break; }
                     ++li;
                 }
                 if (found) {
@@ -498,7 +521,7 @@ __global__ void __launch_bounds__(128, B200RT_TRACE_MIN_BLOCKS) trace_kernel(con
                     }
                 }
             }
-            phase = __any_sync(kFullMask, rf_on) ? P_REFR_TIR : P_AFTER_REFRACT;
+            phase = PHASE_ANY(rf_on) ? P_REFR_TIR : P_AFTER_REFRACT;
             break;
         }
         default: phase = P_EXIT; break;
@@ -619,26 +642,28 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* sink, int iters) 
 }
 
 // ---- launchers -----------------------------------------------------------------------------------
+template <int MODE>
 static inline uint32_t grid_tiles(const DParams& p) {
     const uint32_t rows = p.row_count ? p.row_count : p.height;
-    return ((p.width + 15u) / 16u) * ((rows + 7u) / 8u);
+    const uint32_t tw = TraceCfg<MODE>::kThreads >= 512 ? 32u : 16u, th = (uint32_t)TraceCfg<MODE>::kThreads / tw;
+    return ((p.width + tw - 1u) / tw) * ((rows + th - 1u) / th);
 }
 
 cudaError_t launch_whitted(const DScene& sc, const DCamera& cam, const DParams& p, float* d_rgb, int32_t* d_prim,
                            DCounters* d_cnt, cudaStream_t stream) {
     if (p.cast_mode == B200RT_CAST_BRUTE_EXACT)
-        trace_kernel<kModeWhitted, B200RT_CAST_BRUTE_EXACT><<<grid_tiles(p), 128, 0, stream>>>(sc, cam, p, d_rgb, d_prim, d_cnt);
+        trace_kernel<kModeWhitted, B200RT_CAST_BRUTE_EXACT><<<grid_tiles<kModeWhitted>(p), TraceCfg<kModeWhitted>::kThreads, 0, stream>>>(sc, cam, p, d_rgb, d_prim, d_cnt);
     else
-        trace_kernel<kModeWhitted, B200RT_CAST_TWO_PHASE><<<grid_tiles(p), 128, 0, stream>>>(sc, cam, p, d_rgb, d_prim, d_cnt);
+        trace_kernel<kModeWhitted, B200RT_CAST_TWO_PHASE><<<grid_tiles<kModeWhitted>(p), TraceCfg<kModeWhitted>::kThreads, 0, stream>>>(sc, cam, p, d_rgb, d_prim, d_cnt);
     return cudaGetLastError();
 }
 
 cudaError_t launch_distributed(const DScene& sc, const DCamera& cam, const DParams& p, float* d_accum,
                                DCounters* d_cnt, cudaStream_t stream) {
     if (p.cast_mode == B200RT_CAST_BRUTE_EXACT)
-        trace_kernel<kModeDistributed, B200RT_CAST_BRUTE_EXACT><<<grid_tiles(p), 128, 0, stream>>>(sc, cam, p, d_accum, nullptr, d_cnt);
+        trace_kernel<kModeDistributed, B200RT_CAST_BRUTE_EXACT><<<grid_tiles<kModeDistributed>(p), TraceCfg<kModeDistributed>::kThreads, 0, stream>>>(sc, cam, p, d_accum, nullptr, d_cnt);
     else
-        trace_kernel<kModeDistributed, B200RT_CAST_TWO_PHASE><<<grid_tiles(p), 128, 0, stream>>>(sc, cam, p, d_accum, nullptr, d_cnt);
+        trace_kernel<kModeDistributed, B200RT_CAST_TWO_PHASE><<<grid_tiles<kModeDistributed>(p), TraceCfg<kModeDistributed>::kThreads, 0, stream>>>(sc, cam, p, d_accum, nullptr, d_cnt);
     return cudaGetLastError();
 }
 

@@ -96,9 +96,8 @@ struct Rng {
     uint32_t k0, k1, x, y, epoch, draws;
     uint32_t b[4];
 };
-RT_DI void philox_block(Rng& r, uint32_t block) {
-    uint32_t c0 = r.x, c1 = r.y, c2 = r.epoch, c3 = block;
-    uint32_t k0 = r.k0, k1 = r.k1;
+// one out-of-line copy; by-value ABI (no stack traffic)
+RT_DN uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -107,7 +106,11 @@ RT_DI void philox_block(Rng& r, uint32_t block) {
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    r.b[0] = c0; r.b[1] = c1; r.b[2] = c2; r.b[3] = c3;
+    return make_uint4(c0, c1, c2, c3);
+}
+RT_DI void philox_block(Rng& r, uint32_t block) {
+    const uint4 v = philox4x32_10(r.x, r.y, r.epoch, block, r.k0, r.k1);
+    r.b[0] = v.x; r.b[1] = v.y; r.b[2] = v.z; r.b[3] = v.w;
 }
 RT_DI void rng_init(Rng& r, uint32_t seed_lo, uint32_t seed_hi, uint32_t y, uint32_t x, uint32_t epoch) {
     r.k0 = seed_lo; r.k1 = seed_hi; r.x = x; r.y = y; r.epoch = epoch; r.draws = 0;
