@@ -191,31 +191,107 @@ RT_DI void load_tripair(const float4* __restrict__ tri_filter, uint32_t tile, ui
 }
 
 // Filter of this lane's two triangles against one (warp-uniform) ray.  Returns keep flags.
-RT_DI void filter_pair(const TriPair& c, float ox, float oy, float oz, float dx, float dy, float dz, float A, float g,
-                       bool& keep_a, bool& keep_b) {
+//   cf: the ray's face-cull factor (-K for Front rays, +K for Back rays, 0 for Both; main.rs:185-188): the term
+//   c = cf * nd is negative exactly for the faces the ray's mode culls, and -K|nd| + A/|nd| < 0 for every
+//   |nd| >= g, so culled pairs leave the candidate set here (1 FMUL2 per triangle pair, no extra min: FMNMX3).
+RT_DI void filter_pair(const TriPair& c, float ox, float oy, float oz, float cf, float dx, float dy, float dz, float A,
+                       float g, bool& keep_a, bool& keep_b) {
     const float2 nd = __ffma2_rn(c.nz, bc2(dz), __ffma2_rn(c.ny, bc2(dy), __fmul2_rn(c.nx, bc2(dx))));
     const float2 num = __ffma2_rn(c.nz, bc2(-oz), __ffma2_rn(c.ny, bc2(-oy), __ffma2_rn(c.nx, bc2(-ox), c.d)));
     const float2 r = pk(rcp_approx(nd.x), rcp_approx(nd.y));
     const float2 t = __fmul2_rn(num, r);
+    const float2 cull = __fmul2_rn(nd, bc2(cf));
     const float2 px = __ffma2_rn(t, bc2(dx), bc2(ox));
     const float2 py = __ffma2_rn(t, bc2(dy), bc2(oy));
     const float2 pz = __ffma2_rn(t, bc2(dz), bc2(oz));
     const float2 e0 = __ffma2_rn(c.m0z, pz, __ffma2_rn(c.m0y, py, __ffma2_rn(c.m0x, px, c.w0)));
     const float2 e1 = __ffma2_rn(c.m1z, pz, __ffma2_rn(c.m1y, py, __ffma2_rn(c.m1x, px, c.w1)));
     const float2 e2 = __ffma2_rn(c.m2z, pz, __ffma2_rn(c.m2y, py, __ffma2_rn(c.m2x, px, c.w2)));
-    const float ma = fminf(fminf(fminf(e0.x, e1.x), e2.x), t.x);
-    const float mb = fminf(fminf(fminf(e0.y, e1.y), e2.y), t.y);
+    const float ma = fminf(fminf(fminf(e0.x, e1.x), e2.x), fminf(t.x, cull.x));
+    const float mb = fminf(fminf(fminf(e0.y, e1.y), e2.y), fminf(t.y, cull.y));
     const float2 ms = __ffma2_rn(bc2(A), pk(fabsf(r.x), fabsf(r.y)), pk(ma, mb));
     keep_a = (ms.x >= 0.0f) | (fabsf(nd.x) < g);
     keep_b = (ms.y >= 0.0f) | (fabsf(nd.y) < g);
 }
+constexpr float kCullK = 1099511627776.0f;   // 2^40
 
 struct CastStats {
     unsigned long long casts, confirms, filter_steps;
 };
 
+// Per-warp shared-memory slot of the cast: 32 staged rays (2 float4 each) + the 32 x 64-bit candidate masks.
+constexpr int kCastSlotFloat4 = 64 + 16 + 2;      // rays, masks (uint2[32] = 16 float4), 2 float4 of tail padding
+RT_DI uint2* cast_slot_masks(float4* s_rays) { return reinterpret_cast<uint2*>(s_rays + 64); }
+
+// Phase 2 for one tile: nearest exact hit among this ray's filter candidates (bit i of `cand` = triangle
+// base + i), merged into `best`.
+//
+// CERTIFIED SELECT.  The reference walks the candidates in index order through the exact test.  Here each
+// candidate first gets the filter's own cheap estimate t_i (|t_i - t_exact| <= delta_i = A/|nd|, the bound the
+// filter itself relies on) and is dropped when the exact test is CERTAIN to reject it: face culled or
+// excluded (sign of n.dir is certain for |nd| >= g), t_i + delta_i < 0, or t_i - delta_i > best.t.  The
+// nearest survivor w goes through the exact test; if it is accepted, becomes `best`, and every other
+// survivor j has t_j - delta_j > t_w (exact), the ordered walk would have ended with the same `best`
+// (the others lose on distance whatever their inside test says, ties are impossible) - ONE exact test
+// instead of one per candidate.  Anything else (w rejected, near tie, |nd| < g, untrusted ray) restores
+// `best` and takes the reference's ordered walk over all candidates.
+RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand, bool certify, const DRay& ray,
+                        Best& best, CastStats& cs) {
+    if (cand == 0ull) return;
+    unsigned long long todo = cand;
+    bool fast = false;
+    float lo2 = 0.0f;
+    int32_t w = -1;
+    if (certify) {
+        float lo1 = CUDART_INF_F;
+        lo2 = CUDART_INF_F;
+        unsigned long long rem = cand;
+        bool ambiguous = false;
+#pragma unroll 1
+        while (rem) {
+            const uint32_t i = (uint32_t)__ffsll((long long)rem) - 1u;
+            rem &= rem - 1ull;
+            const float4 q0 = sc.tri_exact[4 * (size_t)(base + i)];
+            const float nd = __fmaf_rn(q0.z, ray.d.z, __fmaf_rn(q0.y, ray.d.y, q0.x * ray.d.x));
+            if (!(fabsf(nd) >= sc.filter_g)) { ambiguous = true; break; }
+            const bool bf = nd > 0.0f;
+            if ((bf && ray.face == kFront) || (!bf && ray.face == kBack)) continue;   // main.rs:185-188, certain
+            if (excluded(ray, (int32_t)(base + i), bf)) continue;                     // main.rs:190-200, certain
+            const float num = __fmaf_rn(q0.z, -ray.o.z, __fmaf_rn(q0.y, -ray.o.y, __fmaf_rn(q0.x, -ray.o.x, q0.w)));
+            const float r = rcp_approx(nd);
+            const float t = num * r, delta = sc.filter_A * fabsf(r);
+            if (t + delta < 0.0f) continue;                                           // t_exact < 0, main.rs:205
+            const float lo = t - delta;
+            if (best.prim >= 0 && lo > best.t) continue;                              // main.rs:229-233, certain
+            if (lo < lo1) { lo2 = lo1; lo1 = lo; w = (int32_t)i; }
+            else if (lo < lo2) lo2 = lo;
+        }
+        if (!ambiguous) {
+            if (w < 0) return;                        // every candidate is certain to be rejected
+            fast = true;
+            todo = 1ull << w;
+        }
+    }
+    const Best saved = best;
+    for (;;) {
+        cs.confirms += (unsigned long long)__popcll(todo);
+#pragma unroll 1
+        while (todo) {                                // increasing primitive index
+            const uint32_t i = (uint32_t)__ffsll((long long)todo) - 1u;
+            todo &= todo - 1ull;
+            tri_exact_test(sc.tri_exact + 4 * (size_t)(base + i), (int32_t)(base + i), ray, best);
+        }
+        if (!fast) break;
+        // certified: w is the new best and everything else is strictly farther; or w was the only survivor
+        if (best.prim == (int32_t)(base + (uint32_t)w) ? (lo2 > best.t) : (lo2 == CUDART_INF_F)) break;
+        best = saved;
+        todo = cand;
+        fast = false;
+    }
+}
+
 // Warp-collective cast: EVERY lane of the warp must call it (converged).  `active` lanes carry a ray.
-// s_rays: this warp's 32 x 2 float4 staging slot in shared memory.  tile0: the lane's records of tile 0,
+// s_rays: this warp's kCastSlotFloat4 staging slot in shared memory.  tile0: the lane's records of tile 0,
 // loaded once per kernel (scenes of <= 64 triangles never reload them).
 RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPair& tile0, uint32_t lane, bool active,
                      const DRay& ray, DHit& hit, CastStats& cs) {
@@ -228,10 +304,11 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
     const uint32_t n_act = (uint32_t)__popc(act);
     const uint32_t rank = (uint32_t)__popc(act & ((1u << lane) - 1u));
     if (active) {
-        s_rays[2 * rank + 0] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.0f);
+        const float cf = ray.face == kFront ? -kCullK : (ray.face == kBack ? kCullK : 0.0f);
+        s_rays[2 * rank + 0] = make_float4(ray.o.x, ray.o.y, ray.o.z, cf);
         s_rays[2 * rank + 1] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f);
     }
-    const uint32_t my_slot = active ? rank : 0xffffffffu;
+    uint2* s_mask = cast_slot_masks(s_rays);
     // rays outside the filter's assumptions go through every pair exactly
     const float oo = ray.o.x * ray.o.x + ray.o.y * ray.o.y + ray.o.z * ray.o.z;
     const float dd = ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z;
@@ -241,40 +318,33 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
     for (uint32_t tile = 0; tile < n_tiles; ++tile) {
         TriPair c;
         if (tile == 0) c = tile0; else load_tripair(sc.tri_filter, tile, lane, c);
-        uint32_t m_lo = 0u, m_hi = 0u;
         // two rays per iteration: two independent FFMA2 dependency chains in flight per warp
 #pragma unroll 1
         for (uint32_t i0 = 0; i0 < n_act; i0 += 2u) {
-            const uint32_t i1 = min(i0 + 1u, n_act - 1u);               // odd count: the last ray is done twice
             const float4 ro0 = s_rays[2 * i0 + 0], rd0 = s_rays[2 * i0 + 1];   // broadcast reads
-            const float4 ro1 = s_rays[2 * i1 + 0], rd1 = s_rays[2 * i1 + 1];
+            const float4 ro1 = s_rays[2 * i0 + 2], rd1 = s_rays[2 * i0 + 3];   // (odd count: a stale slot, its mask is unused)
             bool ka0, kb0, ka1, kb1;
-            filter_pair(c, ro0.x, ro0.y, ro0.z, rd0.x, rd0.y, rd0.z, sc.filter_A, sc.filter_g, ka0, kb0);
-            filter_pair(c, ro1.x, ro1.y, ro1.z, rd1.x, rd1.y, rd1.z, sc.filter_A, sc.filter_g, ka1, kb1);
+            filter_pair(c, ro0.x, ro0.y, ro0.z, ro0.w, rd0.x, rd0.y, rd0.z, sc.filter_A, sc.filter_g, ka0, kb0);
+            filter_pair(c, ro1.x, ro1.y, ro1.z, ro1.w, rd1.x, rd1.y, rd1.z, sc.filter_A, sc.filter_g, ka1, kb1);
             const unsigned ba0 = __ballot_sync(kFullMask, ka0), bb0 = __ballot_sync(kFullMask, kb0);
             const unsigned ba1 = __ballot_sync(kFullMask, ka1), bb1 = __ballot_sync(kFullMask, kb1);
-            if (my_slot == i0) { m_lo = ba0; m_hi = bb0; }
-            if (my_slot == i1) { m_lo = ba1; m_hi = bb1; }
+            if (lane == 0u) *reinterpret_cast<uint4*>(s_mask + i0) = make_uint4(ba0, bb0, ba1, bb1);   // one STS.128
         }
+        __syncwarp();
         if (active) {
+            const uint2 m = s_mask[rank];
             const uint32_t base = tile * kTileTris;
             const uint32_t left = sc.n_tris - base;                      // >= 1
             const uint32_t v_lo = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
             const uint32_t v_hi = left >= 64u ? 0xffffffffu : (left > 32u ? ((1u << (left - 32u)) - 1u) : 0u);
-            const uint32_t c_lo = trust ? (m_lo & v_lo) : v_lo;
-            const uint32_t c_hi = trust ? (m_hi & v_hi) : v_hi;
-            unsigned long long cand = ((unsigned long long)c_hi << 32) | (unsigned long long)c_lo;
-            cs.confirms += (unsigned long long)__popcll(cand);
-#pragma unroll 1
-            while (cand) {                                                // increasing primitive index
-                const uint32_t i = (uint32_t)__ffsll((long long)cand) - 1u;
-                cand &= cand - 1ull;
-                tri_exact_test(sc.tri_exact + 4 * (size_t)(base + i), (int32_t)(base + i), ray, best);
-            }
+            const uint32_t c_lo = trust ? (m.x & v_lo) : v_lo;
+            const uint32_t c_hi = trust ? (m.y & v_hi) : v_hi;
+            const unsigned long long cand = ((unsigned long long)c_hi << 32) | (unsigned long long)c_lo;
+            confirm_tile(sc, base, cand, trust, ray, best, cs);
         }
-        if (lane == 0u) cs.filter_steps += (unsigned long long)__popc(act);
+        if (lane == 0u) cs.filter_steps += (unsigned long long)n_act;
+        __syncwarp();   // masks (and, after the last tile, the ray slots) are free again
     }
-    __syncwarp();   // staging slot is free for the next cast
     if (active) {
 #pragma unroll 1
         for (uint32_t j = 0; j < sc.n_sph; ++j) {

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(TraceCfg<MODE>::kThreads, TraceCfg<MODE>::kMin
     unsigned long long n_samples = 0ull;
     CastStats cs;
     cs.casts = cs.confirms = cs.filter_steps = 0ull;
-    __shared__ float4 s_rays_all[kTraceWarps][64];     // per-warp ray staging slot of the transposed filter
+    __shared__ float4 s_rays_all[kTraceWarps][kCastSlotFloat4];     // per-warp ray staging slot of the transposed filter
     float4* s_rays = s_rays_all[warp];
     TriPair tile0;                                     // this lane's two triangles of tile 0: register resident
     if (CAST != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(const DScene sc, const b
                                                         b200rt_hit* __restrict__ hits, DCounters* __restrict__ cnt) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    __shared__ float4 s_rays_all[4][64];
+    __shared__ float4 s_rays_all[4][kCastSlotFloat4];
     float4* s_rays = s_rays_all[warp];
     TriPair tile0;
     if (CAST != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
