@@ -26,6 +26,7 @@ DIFFUSE_CONST, DIFFUSE_STRIPE_V, DIFFUSE_CHECKER_UPV = 0, 1, 2
 NORMAL_CONST, NORMAL_SINCOS_U = 0, 1
 LIGHT_DIRECTIONAL, LIGHT_SPOT, LIGHT_POINT = 0, 1, 2
 CAST_TWO_PHASE, CAST_BRUTE_EXACT = 0, 1
+TRACER_WAVEFRONT, TRACER_MEGAKERNEL = 0, 1
 MAX_DEPTH = 16
 
 
@@ -93,7 +94,7 @@ class Params(C.Structure):
         ("width", C.c_uint32), ("height", C.c_uint32), ("row_begin", C.c_uint32), ("row_count", C.c_uint32),
         ("depth", C.c_int32), ("threshold", C.c_float), ("refract_max_distance", C.c_float),
         ("tir_retries", C.c_uint32), ("focus", C.c_float), ("blur", C.c_float), ("seed", C.c_uint64),
-        ("cast_mode", C.c_uint32), ("reserved", C.c_uint32),
+        ("cast_mode", C.c_uint32), ("tracer", C.c_uint32),
     ]
 
 
@@ -101,7 +102,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("casts", C.c_uint64), ("tri_pair_tests", C.c_uint64), ("sph_pair_tests", C.c_uint64),
         ("exact_confirms", C.c_uint64), ("samples", C.c_uint64), ("kernel_ms", C.c_float), ("h2d_ms", C.c_float),
-        ("d2h_ms", C.c_float),
+        ("d2h_ms", C.c_float), ("wavefront_rounds", C.c_uint32), ("certify_fallbacks", C.c_uint64),
     ]
 
 

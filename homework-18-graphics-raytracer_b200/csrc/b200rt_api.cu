@@ -15,6 +15,7 @@
 #include "b200rt.h"
 #include "hvec.h"
 #include "rt_types.h"
+#include "rt_wavefront.h"
 
 using namespace b200rt;
 using namespace b200rt_host;
@@ -45,6 +46,11 @@ struct b200rt_ctx {
     void* d_out = nullptr;  size_t d_out_bytes = 0;
     void* d_aux = nullptr;  size_t d_aux_bytes = 0;
     DCounters* d_cnt = nullptr;
+    // wavefront tracer: path state / ray queues in HBM, a pinned word and an event to poll the retired counter
+    void* d_wf = nullptr;   size_t d_wf_bytes = 0;
+    uint32_t* h_poll = nullptr;
+    cudaEvent_t ev_poll = nullptr;
+    uint32_t last_rounds = 0;
 
     b200rt_stats stats{};
 };
@@ -155,6 +161,7 @@ int make_params(const b200rt_params& p, uint32_t epoch_begin, uint32_t epoch_cou
     if (p.depth < 0 || p.depth > B200RT_MAX_DEPTH) return B200RT_ERR_UNSUPPORTED;
     if (p.row_count && (p.row_begin >= p.height || p.row_begin + p.row_count > p.height)) return B200RT_ERR_INVALID;
     if (p.cast_mode > B200RT_CAST_BRUTE_EXACT) return B200RT_ERR_INVALID;
+    if (p.tracer > B200RT_TRACER_MEGAKERNEL) return B200RT_ERR_INVALID;
     o.width = p.width; o.height = p.height;
     o.row_begin = p.row_count ? p.row_begin : 0u;
     o.row_count = p.row_count ? p.row_count : p.height;
@@ -178,6 +185,8 @@ int fetch_counters(b200rt_ctx* ctx) {
     ctx->stats.sph_pair_tests = h.sph_pairs;
     ctx->stats.exact_confirms = h.confirms;
     ctx->stats.samples = h.samples;
+    ctx->stats.certify_fallbacks = h.fallbacks;
+    ctx->stats.wavefront_rounds = ctx->last_rounds;
     return B200RT_OK;
 }
 
@@ -221,6 +230,8 @@ int b200rt_create(int device_id, b200rt_ctx** out_ctx) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_poll, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_poll, sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_cnt, sizeof(DCounters)) != cudaSuccess ||
         cudaMemset(ctx->d_cnt, 0, sizeof(DCounters)) != cudaSuccess) {
         b200rt_destroy(ctx);
@@ -239,6 +250,9 @@ int b200rt_destroy(b200rt_ctx* ctx) {
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_aux) cudaFree(ctx->d_aux);
     if (ctx->d_cnt) cudaFree(ctx->d_cnt);
+    if (ctx->d_wf) cudaFree(ctx->d_wf);
+    if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
+    if (ctx->ev_poll) cudaEventDestroy(ctx->ev_poll);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -452,7 +466,31 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
     if (rc != B200RT_OK) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the CUDA default stream
     CU(cudaEventRecord(ctx->ev0, st));
-    if (epoch_count) CU(launch_distributed(ctx->scene, dc, dp, d_accum, ctx->d_cnt, st));
+    if (epoch_count) {
+        if (params->tracer == B200RT_TRACER_MEGAKERNEL || params->cast_mode == B200RT_CAST_BRUTE_EXACT) {
+            CU(launch_distributed(ctx->scene, dc, dp, d_accum, ctx->d_cnt, st));
+        } else {
+            // wavefront: rows are rendered in bands of at most kMaxPaths path slots (the whole frame at 4K)
+            const uint32_t epar = wf_epochs_in_flight(dp.width, dp.height, epoch_count);
+            const uint64_t kMaxPaths = 40ull << 20;
+            uint32_t band_rows = (uint32_t)std::max<uint64_t>(1, kMaxPaths / ((uint64_t)dp.width * epar));
+            band_rows = std::min(band_rows, dp.row_count);
+            const uint32_t max_paths = band_rows * dp.width * epar;
+            rc = ensure(ctx, &ctx->d_wf, &ctx->d_wf_bytes, wf_workspace_bytes(max_paths));
+            if (rc != B200RT_OK) return rc;
+            ctx->last_rounds = 0;
+            for (uint32_t r = 0; r < dp.row_count; r += band_rows) {
+                DParams band = dp;
+                band.row_begin = dp.row_begin + r;
+                band.row_count = std::min(band_rows, dp.row_count - r);
+                uint32_t rounds = 0;
+                CU(launch_distributed_wavefront(ctx->scene, dc, band, d_accum, ctx->d_cnt, ctx->d_wf,
+                                                band.row_count * dp.width * epar, epar, ctx->sm_count, ctx->h_poll,
+                                                ctx->ev_poll, st, &rounds));
+                ctx->last_rounds += rounds;
+            }
+        }
+    }
     CU(cudaEventRecord(ctx->ev1, st));
     return B200RT_OK;
 }

@@ -120,12 +120,13 @@ RT_DI void sphere_exact_test(float4 s, int32_t prim, const DRay& r, Best& best) 
 }
 
 // Winner-only work: barycentric normal / uv (main.rs:235-252) or sphere normal / uv (main.rs:305-313)
-RT_DI void finalize_hit(const DScene& sc, const Best& best, DHit& h) {
+RT_DI void finalize_hit(const DScene& sc, const Best& best, DHit& h, bool want_attrs = true) {
     h.prim = best.prim;
     if (best.prim < 0) return;
     h.face = best.bf;
     h.t = best.t;
     h.pos = best.pos;
+    if (!want_attrs) return;    // shadow rays: only "is there a hit, and how far" is used (main.rs:435-447)
     if ((uint32_t)best.prim < sc.n_tris) {
         const float4* ex = sc.tri_exact + 4 * (size_t)best.prim;
         const float4* at = sc.tri_attr + 4 * (size_t)best.prim;
@@ -216,7 +217,7 @@ RT_DI void filter_pair(const TriPair& c, float ox, float oy, float oz, float cf,
 constexpr float kCullK = 1099511627776.0f;   // 2^40
 
 struct CastStats {
-    unsigned long long casts, confirms, filter_steps;
+    unsigned long long casts, confirms, fallbacks;
 };
 
 // Per-warp shared-memory slot of the cast: 32 staged rays (2 float4 each) + the 32 x 64-bit candidate masks.
@@ -227,66 +228,69 @@ RT_DI uint2* cast_slot_masks(float4* s_rays) { return reinterpret_cast<uint2*>(s
 // base + i), merged into `best`.
 //
 // CERTIFIED SELECT.  The reference walks the candidates in index order through the exact test.  Here each
-// candidate first gets the filter's own cheap estimate t_i (|t_i - t_exact| <= delta_i = A/|nd|, the bound the
-// filter itself relies on) and is dropped when the exact test is CERTAIN to reject it: face culled or
-// excluded (sign of n.dir is certain for |nd| >= g), t_i + delta_i < 0, or t_i - delta_i > best.t.  The
-// nearest survivor w goes through the exact test; if it is accepted, becomes `best`, and every other
-// survivor j has t_j - delta_j > t_w (exact), the ordered walk would have ended with the same `best`
-// (the others lose on distance whatever their inside test says, ties are impossible) - ONE exact test
-// instead of one per candidate.  Anything else (w rejected, near tie, |nd| < g, untrusted ray) restores
-// `best` and takes the reference's ordered walk over all candidates.
+// candidate is first classified with a few instructions:
+//   * face culling and the exclusion (main.rs:185-200) depend only on the sign of n.dir, evaluated with the
+//     reference's own non-fused dot product: culled / excluded candidates are dropped, exactly as the walk would;
+//   * the filter's estimate t_i (|t_i - t_exact| <= delta_i = A/|nd|, the bound the filter itself relies on)
+//     drops candidates with t_i + delta_i < 0 (main.rs:205) or t_i - delta_i > best.t (main.rs:229-233);
+//   * near-parallel candidates (|nd| < g) have no usable estimate: set U.
+// Of the survivors only the one with the smallest lower bound, w, can be the nearest hit unless bounds overlap.
+// U and w go through the exact test in index order; if afterwards every other survivor j has
+// t_j - delta_j > best.t, the full ordered walk would have ended with the same `best`: those j lose the
+// strict distance test whatever their inside test says, and no tie with them is possible.  A NaN distance (ray
+// inside a triangle's plane, 0/0 at main.rs:204) makes the walk order-dependent (main.rs:229-231 accepts NaN),
+// so it, like any overlap of bounds, restores `best` and takes the reference's walk over all candidates.
 RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand, bool certify, const DRay& ray,
                         Best& best, CastStats& cs) {
     if (cand == 0ull) return;
     unsigned long long todo = cand;
     bool fast = false;
-    float lo2 = 0.0f;
-    int32_t w = -1;
+    float lo2 = CUDART_INF_F;
     if (certify) {
         float lo1 = CUDART_INF_F;
-        lo2 = CUDART_INF_F;
-        unsigned long long rem = cand;
-        bool ambiguous = false;
+        int32_t w = -1;
+        unsigned long long rem = cand, amb = 0ull;
 #pragma unroll 1
         while (rem) {
             const uint32_t i = (uint32_t)__ffsll((long long)rem) - 1u;
             rem &= rem - 1ull;
             const float4 q0 = sc.tri_exact[4 * (size_t)(base + i)];
+            const bool bf = dot(mk3(q0), ray.d) > 0.0f;                               // primitives.rs:45, exact
+            if ((bf && ray.face == kFront) || (!bf && ray.face == kBack)) continue;   // main.rs:185-188
+            if (excluded(ray, (int32_t)(base + i), bf)) continue;                     // main.rs:190-200
             const float nd = __fmaf_rn(q0.z, ray.d.z, __fmaf_rn(q0.y, ray.d.y, q0.x * ray.d.x));
-            if (!(fabsf(nd) >= sc.filter_g)) { ambiguous = true; break; }
-            const bool bf = nd > 0.0f;
-            if ((bf && ray.face == kFront) || (!bf && ray.face == kBack)) continue;   // main.rs:185-188, certain
-            if (excluded(ray, (int32_t)(base + i), bf)) continue;                     // main.rs:190-200, certain
+            if (!(fabsf(nd) >= sc.filter_g)) { amb |= 1ull << i; continue; }
             const float num = __fmaf_rn(q0.z, -ray.o.z, __fmaf_rn(q0.y, -ray.o.y, __fmaf_rn(q0.x, -ray.o.x, q0.w)));
             const float r = rcp_approx(nd);
             const float t = num * r, delta = sc.filter_A * fabsf(r);
             if (t + delta < 0.0f) continue;                                           // t_exact < 0, main.rs:205
             const float lo = t - delta;
-            if (best.prim >= 0 && lo > best.t) continue;                              // main.rs:229-233, certain
+            if (best.prim >= 0 && lo > best.t) continue;                              // main.rs:229-233
             if (lo < lo1) { lo2 = lo1; lo1 = lo; w = (int32_t)i; }
             else if (lo < lo2) lo2 = lo;
         }
-        if (!ambiguous) {
-            if (w < 0) return;                        // every candidate is certain to be rejected
-            fast = true;
-            todo = 1ull << w;
-        }
+        todo = amb | (w >= 0 ? (1ull << w) : 0ull);
+        if (todo == 0ull) return;                     // every candidate is certain to be rejected
+        fast = true;
     }
     const Best saved = best;
     for (;;) {
         cs.confirms += (unsigned long long)__popcll(todo);
+        bool nan_seen = false;
 #pragma unroll 1
         while (todo) {                                // increasing primitive index
             const uint32_t i = (uint32_t)__ffsll((long long)todo) - 1u;
             todo &= todo - 1ull;
             tri_exact_test(sc.tri_exact + 4 * (size_t)(base + i), (int32_t)(base + i), ray, best);
+            nan_seen |= best.t != best.t;
         }
         if (!fast) break;
-        // certified: w is the new best and everything else is strictly farther; or w was the only survivor
-        if (best.prim == (int32_t)(base + (uint32_t)w) ? (lo2 > best.t) : (lo2 == CUDART_INF_F)) break;
+        // certified: every survivor that was not tested is strictly farther than the nearest hit so far
+        if (!nan_seen && (lo2 == CUDART_INF_F || (best.prim >= 0 && lo2 > best.t))) break;
         best = saved;
         todo = cand;
         fast = false;
+        cs.fallbacks += 1ull;
     }
 }
 
@@ -294,7 +298,7 @@ RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand
 // s_rays: this warp's kCastSlotFloat4 staging slot in shared memory.  tile0: the lane's records of tile 0,
 // loaded once per kernel (scenes of <= 64 triangles never reload them).
 RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPair& tile0, uint32_t lane, bool active,
-                     const DRay& ray, DHit& hit, CastStats& cs) {
+                     const DRay& ray, DHit& hit, CastStats& cs, bool want_attrs = true) {
     const unsigned act = __ballot_sync(kFullMask, active);
     Best best;
     best_init(best);
@@ -342,7 +346,6 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
             const unsigned long long cand = ((unsigned long long)c_hi << 32) | (unsigned long long)c_lo;
             confirm_tile(sc, base, cand, trust, ray, best, cs);
         }
-        if (lane == 0u) cs.filter_steps += (unsigned long long)n_act;
         __syncwarp();   // masks (and, after the last tile, the ray slots) are free again
     }
     if (active) {
@@ -361,7 +364,7 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
             if (trust && d2 > bound) continue;
             sphere_exact_test(s4, (int32_t)(sc.n_tris + j), ray, best);
         }
-        finalize_hit(sc, best, hit);
+        finalize_hit(sc, best, hit, want_attrs);
         cs.casts += 1ull;
     } else {
         hit.prim = -1;

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(TraceCfg<MODE>::kThreads, TraceCfg<MODE>::kMin
 
     unsigned long long n_samples = 0ull;
     CastStats cs;
-    cs.casts = cs.confirms = cs.filter_steps = 0ull;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
     __shared__ float4 s_rays_all[kTraceWarps][kCastSlotFloat4];     // per-warp ray staging slot of the transposed filter
     float4* s_rays = s_rays_all[warp];
     TriPair tile0;                                     // this lane's two triangles of tile 0: register resident
@@ -545,14 +545,16 @@ __global__ void __launch_bounds__(TraceCfg<MODE>::kThreads, TraceCfg<MODE>::kMin
 
     // statistics: warp reduce, one atomic per warp
     if (cnt) {
-        unsigned long long n_casts = cs.casts, n_conf = cs.confirms;
+        unsigned long long n_casts = cs.casts, n_conf = cs.confirms, n_fb = cs.fallbacks;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             n_casts += __shfl_xor_sync(0xffffffffu, n_casts, o);
             n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+            n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
             n_samples += __shfl_xor_sync(0xffffffffu, n_samples, o);
         }
         if (lane == 0) {
+            if (n_fb) atomicAdd(&cnt->fallbacks, n_fb);
             atomicAdd(&cnt->casts, n_casts);
             atomicAdd(&cnt->tri_pairs, n_casts * sc.n_tris);
             atomicAdd(&cnt->sph_pairs, n_casts * sc.n_sph);
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(const DScene sc, const b
     if (CAST != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
     else zero_tripair(tile0);
     CastStats cs;
-    cs.casts = cs.confirms = cs.filter_steps = 0ull;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
     const bool active = i < n;
     DRay r;
     r.o = mk3(0.f, 0.f, 0.f); r.d = mk3(0.f, 0.f, 1.f); r.face = kFront; r.ex_prim = -1; r.ex_face = kFront;
@@ -600,13 +602,15 @@ __global__ void __launch_bounds__(128) intersect_kernel(const DScene sc, const b
         hits[i] = o;
     }
     if (cnt) {
-        unsigned long long n_casts = cs.casts, n_conf = cs.confirms;
+        unsigned long long n_casts = cs.casts, n_conf = cs.confirms, n_fb = cs.fallbacks;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             n_casts += __shfl_xor_sync(0xffffffffu, n_casts, o);
             n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+            n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
         }
         if (lane == 0u && n_casts) {
+            if (n_fb) atomicAdd(&cnt->fallbacks, n_fb);
             atomicAdd(&cnt->casts, n_casts);
             atomicAdd(&cnt->tri_pairs, n_casts * sc.n_tris);
             atomicAdd(&cnt->sph_pairs, n_casts * sc.n_sph);

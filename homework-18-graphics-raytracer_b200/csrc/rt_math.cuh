@@ -18,7 +18,7 @@ struct f2 { float x, y; };
 #define RT_DI __device__ __forceinline__
 // heavy leaf math (IEEE div/sqrt expansions, libm calls): ONE copy in the kernel, keeps the phase machine inside
 // the instruction cache (ncu: 70% of stalls were no_instruction when these were inlined at every site)
-#define RT_DN __device__ __noinline__
+#define RT_DN static __device__ __noinline__
 
 RT_DI f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
 RT_DI f3 mk3(const float* p) { return mk3(p[0], p[1], p[2]); }

@@ -84,7 +84,7 @@ struct DParams {
 };
 
 struct DCounters {  // device-side statistics, one 64-bit atomic per CTA at kernel end
-    unsigned long long casts, tri_pairs, sph_pairs, confirms, samples;
+    unsigned long long casts, tri_pairs, sph_pairs, confirms, samples, fallbacks;
 };
 
 constexpr int kTileTris = 64;  // triangles per shared-memory tile (64 x 64 B = 4 KB)

@@ -1,0 +1,665 @@
+// rt_wavefront.cu — the stochastic tracer (distributed_ray_trace, main.rs:521-614, driven by the epoch loop
+// main.rs:1129-1167) as a WAVEFRONT pipeline: every pixel sample is a path whose state lives in HBM, and the
+// frame advances in rounds of two kernels
+//
+//     wf_cast_kernel    World::cast (main.rs:180-326) for every ray requested in the previous round — the
+//                       warp-transposed FFMA2 filter + certified exact select of rt_cast.cuh with all 32
+//                       lanes of every warp carrying a ray (the FP32-roofline kernel of the render);
+//     wf_logic_kernel   everything between two casts (camera, get_shade, scatter, reflect / refract,
+//                       accumulation), run on queues that are binned by WHAT the finished cast was for
+//                       (primary / bounce / shadow rays / refraction step), so each warp executes one
+//                       branch of the reference's recursion with full lanes.
+//
+// The per-path transitions are the same ones, in the same arithmetic, as the phase machine of rt_kernels.cu
+// (trace_kernel<kModeDistributed>): with one epoch in flight per pixel both tracers produce bit-identical
+// {sum.rgb, count} accumulators.
+//
+// HBM layout (n = paths in flight = pixels of the rendered rows x epochs-in-flight `epar`).  Queues permute the
+// paths, so everything a path owns is ARRAY-OF-STRUCTS in whole 32-byte sectors: a lane that reads its path's
+// rows uses every byte of every sector it touches, however the queue ordered the paths.
+//   st  [n][12]  path state, float4 rows (see ROW_*)                                   192 B / path
+//   req [n][6]   {origin, meta}{direction} of the path ray + the directions of up to 4 shadow rays
+//                (a shadow ray's origin / exclusion is the current hit: ROW_HPOS)      96 B
+//   res [n][2]   result of the path ray {prim, meta, t, uv.x}{normal, uv.y}             32 B
+//   sres[n][4]   float2 {prim, t} per shadow ray                                        32 B
+//   q   [2][6][n] path ids per consumer segment (double buffered by round parity)       48 B
+//   work[2][4n]  cast work items (path << 3 | slot)                                     32 B
+#include <cuda_runtime.h>
+
+#include "rt_cast.cuh"
+#include "rt_shade.cuh"
+#include "rt_types.h"
+#include "rt_wavefront.h"
+
+namespace b200rt {
+
+namespace {
+
+// rows that are written together are neighbours, so every store pair fills one whole 32-byte sector
+enum : int {
+    ROW_CTRL = 0,     // flags, depth, rng draws, sample index (4 x u32)
+    ROW_RNG,          // Philox block of the sample stream
+    ROW_ACC,          // radiance of the sample so far
+    ROW_T,            // throughput: what a unit of radiance at the current hit adds to the sample
+    ROW_HPOS,         // hit.at.position, hit.index
+    ROW_HNORMAL,      // hit.at.normal, meta (face | ray_face << 1 | object << 8)
+    ROW_HDIR,         // hit.ray.direction (after scatter_hit), uv.x
+    ROW_HDIR0,        // hit.ray.direction before scatter_hit (view direction of the BRDF probes), uv.y
+    ROW_PEND,         // pending factor (BRDF probe value or decay^distance); w = get_refract travel distance
+    ROW_HI_POS,       // get_refract: previous inside hit position, retry count | get_shade: sum of earlier light chunks
+    ROW_SUM,          // this slot's PhotonAccumulator {sum.rgb, weight_sum} (photon.rs:9-12)
+    ROW_SPARE,
+    kStateRows
+};
+static_assert(kStateRows == WF_STATE_ROWS, "state rows");
+enum : int { REQ_O = 0, REQ_D = 1, REQ_SHADOW_D = 2 };
+
+// flags word of ROW_CTRL
+enum : uint32_t {
+    F_A_KNOWN = 1u << 0,
+    F_RAYTYPE_SHIFT = 1,        // 2 bits: RayType (main.rs:532): 0 diffuse, 1 reflection, 2 refraction
+    F_PURPOSE_SHIFT = 3,        // 2 bits: SH_FINAL / SH_NEXT_MIX / SH_NEXT_REFR
+    F_TIR = 1u << 5,            // refraction step in flight is a total-internal-reflection bounce (else the first inside ray)
+    F_NEED_SHIFT = 6,           // 4 bits: lights of the current chunk with a shadow ray in flight
+    F_LI0_SHIFT = 10,           // 12 bits: first light of the current chunk
+    F_PARTIAL = 1u << 22        // ROW_HI_POS holds the get_shade sum of earlier chunks
+};
+enum : uint32_t { SH_FINAL = 0, SH_NEXT_MIX = 1, SH_NEXT_REFR = 2 };
+
+enum : int { OUT_NONE = 0, OUT_PRIMARY, OUT_BOUNCE, OUT_REFR, OUT_SHADE, OUT_SHB, OUT_RETIRE };
+
+RT_DI float u2f(uint32_t v) { return __uint_as_float(v); }
+RT_DI uint32_t f2u(float v) { return __float_as_uint(v); }
+
+RT_DI uint32_t pack_ray_meta(uint32_t face, int32_t ex_prim, uint32_t ex_face) {
+    return face | (ex_face << 2) | ((uint32_t)(ex_prim + 1) << 4);
+}
+
+struct PathMem {
+    float4* st; float4* req; uint32_t pid;
+    RT_DI float4 ld(int row) const { return st[(size_t)pid * kStateRows + row]; }
+    RT_DI void sv(int row, float4 v) const { st[(size_t)pid * kStateRows + row] = v; }
+    RT_DI void put_ray(const DRay& r) const {
+        req[(size_t)pid * WF_REQ_ROWS + REQ_O] = make_float4(r.o.x, r.o.y, r.o.z, u2f(pack_ray_meta(r.face, r.ex_prim, r.ex_face)));
+        req[(size_t)pid * WF_REQ_ROWS + REQ_D] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+    }
+    RT_DI void get_ray(DRay& r) const {
+        const float4 a = req[(size_t)pid * WF_REQ_ROWS + REQ_O], b = req[(size_t)pid * WF_REQ_ROWS + REQ_D];
+        const uint32_t m = f2u(a.w);
+        r.o = mk3(a); r.d = mk3(b); r.face = m & 3u; r.ex_face = (m >> 2) & 3u; r.ex_prim = (int32_t)(m >> 4) - 1;
+    }
+    RT_DI void put_shadow_dir(uint32_t s, f3 d) const { req[(size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + s] = make_float4(d.x, d.y, d.z, 0.0f); }
+    // shadow ray of light slot s (main.rs:423-431): from the current hit, back faces only, the hit primitive excluded
+    RT_DI void get_shadow_ray(uint32_t s, DRay& r) const {
+        const float4 a = ld(ROW_HPOS), b = req[(size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + s];
+        r.o = mk3(a); r.d = mk3(b); r.face = kBack; r.ex_prim = __float_as_int(a.w); r.ex_face = kBack;
+    }
+};
+
+}  // namespace
+
+// ---- cast --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 4) wf_cast_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf,
+                                                         DCounters* __restrict__ cnt) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    __shared__ float4 s_rays_all[4][kCastSlotFloat4];
+    float4* s_rays = s_rays_all[warp];
+    // the counters the logic kernel of this round appends to
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
+    const uint32_t n_work = wb.ctl->c[buf].work;
+    if (n_work == 0u) return;
+    TriPair tile0;
+    if (sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
+    else {
+        const float2 z = make_float2(0.f, 0.f);
+        tile0.nx = tile0.ny = tile0.nz = tile0.d = tile0.m0x = tile0.m0y = tile0.m0z = tile0.w0 = tile0.m1x = tile0.m1y = tile0.m1z =
+            tile0.w1 = tile0.m2x = tile0.m2y = tile0.m2z = tile0.w2 = z;
+    }
+    const uint32_t* __restrict__ work = wb.work + (size_t)buf * 4u * wb.n;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    const uint32_t stride = gridDim.x * 4u * 32u;
+    // software pipeline: the work item and ray of the NEXT chunk are fetched before the current chunk's filter loop
+    // (a dependent chain work[] -> path -> ray rows of ~2 us that 4 warps per sub-partition cannot hide)
+    auto fetch = [&](uint32_t idx, uint32_t& item, DRay& r) {
+        r.o = mk3(0.f, 0.f, 0.f); r.d = mk3(0.f, 0.f, 1.f); r.face = kFront; r.ex_prim = -1; r.ex_face = kFront;
+        item = 0u;
+        if (idx < n_work) {
+            item = work[idx];
+            const PathMem pm{wb.st, wb.req, item >> 3};
+            if ((item & 7u) == 0u) pm.get_ray(r);
+            else pm.get_shadow_ray((item & 7u) - 1u, r);
+        }
+    };
+    uint32_t base = (blockIdx.x * 4u + warp) * 32u;
+    uint32_t item_next;
+    DRay r_next;
+    fetch(base + lane, item_next, r_next);
+    for (; base < n_work; base += stride) {
+        const bool active = base + lane < n_work;
+        const uint32_t item = item_next;
+        const DRay r = r_next;
+        fetch(base + stride + lane, item_next, r_next);
+        const uint32_t pid = item >> 3, slot = item & 7u;
+        DHit h;
+        h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
+        warp_cast(sc, s_rays, tile0, lane, active, r, h, cs, slot == 0u);
+        if (active) {
+            if (slot == 0u) {
+                const uint32_t meta = h.prim >= 0 ? (h.face | (h.object << 8)) : 0u;
+                wb.res[(size_t)pid * 2u + 0u] = make_float4(__int_as_float(h.prim), u2f(meta), h.t, h.uv.x);
+                wb.res[(size_t)pid * 2u + 1u] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.uv.y);
+            } else {
+                wb.sres[(size_t)pid * 4u + (slot - 1u)] = make_float2(__int_as_float(h.prim), h.t);
+            }
+        }
+    }
+    if (cnt) {
+        unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+            n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
+        }
+        if (lane == 0u && n_conf) atomicAdd(&cnt->confirms, n_conf);
+        if (lane == 0u && n_fb) atomicAdd(&cnt->fallbacks, n_fb);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicAdd(&cnt->casts, (unsigned long long)n_work);
+            atomicAdd(&cnt->tri_pairs, (unsigned long long)n_work * sc.n_tris);
+            atomicAdd(&cnt->sph_pairs, (unsigned long long)n_work * sc.n_sph);
+        }
+    }
+}
+
+// ---- logic -------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256, WF_LOGIC_MIN_BLOCKS) wf_logic_kernel(const DScene sc, const DCamera cam, const DParams p,
+                                                          const WfBuffers wb, const uint32_t buf, const uint32_t init,
+                                                          DCounters* __restrict__ cnt) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nbuf = buf ^ 1u;
+    uint32_t n_seg[WF_SEG_COUNT], chunks[WF_SEG_COUNT], total_chunks = 0u;
+#pragma unroll
+    for (int s = 0; s < WF_SEG_COUNT; ++s) {
+        n_seg[s] = init ? (s == WF_SEG_INIT ? wb.n : 0u) : (s == WF_SEG_INIT ? 0u : wb.ctl->c[buf].seg[s]);
+        chunks[s] = (n_seg[s] + 31u) >> 5;
+        total_chunks += chunks[s];
+    }
+    const f3 cam_toward = mk3(cam.toward), cam_x = mk3(cam.x), cam_y = mk3(cam.y);
+    const uint32_t n_epochs = p.epoch_count;
+    unsigned long long n_samples = 0ull;
+
+    for (uint32_t chunk = gw; chunk < total_chunks; chunk += n_warps) {
+        int seg = 0;
+        uint32_t c = chunk;
+#pragma unroll
+        for (int s = 0; s < WF_SEG_COUNT - 1; ++s)
+            if (seg == s && c >= chunks[s]) { c -= chunks[s]; seg = s + 1; }
+        const uint32_t k = c * 32u + lane;
+        const bool valid = k < n_seg[seg];
+        const uint32_t pid = !valid ? 0u : (seg == WF_SEG_INIT ? k : wb.q[((size_t)buf * WF_SEG_COUNT + seg) * wb.n + k]);
+        const PathMem pm{wb.st, wb.req, pid};
+
+        // ---- per-path registers (the names of trace_kernel) --------------------------------------------------
+        f3 acc = mk3(0.f, 0.f, 0.f), T = mk3(1.f, 1.f, 1.f), a_shade = mk3(0.f, 0.f, 0.f);
+        int32_t depth = 0;
+        uint32_t flags = 0u, sample_idx = 0u;
+        Rng rng;
+        rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.x = rng.y = rng.epoch = rng.draws = 0u; rng.b[0] = rng.b[1] = rng.b[2] = rng.b[3] = 0u;
+        DHit h;
+        h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = mk3(0.f, 0.f, 0.f); h.normal = mk3(0.f, 0.f, 1.f); h.uv.x = h.uv.y = 0.f;
+        f3 h_dir = mk3(0.f, 0.f, 1.f), h_dir_orig = h_dir, pend = mk3(0.f, 0.f, 0.f);
+        float rf_travel = 0.0f;
+        uint32_t h_rayface = kFront;
+        f3 shade = mk3(0.f, 0.f, 0.f);
+        bool do_level = false, do_shade_begin = false, do_finish = false;
+        bool w_hit = false, w_dirs = false, w_acc = false, w_pend = false, w_rng = false;   // rows to write back
+        int out = OUT_NONE;
+        DRay ray;
+        ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.face = kFront; ray.ex_prim = -1; ray.ex_face = kFront;
+
+        // pixel of this path: slot e_lane of pixel pix renders samples e_lane, e_lane + epar, ...
+        const uint32_t pix = pid % wb.n_pixels, e_lane = pid / wb.n_pixels;
+        const uint32_t px = pix % p.width, py = p.row_begin + pix / p.width;
+
+        // ---- load: only the rows this segment reads -----------------------------------------------------------------
+        if (valid && seg != WF_SEG_INIT) {
+            const float4 r0 = pm.ld(ROW_CTRL);
+            flags = f2u(r0.x); depth = __float_as_int(r0.y); rng.draws = f2u(r0.z); sample_idx = f2u(r0.w);
+            rng.x = px; rng.y = py; rng.epoch = p.epoch_begin + sample_idx;
+            if (seg != WF_SEG_PRIMARY) {
+                const float4 r5 = pm.ld(ROW_HPOS), r6 = pm.ld(ROW_HNORMAL), r7 = pm.ld(ROW_HDIR), r8 = pm.ld(ROW_HDIR0);
+                h.pos = mk3(r5); h.prim = __float_as_int(r5.w);
+                h.normal = mk3(r6);
+                const uint32_t meta = f2u(r6.w);
+                h.face = meta & 1u; h_rayface = (meta >> 1) & 3u; h.object = meta >> 8;
+                h_dir = mk3(r7); h.uv.x = r7.w;
+                h_dir_orig = mk3(r8); h.uv.y = r8.w;
+            }
+            if (seg == WF_SEG_SHADE) {
+                acc = mk3(pm.ld(ROW_ACC)); T = mk3(pm.ld(ROW_T));
+            }
+            if (seg == WF_SEG_SHADE || seg == WF_SEG_BOUNCE || seg == WF_SEG_REFR) {
+                const float4 r4 = pm.ld(ROW_PEND);
+                pend = mk3(r4); rf_travel = r4.w;
+            }
+            if (seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE) {
+                const float4 r = pm.ld(ROW_RNG);
+                rng.b[0] = f2u(r.x); rng.b[1] = f2u(r.y); rng.b[2] = f2u(r.z); rng.b[3] = f2u(r.w);
+            }
+        }
+
+        // ---- consume the finished cast(s) ----------------------------------------------------------------------------
+        if (seg == WF_SEG_INIT) {
+            do_finish = valid;
+        } else if (seg == WF_SEG_PRIMARY || seg == WF_SEG_BOUNCE) {
+            if (valid) {
+                pm.get_ray(ray);
+                const float4 a = wb.res[(size_t)pid * 2u], b = wb.res[(size_t)pid * 2u + 1u];
+                DHit hc;
+                hc.prim = __float_as_int(a.x);
+                const uint32_t meta = f2u(a.y);
+                hc.face = meta & 1u; hc.object = meta >> 8; hc.t = a.z;
+                hc.pos = ray.o + ray.d * hc.t;                                         // main.rs:210 / 304
+                hc.normal = mk3(b); hc.uv.x = a.w; hc.uv.y = b.w;
+                const bool hit = hc.prim >= 0;
+                if (seg == WF_SEG_PRIMARY) {                                           // main.rs:1150-1155
+                    // a fresh sample: acc = 0, T = 1 (set when the sample was opened; not stored until they change)
+                    w_acc = true;
+                    if (!hit) do_finish = true;
+                    else { h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face; w_hit = true; w_dirs = true; do_level = true; }
+                } else {                                                               // main.rs:564-574 / 583-593 / 603-608
+                    const uint32_t ray_type = (flags >> F_RAYTYPE_SHIFT) & 3u;
+                    if (!hit) {
+                        if (ray_type == 2u) { acc = mk3(pm.ld(ROW_ACC)); do_finish = true; }                 // main.rs:606-608
+                        else { flags = (flags & ~(3u << F_PURPOSE_SHIFT)) | (SH_FINAL << F_PURPOSE_SHIFT); do_shade_begin = true; }
+                    } else {
+                        // probe / decay of the CURRENT material, before the hit is replaced
+                        const MatEval mat = material_approx(sc.materials, h.object, h.uv);
+                        uint32_t purpose;
+                        if (ray_type == 2u) {
+                            pend = mk3(nl_powf(mat.opaque_decay, rf_travel), 0.f, 0.f);
+                            purpose = SH_NEXT_REFR;
+                        } else {
+                            pend = ray_type == 0u ? get_diffuse(mat, h.normal, ray.d)                    // main.rs:566-570
+                                                  : get_specular(mat, h.normal, -h_dir_orig, ray.d);     // main.rs:585-589
+                            purpose = SH_NEXT_MIX;
+                        }
+                        w_pend = true;
+                        flags = (flags & ~(3u << F_PURPOSE_SHIFT)) | (purpose << F_PURPOSE_SHIFT);
+                        h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face; w_hit = true; w_dirs = true;
+                        do_shade_begin = true;
+                    }
+                }
+            }
+        } else if (seg == WF_SEG_SHB) {
+            do_shade_begin = valid;
+        } else if (seg == WF_SEG_REFR) {                                               // main.rs:371-402
+            if (valid) {
+                pm.get_ray(ray);
+                const float4 a = wb.res[(size_t)pid * 2u], b = wb.res[(size_t)pid * 2u + 1u];
+                const int32_t hprim = __float_as_int(a.x);
+                if (hprim < 0) { acc = mk3(pm.ld(ROW_ACC)); do_finish = true; }        // Infinite
+                else {
+                    const uint32_t meta = f2u(a.y);
+                    const uint32_t hi_face = meta & 1u;
+                    const f3 hi_pos = ray.o + ray.d * a.z, hi_normal = mk3(b);
+                    uint32_t rf_retry;
+                    if (!(flags & F_TIR)) { rf_travel = distance(hi_pos, h.pos); rf_retry = 0u; }       // main.rs:375
+                    else {
+                        const float4 prev = pm.ld(ROW_HI_POS);
+                        rf_travel = rf_travel + distance(mk3(prev), hi_pos);                            // main.rs:385
+                        rf_retry = f2u(prev.w) + 1u;                                                    // main.rs:387
+                    }
+                    const float rf_k = sc.materials[h.object].refraction_index;
+                    f3 rout;
+                    const bool have_out = refract_dir(hi_normal, ray.d, 1.0f / rf_k, rout);             // main.rs:376 / 386
+                    if (!have_out && rf_travel <= p.refract_max_distance && rf_retry < p.tir_retries) {  // main.rs:378
+                        pm.sv(ROW_HI_POS, make_float4(hi_pos.x, hi_pos.y, hi_pos.z, u2f(rf_retry)));
+                        ray = make_reflect(hi_pos, hi_normal, ray.d, ray.face, hprim, hi_face);         // main.rs:379-381
+                        flags |= F_TIR;
+                        w_pend = true;
+                        out = OUT_REFR;
+                    } else if (!have_out) {
+                        acc = mk3(pm.ld(ROW_ACC)); do_finish = true;                   // Trapped
+                    } else {                                                           // main.rs:392-402, then 603
+                        DRay e;
+                        e.o = hi_pos; e.d = normalize(rout); e.face = kFront; e.ex_prim = hprim; e.ex_face = kBack;
+                        ray = e;
+                        w_pend = true;
+                        out = OUT_BOUNCE;
+                    }
+                }
+            }
+        } else {   // WF_SEG_SHADE: the shadow rays of the current light chunk are back (main.rs:435-461)
+            if (valid) {
+                const MatEval mat = material_approx(sc.materials, h.object, h.uv);
+                const f3 nadj = adjust_normal(mat, h.normal);
+                const uint32_t li0 = (flags >> F_LI0_SHIFT) & 0xfffu, need = (flags >> F_NEED_SHIFT) & 15u;
+                if (flags & F_PARTIAL) shade = mk3(pm.ld(ROW_HI_POS));
+#pragma unroll 1
+                for (uint32_t s = 0; s < 4u; ++s) {
+                    if (!((need >> s) & 1u)) continue;
+                    DirLight L;
+                    approx_light(sc.lights[li0 + s], h.pos, L);
+                    const float2 sr = wb.sres[(size_t)pid * 4u + s];
+                    bool occluded = false;
+                    if (__float_as_int(sr.x) >= 0) {
+                        if (L.has_origin) {
+                            const f3 occ = h.pos + (-L.dir) * sr.y;                    // the shadow ray's hit point
+                            if (distance(h.pos, occ) < distance(h.pos, L.origin)) occluded = true;
+                        } else occluded = true;
+                    }
+                    if (!occluded) {
+                        const f3 view = -h_dir, ldir = -L.dir;
+                        const f3 diffuse = get_diffuse(mat, nadj, ldir) * L.color;         // main.rs:458
+                        const f3 specular = get_specular(mat, nadj, view, ldir) * L.color; // main.rs:459
+                        shade = shade + diffuse * (1.0f - mat.shiness) + specular * mat.shiness;  // main.rs:461
+                    }
+                }
+                if (li0 + 4u < sc.n_lights) {     // more lights: next chunk
+                    pm.sv(ROW_HI_POS, make_float4(shade.x, shade.y, shade.z, 0.f));
+                    flags = (flags & ~((0xfffu << F_LI0_SHIFT) | (15u << F_NEED_SHIFT))) | ((li0 + 4u) << F_LI0_SHIFT) | F_PARTIAL;
+                    do_shade_begin = true;
+                } else {
+                    const uint32_t purpose = (flags >> F_PURPOSE_SHIFT) & 3u;
+                    w_acc = true;
+                    if (purpose == SH_FINAL) {
+                        acc = acc + T * shade;
+                        do_finish = true;
+                    } else if (purpose == SH_NEXT_MIX) {
+                        // mix(get_shade(next), x*probe, 0.5) = a + (x*probe - a)*0.5   (main.rs:571, 590)
+                        acc = acc + T * (shade - shade * 0.5f);
+                        T = T * (pend * 0.5f);
+                        a_shade = shade; flags |= F_A_KNOWN; depth -= 1;
+                        do_level = true;
+                    } else {
+                        // (x + get_shade(next)) * decay^distance   (main.rs:605)
+                        acc = acc + T * (shade * pend.x);
+                        T = T * pend.x;
+                        a_shade = shade; flags |= F_A_KNOWN; depth -= 1;
+                        do_level = true;
+                    }
+                }
+            }
+        }
+
+        // ---- top of distributed_ray_trace for the current hit (main.rs:521-554), then the bounce ray ---------------------
+        if (seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE) {
+            if (do_level) {
+                if (depth <= 0) {
+                    if (flags & F_A_KNOWN) { acc = acc + T * a_shade; do_finish = true; }    // main.rs:525-527
+                    else {                                                                    // depth 0 at the primary hit
+                        flags = (flags & ~(3u << F_PURPOSE_SHIFT)) | (SH_FINAL << F_PURPOSE_SHIFT);
+                        out = OUT_SHB;
+                    }
+                } else {
+                    const MatEval mat = material_approx(sc.materials, h.object, h.uv);
+                    const float w0 = (1.0f - mat.shiness) * (1.0f - mat.transparency);
+                    const float w1 = mat.shiness * (1.0f - mat.transparency);
+                    const float w2 = mat.transparency;
+                    // weighted_select, main.rs:652-666
+                    const float wsum = (w0 + w1) + w2;
+                    const float rsel = rng_range(rng, 0.0f, wsum);
+                    float accum = 0.0f;
+                    accum += w0;
+                    uint32_t ray_type;
+                    if (rsel < accum) ray_type = 0u;
+                    else { accum += w1; ray_type = rsel < accum ? 1u : 2u; }
+                    // scatter_hit, main.rs:539-554
+                    const f3 base_dir = ray_type == 0u ? -h.normal : h_dir;
+                    const float exponent = ray_type == 0u ? 1.0f : mat.smoothness;
+                    const float phi = nl_acosf(nl_powf(1.0f - rng_range(rng, 0.0f, 1.0f), exponent));
+                    const float theta = rng_range(rng, -kPi, kPi);
+                    const quat from_z = from_arc(mk3(0.0f, 0.0f, 1.0f), normalize(base_dir));
+                    const float2 scp = nl_sincosf(phi), sct = nl_sincosf(theta);
+                    const f3 new_dir = rotate(from_z, mk3(scp.x * sct.y, scp.x * sct.x, scp.y));
+                    h_dir_orig = h_dir;
+                    h_dir = new_dir;                                                   // main.rs:552
+                    w_dirs = true; w_rng = true;
+                    flags = (flags & ~((3u << F_RAYTYPE_SHIFT) | F_TIR)) | (ray_type << F_RAYTYPE_SHIFT);
+                    const float cosine = -dot(h.normal, h_dir);                        // main.rs:559 / 578 / 597
+                    if (cosine <= 0.0f) do_finish = true;                              // black
+                    else if (ray_type == 2u) {                                         // get_refract, main.rs:354-368
+                        f3 rin;
+                        if (refract_dir(h.normal, h_dir, mat.refraction_index, rin)) {
+                            ray.o = h.pos; ray.d = normalize(rin); ray.face = kBack; ray.ex_prim = h.prim; ray.ex_face = kFront;
+                            out = OUT_REFR;
+                        } else do_finish = true;                                       // Trapped
+                    } else {
+                        ray = make_reflect(h.pos, h.normal, h_dir, h_rayface, h.prim, h.face);   // main.rs:563 / 582
+                        out = OUT_BOUNCE;
+                    }
+                }
+            }
+        }
+
+        // ---- get_shade entry (main.rs:408-433): shadow rays of the next chunk of up to 4 lights ------------------------
+        uint32_t n_shadow = 0u;
+        if (seg == WF_SEG_BOUNCE || seg == WF_SEG_SHB || seg == WF_SEG_SHADE) {
+            if (do_shade_begin) {
+                const MatEval mat = material_approx(sc.materials, h.object, h.uv);
+                const f3 nadj = adjust_normal(mat, h.normal);
+                uint32_t li0 = (seg == WF_SEG_SHADE) ? ((flags >> F_LI0_SHIFT) & 0xfffu) : 0u;
+                if (seg != WF_SEG_SHADE) flags &= ~F_PARTIAL;
+                uint32_t need = 0u;
+                // chunks without any shadow ray are skipped here (their lights contribute nothing, main.rs:418-421)
+                for (;;) {
+#pragma unroll 1
+                    for (uint32_t s = 0; s < 4u && li0 + s < sc.n_lights; ++s) {
+                        DirLight L;
+                        if (!approx_light(sc.lights[li0 + s], h.pos, L)) continue;
+                        const float cosine = -dot(L.dir, nadj);                        // main.rs:420
+                        if (cosine <= 0.0f) continue;
+                        pm.put_shadow_dir(s, -L.dir);                                  // main.rs:423-431
+                        need |= 1u << s;
+                    }
+                    if (need || li0 + 4u >= sc.n_lights) break;
+                    li0 += 4u;
+                }
+                if (need & 0x3u) { if (!(need & 1u)) pm.put_shadow_dir(0, mk3(0.f, 0.f, 0.f)); if (!(need & 2u)) pm.put_shadow_dir(1, mk3(0.f, 0.f, 0.f)); }   // whole sectors
+                if (need & 0xcu) { if (!(need & 4u)) pm.put_shadow_dir(2, mk3(0.f, 0.f, 0.f)); if (!(need & 8u)) pm.put_shadow_dir(3, mk3(0.f, 0.f, 0.f)); }
+                flags = (flags & ~((0xfffu << F_LI0_SHIFT) | (15u << F_NEED_SHIFT))) | (li0 << F_LI0_SHIFT) | (need << F_NEED_SHIFT);
+                n_shadow = (uint32_t)__popc(need);
+                out = OUT_SHADE;      // with need == 0 the path passes through the SHADE segment of the next round with no cast
+            }
+        }
+
+        // ---- close the sample and open the next one (main.rs:1133-1166; photon.rs:28-33) ------------------------------------
+        if (__any_sync(kFullMask, do_finish)) {
+            if (do_finish) {
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (seg != WF_SEG_INIT) {
+                    sum = pm.ld(ROW_SUM);
+                    if (is_normal_f32(acc.x) && is_normal_f32(acc.y) && is_normal_f32(acc.z)) {   // main.rs:1157-1160
+                        sum.x += acc.x; sum.y += acc.y; sum.z += acc.z; sum.w += 1.0f;            // photon.rs:30-31
+                        n_samples += 1ull;
+                        pm.sv(ROW_SUM, sum);
+                    }
+                    sample_idx += wb.epar;
+                } else {
+                    sample_idx = e_lane;
+                    pm.sv(ROW_SUM, sum);
+                }
+                if (sample_idx >= n_epochs) out = OUT_RETIRE;
+                else {
+                    acc = mk3(0.f, 0.f, 0.f); T = mk3(1.f, 1.f, 1.f); depth = p.depth; flags = 0u;
+                    w_acc = false; w_hit = false; w_dirs = false; w_pend = false;
+                    // Camera::shoot_focus, main.rs:101-127 (Box-Muller on two stream uniforms)
+                    float clip_x, clip_y;
+                    clip_y = ((float)p.height / 2.0f - (float)py) / (float)p.height;   // main.rs:1094
+                    clip_x = ((float)px - (float)p.width / 2.0f) / (float)p.height;    // main.rs:1095
+                    const f3 pinhole_dir = normalize(clip_x * cam_x + clip_y * cam_y + cam_toward);   // main.rs:110
+                    rng_init(rng, p.seed_lo, p.seed_hi, py, px, p.epoch_begin + sample_idx);
+                    const float u1 = 1.0f - rng_uniform(rng);
+                    const float u2 = rng_uniform(rng);
+                    const float radius = sqrtf(-2.0f * nl_logf(u1));
+                    const float ang = 2.0f * kPi * u2;
+                    const float2 sca = nl_sincosf(ang);
+                    const float xoffset = p.blur * (radius * sca.y);
+                    const float yoffset = p.blur * (radius * sca.x);
+                    ray.d = normalize(pinhole_dir * p.focus + cam_x * xoffset + cam_y * yoffset);        // main.rs:115-117
+                    ray.o = mk3(cam.center) + normalize(cam_toward) * cam.near - (cam_x * xoffset + cam_y * yoffset);  // :118-120
+                    ray.face = kFront; ray.ex_prim = -1; ray.ex_face = kFront;
+                    w_rng = true;
+                    out = OUT_PRIMARY;
+                }
+            }
+        }
+
+        // ---- store what changed and append the path to the next round's queues -------------------------------------------
+        if (valid && out != OUT_RETIRE) {
+            pm.sv(ROW_CTRL, make_float4(u2f(flags), __int_as_float(depth), u2f(rng.draws), u2f(sample_idx)));
+            if (w_acc) { pm.sv(ROW_ACC, make_float4(acc.x, acc.y, acc.z, 0.f)); pm.sv(ROW_T, make_float4(T.x, T.y, T.z, 0.f)); }
+            if (w_pend) pm.sv(ROW_PEND, make_float4(pend.x, pend.y, pend.z, rf_travel));
+            if (w_hit) {
+                pm.sv(ROW_HPOS, make_float4(h.pos.x, h.pos.y, h.pos.z, __int_as_float(h.prim)));
+                pm.sv(ROW_HNORMAL, make_float4(h.normal.x, h.normal.y, h.normal.z, u2f(h.face | (h_rayface << 1) | (h.object << 8))));
+            }
+            if (w_dirs) {
+                pm.sv(ROW_HDIR, make_float4(h_dir.x, h_dir.y, h_dir.z, h.uv.x));
+                pm.sv(ROW_HDIR0, make_float4(h_dir_orig.x, h_dir_orig.y, h_dir_orig.z, h.uv.y));
+            }
+            if (w_rng) pm.sv(ROW_RNG, make_float4(u2f(rng.b[0]), u2f(rng.b[1]), u2f(rng.b[2]), u2f(rng.b[3])));
+            if (out == OUT_PRIMARY || out == OUT_BOUNCE || out == OUT_REFR) pm.put_ray(ray);
+        }
+        // ---- route: every reservation of this chunk (5 queues, the cast work list, the retired counter) is one
+        // atomic issued by a different lane, so the warp pays one round trip to L2 instead of seven
+        {
+            const bool path_ray = out == OUT_PRIMARY || out == OUT_BOUNCE || out == OUT_REFR;
+            const uint32_t n_items = !valid ? 0u : (path_ray ? 1u : (out == OUT_SHADE ? n_shadow : 0u));
+            uint32_t incl = n_items;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(kFullMask, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+            const int my_seg = out == OUT_PRIMARY ? WF_SEG_PRIMARY : out == OUT_BOUNCE ? WF_SEG_BOUNCE : out == OUT_REFR ? WF_SEG_REFR
+                             : out == OUT_SHADE ? WF_SEG_SHADE : out == OUT_SHB ? WF_SEG_SHB : 0;   // 0 = none (INIT is never a target)
+            unsigned m_seg[WF_SEG_COUNT];
+#pragma unroll
+            for (int sgi = 1; sgi < WF_SEG_COUNT; ++sgi) m_seg[sgi] = __ballot_sync(kFullMask, valid && my_seg == sgi);
+            const unsigned m_ret = __ballot_sync(kFullMask, valid && out == OUT_RETIRE);
+            uint32_t my_n = 0u;
+            uint32_t* my_addr = nullptr;
+#pragma unroll
+            for (int sgi = 1; sgi < WF_SEG_COUNT; ++sgi)
+                if ((int)lane == sgi) { my_n = (uint32_t)__popc(m_seg[sgi]); my_addr = &wb.ctl->c[nbuf].seg[sgi]; }
+            if (lane == 0u) { my_n = total; my_addr = &wb.ctl->c[nbuf].work; }
+            if (lane == (uint32_t)WF_SEG_COUNT) { my_n = (uint32_t)__popc(m_ret); my_addr = &wb.ctl->retired; }
+            uint32_t my_base = 0u;
+            if (my_n) my_base = atomicAdd(my_addr, my_n);
+            uint32_t seg_base = 0u;
+            unsigned seg_mask = 0u;
+#pragma unroll
+            for (int sgi = 1; sgi < WF_SEG_COUNT; ++sgi) {
+                const uint32_t bse = __shfl_sync(kFullMask, my_base, sgi);
+                if (my_seg == sgi) { seg_base = bse; seg_mask = m_seg[sgi]; }
+            }
+            const uint32_t work_base = __shfl_sync(kFullMask, my_base, 0) + (incl - n_items);
+            if (valid && my_seg != 0)
+                wb.q[((size_t)nbuf * WF_SEG_COUNT + my_seg) * wb.n + seg_base + (uint32_t)__popc(seg_mask & ((1u << lane) - 1u))] = pid;
+            uint32_t* w = wb.work + (size_t)nbuf * 4u * wb.n;
+            if (n_items) {
+                if (path_ray) w[work_base] = pid << 3;
+                else {
+                    const uint32_t need = (flags >> F_NEED_SHIFT) & 15u;
+                    uint32_t at = work_base;
+#pragma unroll
+                    for (uint32_t sl = 0; sl < 4u; ++sl)
+                        if ((need >> sl) & 1u) w[at++] = (pid << 3) | (sl + 1u);
+                }
+            }
+        }
+    }
+    if (cnt) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_samples += __shfl_xor_sync(0xffffffffu, n_samples, o);
+        if (lane == 0u && n_samples) atomicAdd(&cnt->samples, n_samples);
+    }
+}
+
+// accum[pixel] += the PhotonAccumulators of the pixel's slots, in slot order (photon.rs:28-33)
+__global__ void wf_combine_kernel(const WfBuffers wb, const DParams p, float4* __restrict__ accum) {
+    const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= wb.n_pixels) return;
+    float4 s = wb.st[(size_t)pix * kStateRows + ROW_SUM];
+    for (uint32_t e = 1; e < wb.epar; ++e) {
+        const float4 v = wb.st[((size_t)e * wb.n_pixels + pix) * kStateRows + ROW_SUM];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const size_t at = (size_t)(p.row_begin + pix / p.width) * p.width + pix % p.width;
+    float4 v = accum[at];
+    v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+    accum[at] = v;
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+size_t wf_workspace_bytes(uint32_t n_paths) {
+    const size_t n = n_paths;
+    return sizeof(WfControl) + 256 + n * ((size_t)kStateRows * 16 + WF_REQ_ROWS * 16 + 32 + 32 + 2 * WF_SEG_COUNT * 4 + 2 * 4 * 4) + 16 * 64;
+}
+
+uint32_t wf_epochs_in_flight(uint32_t width, uint32_t height, uint32_t epoch_count) {
+    // a function of the FRAME (not of the rendered row band), so that bands are bitwise the same rows of the full frame
+    const unsigned long long px = (unsigned long long)width * height;
+    unsigned long long e = (8ull << 20) / (px ? px : 1ull);     // aim at >= 8 Mi paths in flight
+    if (e < 1ull) e = 1ull;
+    if (e > 8ull) e = 8ull;
+    if (e > epoch_count) e = epoch_count ? epoch_count : 1u;
+    return (uint32_t)e;
+}
+
+static WfBuffers wf_carve(void* workspace, uint32_t n_paths, uint32_t n_pixels, uint32_t epar) {
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    unsigned char* b = static_cast<unsigned char*>(workspace);
+    const size_t n = n_paths;
+    WfBuffers wb;
+    size_t off = 0;
+    wb.ctl = reinterpret_cast<WfControl*>(b + off);            off = align(off + sizeof(WfControl));
+    wb.st = reinterpret_cast<float4*>(b + off);                off = align(off + n * kStateRows * 16);
+    wb.req = reinterpret_cast<float4*>(b + off);               off = align(off + n * WF_REQ_ROWS * 16);
+    wb.res = reinterpret_cast<float4*>(b + off);               off = align(off + n * 32);
+    wb.sres = reinterpret_cast<float2*>(b + off);              off = align(off + n * 32);
+    wb.q = reinterpret_cast<uint32_t*>(b + off);               off = align(off + n * 2 * WF_SEG_COUNT * 4);
+    wb.work = reinterpret_cast<uint32_t*>(b + off);            off = align(off + n * 2 * 4 * 4);
+    wb.n = n_paths; wb.n_pixels = n_pixels; wb.epar = epar;
+    return wb;
+}
+
+cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, const DParams& p, float* d_accum,
+                                         DCounters* d_cnt, void* workspace, uint32_t n_paths, uint32_t epar, int sm_count,
+                                         uint32_t* h_pinned_retired, cudaEvent_t ev_poll, cudaStream_t stream,
+                                         uint32_t* rounds_out) {
+    const uint32_t n_pixels = p.width * p.row_count;
+    const WfBuffers wb = wf_carve(workspace, n_paths, n_pixels, epar);
+    cudaError_t e = cudaMemsetAsync(wb.ctl, 0, sizeof(WfControl), stream);
+    if (e != cudaSuccess) return e;
+    const int cast_blocks = sm_count * 4, logic_blocks = sm_count * 2;
+    // round 0: every slot opens its first sample
+    wf_logic_kernel<<<logic_blocks, 256, 0, stream>>>(sc, cam, p, wb, 1u, 1u, d_cnt);
+    uint32_t round = 0, buf = 0;
+    uint32_t group = 8;
+    for (;;) {
+        for (uint32_t g = 0; g < group; ++g, ++round, buf ^= 1u) {
+            wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+            wf_logic_kernel<<<logic_blocks, 256, 0, stream>>>(sc, cam, p, wb, buf, 0u, d_cnt);
+        }
+        e = cudaMemcpyAsync(h_pinned_retired, &wb.ctl->retired, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(ev_poll, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaEventSynchronize(ev_poll);
+        if (e != cudaSuccess) return e;
+        if (*h_pinned_retired >= n_paths) break;
+        if (group < 64) group *= 2;
+        if (round > (1u << 21)) return cudaErrorLaunchTimeout;   // cannot happen: every path retires after <= epochs * (depth+1) * (14 + lights) rounds
+    }
+    wf_combine_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(wb, p, reinterpret_cast<float4*>(d_accum));
+    if (rounds_out) *rounds_out = round;
+    return cudaGetLastError();
+}
+
+}  // namespace b200rt

@@ -1,0 +1,56 @@
+// rt_wavefront.h — buffers and launcher of the wavefront stochastic tracer (rt_wavefront.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rt_types.h"
+
+namespace b200rt {
+
+// consumer segments of the logic kernel: what the finished cast of a path was for
+enum : int {
+    WF_SEG_INIT = 0,   // round 0: every slot opens its first sample (no queue: path id = index)
+    WF_SEG_PRIMARY,    // primary ray (main.rs:1150)
+    WF_SEG_SHADE,      // shadow rays of get_shade (main.rs:435)
+    WF_SEG_BOUNCE,     // reflected / scattered / escaped ray (main.rs:564, 583, 603)
+    WF_SEG_SHB,        // no cast: get_shade still has to start (depth-0 primary hit)
+    WF_SEG_REFR,       // a step of get_refract (main.rs:371, 380)
+    WF_SEG_COUNT
+};
+
+struct WfCounters {          // per round parity
+    uint32_t seg[8];         // queue length per segment
+    uint32_t work;           // cast work items
+    uint32_t pad[7];
+};
+struct WfControl {
+    WfCounters c[2];
+    uint32_t retired;        // slots that have rendered all their samples
+    uint32_t pad[15];
+};
+
+constexpr int WF_STATE_ROWS = 12;   // float4 rows of path state (192 B = 6 sectors)
+constexpr int WF_REQ_ROWS = 6;      // path ray (2) + 4 shadow directions (96 B = 3 sectors)
+#ifndef WF_LOGIC_MIN_BLOCKS
+#define WF_LOGIC_MIN_BLOCKS 2
+#endif
+
+struct WfBuffers {
+    WfControl* ctl;
+    float4* st;              // [n][WF_STATE_ROWS]
+    float4* req;             // [n][WF_REQ_ROWS]
+    float4* res;             // [n][2]
+    float2* sres;            // [n][4]
+    uint32_t* q;             // [2][WF_SEG_COUNT][n]
+    uint32_t* work;          // [2][4n]
+    uint32_t n, n_pixels, epar;
+};
+
+size_t wf_workspace_bytes(uint32_t n_paths);
+uint32_t wf_epochs_in_flight(uint32_t width, uint32_t height, uint32_t epoch_count);
+cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, const DParams& p, float* d_accum,
+                                         DCounters* d_cnt, void* workspace, uint32_t n_paths, uint32_t epar, int sm_count,
+                                         uint32_t* h_pinned_retired, cudaEvent_t ev_poll, cudaStream_t stream,
+                                         uint32_t* rounds_out);
+
+}  // namespace b200rt

@@ -152,6 +152,13 @@ enum {
     B200RT_CAST_TWO_PHASE = 0,   /* FMA filter over packed plane records + exact confirm (default) */
     B200RT_CAST_BRUTE_EXACT = 1  /* every pair through the exact reference-order test              */
 };
+/* How b200rt_render_distributed* schedules the stochastic tracer on the GPU (same samples, same bits):
+ * WAVEFRONT keeps every path's state in HBM and alternates one cast kernel with one shading kernel per
+ * round (all lanes of every warp busy); MEGAKERNEL runs each pixel's whole recursion in one thread. */
+enum {
+    B200RT_TRACER_WAVEFRONT = 0,  /* default */
+    B200RT_TRACER_MEGAKERNEL = 1
+};
 typedef struct b200rt_params {
     uint32_t width, height;        /* main.rs:1084-1085                                        */
     uint32_t row_begin, row_count; /* rows [row_begin,row_begin+row_count) are rendered; 0,0 = all */
@@ -162,7 +169,7 @@ typedef struct b200rt_params {
     float focus, blur;             /* main.rs:1147-1148 (3.0, 0.04)                            */
     uint64_t seed;                 /* key of the counter-based sample generator                */
     uint32_t cast_mode;            /* B200RT_CAST_*                                            */
-    uint32_t reserved;
+    uint32_t tracer;               /* B200RT_TRACER_* (stochastic tracer only)                 */
 } b200rt_params;
 
 typedef struct b200rt_stats {
@@ -173,6 +180,8 @@ typedef struct b200rt_stats {
     uint64_t samples;              /* pixel samples produced (reference "rays", main.rs:1108)  */
     float kernel_ms;               /* device time of the last render/intersect kernel          */
     float h2d_ms, d2h_ms;
+    uint32_t wavefront_rounds;     /* cast + shading rounds of the last wavefront render        */
+    uint64_t certify_fallbacks;    /* casts whose certified select fell back to the ordered walk */
 } b200rt_stats;
 
 typedef struct b200rt_ctx b200rt_ctx;
@@ -205,6 +214,9 @@ int b200rt_render_distributed(b200rt_ctx* ctx, const b200rt_camera* cam, const b
 int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
                                      uint32_t epoch_begin, uint32_t epoch_count, float* d_accum,
                                      void* cuda_stream);
+/* Note: with B200RT_TRACER_WAVEFRONT the call polls a device counter to know when every path has retired, i.e.
+ * it synchronises with `cuda_stream` a few times while it enqueues rounds; on return all but the final
+ * accumulate kernel have completed.  B200RT_TRACER_MEGAKERNEL enqueues one kernel and returns. */
 
 /* photon.rs:18-21 into_rgb_internal: out_rgb[i] = weight_sum < EPSILON ? 0 : sum / weight_sum */
 int b200rt_resolve_device(b200rt_ctx* ctx, const float* d_accum, float* d_out_rgb, size_t n_pixels,

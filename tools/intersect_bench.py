@@ -66,6 +66,7 @@ for name, rays in (("random_4Mi", random_rays(1 << 22)), ("camera_2560x1440", ca
         res = {"rays": n, "ms_median": med, "ms_min": ms[0], "Gcasts_per_s": n / med / 1e6,
                "algorithmic_TFLOPs": n * flop_per_cast / (med * 1e-3) / 1e12,
                "roofline_frac": n * flop_per_cast / (med * 1e-3) / peak,
-               "exact_tests_per_cast": s["exact_confirms"] / max(s["casts"], 1)}
+               "exact_tests_per_cast": s["exact_confirms"] / max(s["casts"], 1),
+               "fallbacks_per_cast": s["certify_fallbacks"] / max(s["casts"], 1)}
         out[f"{name}/{mname}"] = res
         print(name, mname, json.dumps(res), flush=True)
