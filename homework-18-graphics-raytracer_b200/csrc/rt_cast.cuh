@@ -195,6 +195,10 @@ RT_DI void load_tripair(const float4* __restrict__ tri_filter, uint32_t tile, ui
 //   cf: the ray's face-cull factor (-K for Front rays, +K for Back rays, 0 for Both; main.rs:185-188): the term
 //   c = cf * nd is negative exactly for the faces the ray's mode culls, and -K|nd| + A/|nd| < 0 for every
 //   |nd| >= g, so culled pairs leave the candidate set here (1 FMUL2 per triangle pair, no extra min: FMNMX3).
+//   nd is a FUSED dot product: its sign can differ from the reference's non-fused n.dir when |nd| <~ 3e-7, far
+//   inside the |nd| < g band that always passes; the exact culling decision is taken in confirm_tile.
+//   (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false, so the reference's own
+//   non-fused dot cannot be formed with packed instructions: measured, see DESIGN.md.)
 RT_DI void filter_pair(const TriPair& c, float ox, float oy, float oz, float cf, float dx, float dy, float dz, float A,
                        float g, bool& keep_a, bool& keep_b) {
     const float2 nd = __ffma2_rn(c.nz, bc2(dz), __ffma2_rn(c.ny, bc2(dy), __fmul2_rn(c.nx, bc2(dx))));
@@ -255,7 +259,7 @@ RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand
             const uint32_t i = (uint32_t)__ffsll((long long)rem) - 1u;
             rem &= rem - 1ull;
             const float4 q0 = sc.tri_exact[4 * (size_t)(base + i)];
-            const bool bf = dot(mk3(q0), ray.d) > 0.0f;                               // primitives.rs:45, exact
+            const bool bf = dot(mk3(q0), ray.d) > 0.0f;                               // primitives.rs:45, the reference's bits
             if ((bf && ray.face == kFront) || (!bf && ray.face == kBack)) continue;   // main.rs:185-188
             if (excluded(ray, (int32_t)(base + i), bf)) continue;                     // main.rs:190-200
             const float nd = __fmaf_rn(q0.z, ray.d.z, __fmaf_rn(q0.y, ray.d.y, q0.x * ray.d.x));
@@ -349,20 +353,30 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
         __syncwarp();   // masks (and, after the last tile, the ray slots) are free again
     }
     if (active) {
+        // spheres (main.rs:264-324): a conservative pre-filter of main.rs:265-268 in fused arithmetic for 32 spheres at a
+        // time — squared line-sphere distance |disp|^2 |dir|^2 - (disp.dir)^2 against r^2 with a 64u (r^2 + |disp|^2)
+        // slack (both sides' rounding is <= 13u of that; NaNs pass) — then the exact test of the survivors in index
+        // order.  Walking a mask lets lanes that pass DIFFERENT spheres run their exact tests in the same iteration.
+        for (uint32_t j0 = 0; j0 < sc.n_sph; j0 += 32u) {
+            const uint32_t nj = min(32u, sc.n_sph - j0);
+            uint32_t smask = 0u;
+#pragma unroll 4
+            for (uint32_t j = 0; j < nj; ++j) {
+                const float4 s4 = sc.sph[j0 + j];
+                const float ex = s4.x - ray.o.x, ey = s4.y - ray.o.y, ez = s4.z - ray.o.z;
+                const float b = __fmaf_rn(ez, ray.d.z, __fmaf_rn(ey, ray.d.y, ex * ray.d.x));
+                const float e2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex));
+                const float r2 = s4.w * s4.w;
+                const float d2 = __fmaf_rn(-b, b, e2 * dd);
+                const float bound = __fmaf_rn(3.8146973e-6f, r2 + e2, r2);
+                if (!(trust && d2 > bound)) smask |= 1u << j;
+            }
 #pragma unroll 1
-        for (uint32_t j = 0; j < sc.n_sph; ++j) {
-            const float4 s4 = sc.sph[j];
-            // conservative pre-filter of main.rs:265-268 (fused arithmetic): squared line-sphere distance
-            // |disp|^2 |dir|^2 - (disp.dir)^2 against r^2 with a 64u (r^2 + |disp|^2) slack (both sides' rounding is
-            // <= 13u of that); NaNs fall through to the exact test
-            const float ex = s4.x - ray.o.x, ey = s4.y - ray.o.y, ez = s4.z - ray.o.z;
-            const float b = __fmaf_rn(ez, ray.d.z, __fmaf_rn(ey, ray.d.y, ex * ray.d.x));
-            const float e2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex));
-            const float r2 = s4.w * s4.w;
-            const float d2 = __fmaf_rn(-b, b, e2 * dd);
-            const float bound = __fmaf_rn(3.8146973e-6f, r2 + e2, r2);
-            if (trust && d2 > bound) continue;
-            sphere_exact_test(s4, (int32_t)(sc.n_tris + j), ray, best);
+            while (smask) {
+                const uint32_t j = (uint32_t)__ffs((int)smask) - 1u;
+                smask &= smask - 1u;
+                sphere_exact_test(sc.sph[j0 + j], (int32_t)(sc.n_tris + j0 + j), ray, best);
+            }
         }
         finalize_hit(sc, best, hit, want_attrs);
         cs.casts += 1ull;

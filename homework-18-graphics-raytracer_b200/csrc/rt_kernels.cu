@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(TraceCfg<MODE>::kThreads, TraceCfg<MODE>::kMin
 // World::cast for a batch of rays (b200rt_intersect): one ray per lane, warp-collective two-phase cast.
 // This is K2, the intersection kernel on its own.
 template <int CAST>
-__global__ void __launch_bounds__(128) intersect_kernel(const DScene sc, const b200rt_ray* __restrict__ rays, size_t n,
+__global__ void __launch_bounds__(128, 4) intersect_kernel(const DScene sc, const b200rt_ray* __restrict__ rays, size_t n,
                                                         b200rt_hit* __restrict__ hits, DCounters* __restrict__ cnt) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;

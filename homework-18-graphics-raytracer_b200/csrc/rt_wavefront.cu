@@ -173,31 +173,29 @@ __global__ void __launch_bounds__(128, 4) wf_cast_kernel(const DScene sc, const 
 
 // ---- logic -------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(256, WF_LOGIC_MIN_BLOCKS) wf_logic_kernel(const DScene sc, const DCamera cam, const DParams p,
-                                                          const WfBuffers wb, const uint32_t buf, const uint32_t init,
+// One instantiation per segment: each is a small kernel (the code of the other segments is compiled out), so it keeps
+// few registers and many warps in flight — these kernels are bound by the latency of gathering path rows from HBM.
+template <int SEG> struct LogicCfg { static constexpr int kMinBlocks = 3; };
+template <> struct LogicCfg<WF_SEG_INIT> { static constexpr int kMinBlocks = 4; };
+template <> struct LogicCfg<WF_SEG_REFR> { static constexpr int kMinBlocks = 4; };
+
+template <int SEG>
+__global__ void __launch_bounds__(256, LogicCfg<SEG>::kMinBlocks) wf_logic_kernel(const DScene sc, const DCamera cam, const DParams p,
+                                                          const WfBuffers wb, const uint32_t buf,
                                                           DCounters* __restrict__ cnt) {
+    constexpr int seg = SEG;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nbuf = buf ^ 1u;
-    uint32_t n_seg[WF_SEG_COUNT], chunks[WF_SEG_COUNT], total_chunks = 0u;
-#pragma unroll
-    for (int s = 0; s < WF_SEG_COUNT; ++s) {
-        n_seg[s] = init ? (s == WF_SEG_INIT ? wb.n : 0u) : (s == WF_SEG_INIT ? 0u : wb.ctl->c[buf].seg[s]);
-        chunks[s] = (n_seg[s] + 31u) >> 5;
-        total_chunks += chunks[s];
-    }
+    const uint32_t n_this = SEG == WF_SEG_INIT ? wb.n : wb.ctl->c[buf].seg[SEG];
+    const uint32_t total_chunks = (n_this + 31u) >> 5;
     const f3 cam_toward = mk3(cam.toward), cam_x = mk3(cam.x), cam_y = mk3(cam.y);
     const uint32_t n_epochs = p.epoch_count;
     unsigned long long n_samples = 0ull;
 
     for (uint32_t chunk = gw; chunk < total_chunks; chunk += n_warps) {
-        int seg = 0;
-        uint32_t c = chunk;
-#pragma unroll
-        for (int s = 0; s < WF_SEG_COUNT - 1; ++s)
-            if (seg == s && c >= chunks[s]) { c -= chunks[s]; seg = s + 1; }
-        const uint32_t k = c * 32u + lane;
-        const bool valid = k < n_seg[seg];
+        const uint32_t k = chunk * 32u + lane;
+        const bool valid = k < n_this;
         const uint32_t pid = !valid ? 0u : (seg == WF_SEG_INIT ? k : wb.q[((size_t)buf * WF_SEG_COUNT + seg) * wb.n + k]);
         const PathMem pm{wb.st, wb.req, pid};
 
@@ -637,15 +635,21 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     const WfBuffers wb = wf_carve(workspace, n_paths, n_pixels, epar);
     cudaError_t e = cudaMemsetAsync(wb.ctl, 0, sizeof(WfControl), stream);
     if (e != cudaSuccess) return e;
-    const int cast_blocks = sm_count * 4, logic_blocks = sm_count * 2;
+    const int cast_blocks = sm_count * 4;
+    auto logic_blocks = [&](int min_blocks) { return sm_count * min_blocks; };
     // round 0: every slot opens its first sample
-    wf_logic_kernel<<<logic_blocks, 256, 0, stream>>>(sc, cam, p, wb, 1u, 1u, d_cnt);
+    wf_logic_kernel<WF_SEG_INIT><<<logic_blocks(LogicCfg<WF_SEG_INIT>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, 1u, d_cnt);
     uint32_t round = 0, buf = 0;
     uint32_t group = 8;
     for (;;) {
         for (uint32_t g = 0; g < group; ++g, ++round, buf ^= 1u) {
             wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
-            wf_logic_kernel<<<logic_blocks, 256, 0, stream>>>(sc, cam, p, wb, buf, 0u, d_cnt);
+            wf_logic_kernel<WF_SEG_PRIMARY><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            wf_logic_kernel<WF_SEG_SHADE><<<logic_blocks(LogicCfg<WF_SEG_SHADE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            wf_logic_kernel<WF_SEG_BOUNCE><<<logic_blocks(LogicCfg<WF_SEG_BOUNCE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            wf_logic_kernel<WF_SEG_REFR><<<logic_blocks(LogicCfg<WF_SEG_REFR>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            if (p.depth <= 0)   // get_shade of depth-0 primary hits (the only source of this segment)
+                wf_logic_kernel<WF_SEG_SHB><<<logic_blocks(LogicCfg<WF_SEG_SHB>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
         }
         e = cudaMemcpyAsync(h_pinned_retired, &wb.ctl->retired, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess) return e;

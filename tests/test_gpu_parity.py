@@ -160,3 +160,79 @@ def test_errors(b200rt, gpu_ctx):
         fresh.render_whitted(cam, b200rt.default_params(width=8, height=8))
     assert e.value.code == b200rt.ERR_NO_SCENE
     fresh.close()
+
+
+# ---- stochastic tracer: wavefront == megakernel == brute-force exact cast ------------------------------------------
+def test_grazing_rays_hit_at_infinity(b200rt, oracle, gpu_ctx, fixture_world):
+    """Rays found by the 4K stochastic render whose reference n.dir is exactly 0 for one triangle while the fused dot
+    product is not: the reference reports a hit at t = +inf (main.rs:204-231 accept inf / NaN).  The cast filter must
+    keep such pairs whatever the sign of its own fused n.dir."""
+    cases = [("3f959753 00000000 bf87819a", "bf00d52e 3f3c2e41 bee89aa4", 0, 37, 1, 30),
+             ("40042e8a 4024e36a 400203d6", "befd3bb2 bead9492 bf4cdeb7", 0, -1, 0, 10),
+             ("3f83e17c 00000000 bf0a1ae0", "beaf1a07 3f4ca2b9 befcf18c", 0, 37, 1, 31),
+             ("bfd6e906 00000000 3fb82ed9", "3f7b6335 3e249b5d bdcb772a", 0, 36, 1, 25)]
+    rays = np.zeros(len(cases) * 16, dtype=b200rt.RAY_DTYPE)
+    for i in range(len(rays)):
+        o, d, face, ex, exf, _ = cases[i % len(cases)]
+        rays["origin"][i] = np.array([int(x, 16) for x in o.split()], dtype=np.uint32).view(np.float32)
+        rays["direction"][i] = np.array([int(x, 16) for x in d.split()], dtype=np.uint32).view(np.float32)
+        rays["face_direction"][i] = face; rays["exclude_prim"][i] = ex; rays["exclude_face"][i] = exf
+    o = oracle.intersect(fixture_world.scene(), rays)
+    for mode in (b200rt.CAST_TWO_PHASE, b200rt.CAST_BRUTE_EXACT):
+        g = gpu_ctx.intersect(rays, mode)
+        assert np.array_equal(g["prim_id"], o["prim_id"])
+        assert np.array_equal(g["prim_id"][:4], [c[5] for c in cases])
+        assert np.all(np.isinf(g["distance"]))
+
+
+def test_tracers_and_cast_modes_bitwise(b200rt, gpu_ctx):
+    """The wavefront tracer, the megakernel, and the megakernel with every pair through the exact test produce the same
+    bits (one epoch in flight per pixel: 2560x1440 is above the wavefront's multi-epoch threshold)."""
+    cam = b200rt.fixture_camera()
+    out = {}
+    for name, cm, tr in (("wave", b200rt.CAST_TWO_PHASE, b200rt.TRACER_WAVEFRONT),
+                         ("mega", b200rt.CAST_TWO_PHASE, b200rt.TRACER_MEGAKERNEL),
+                         ("brute", b200rt.CAST_BRUTE_EXACT, b200rt.TRACER_MEGAKERNEL)):
+        p = b200rt.default_params(width=3840, height=2160, seed=11, tracer=tr, cast_mode=cm, row_begin=700, row_count=600)
+        gpu_ctx.reset_stats()
+        out[name] = (gpu_ctx.render_distributed(cam, p, 0, 3), gpu_ctx.stats())
+    for name in ("wave", "mega"):
+        assert out[name][1]["casts"] == out["brute"][1]["casts"]
+        assert out[name][1]["samples"] == out["brute"][1]["samples"]
+        assert np.array_equal(out[name][0].view(np.uint32), out["brute"][0].view(np.uint32)), name
+    assert out["wave"][1]["wavefront_rounds"] > 0 and out["mega"][1]["wavefront_rounds"] == 0
+
+
+@pytest.mark.parametrize("size", [(64, 48, 5), (333, 77, 3), (1920, 1080, 8)])
+def test_wavefront_matches_megakernel(b200rt, gpu_ctx, size):
+    """Small frames run several epochs in flight per pixel: same samples, sums differ only by fp32 summation order."""
+    w, h, ep = size
+    cam = b200rt.fixture_camera()
+    a = gpu_ctx.render_distributed(cam, b200rt.default_params(width=w, height=h, seed=5, tracer=b200rt.TRACER_WAVEFRONT), 0, ep)
+    m = gpu_ctx.render_distributed(cam, b200rt.default_params(width=w, height=h, seed=5, tracer=b200rt.TRACER_MEGAKERNEL), 0, ep)
+    assert np.array_equal(a[..., 3], m[..., 3])
+    np.testing.assert_allclose(a[..., :3], m[..., :3], rtol=2e-6, atol=1e-7)
+
+
+def test_wavefront_depth0_and_many_lights(b200rt, oracle, gpu_ctx, fixture_world):
+    """depth 0 (get_shade of the primary hit only, main.rs:525-527) and a scene with 6 lights (two chunks of shadow rays)."""
+    cam = b200rt.fixture_camera()
+    for depth in (0, 1):
+        p = b200rt.default_params(width=200, height=150, seed=2, depth=depth)
+        acc = gpu_ctx.render_distributed(cam, p, 0, 3)
+        o_acc, _ = oracle.render_distributed(fixture_world.scene(), cam, p, 0, 3)
+        assert np.array_equal(acc[..., 3], o_acc[..., 3])
+        assert (rel_err(acc[..., :3], o_acc[..., :3]).max(axis=2) > 1e-3).mean() < 2e-3
+    w = b200rt.World.fixture()
+    for k in range(3):
+        w.push_light(b200rt.point_light([1.0 + k, 2.0, 1.5 - k], [0.3, 0.4, 0.5]))
+    ctx = b200rt.Context(0)
+    ctx.upload_scene(w)
+    p = b200rt.default_params(width=160, height=120, seed=4)
+    acc = ctx.render_distributed(cam, p, 0, 2)
+    mega = ctx.render_distributed(cam, b200rt.copy_params(p, tracer=b200rt.TRACER_MEGAKERNEL), 0, 2)
+    o_acc, _ = oracle.render_distributed(w.scene(), cam, p, 0, 2)
+    assert np.array_equal(acc[..., 3], o_acc[..., 3]) and np.array_equal(acc[..., 3], mega[..., 3])
+    np.testing.assert_allclose(acc[..., :3], mega[..., :3], rtol=2e-6, atol=1e-7)
+    assert (rel_err(acc[..., :3], o_acc[..., :3]).max(axis=2) > 1e-3).mean() < 2e-3
+    ctx.close()
