@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "_lib", "libb200rt.so")
+LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(_PKG_DIR, "_lib", "libb200rt.so")   # B200RT_LIB: tuning builds
 
 # ---- error codes / enums (include/b200rt.h) ----------------------------------------------------------
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_SCENE, ERR_NO_DEVICE, ERR_IO, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6

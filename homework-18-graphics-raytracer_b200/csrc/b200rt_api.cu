@@ -466,28 +466,37 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
     if (rc != B200RT_OK) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the CUDA default stream
     CU(cudaEventRecord(ctx->ev0, st));
+    ctx->last_rounds = 0;
     if (epoch_count) {
         if (params->tracer == B200RT_TRACER_MEGAKERNEL || params->cast_mode == B200RT_CAST_BRUTE_EXACT) {
             CU(launch_distributed(ctx->scene, dc, dp, d_accum, ctx->d_cnt, st));
         } else {
-            // wavefront: rows are rendered in bands of at most kMaxPaths path slots (the whole frame at 4K)
-            const uint32_t epar = wf_epochs_in_flight(dp.width, dp.height, epoch_count);
-            const uint64_t kMaxPaths = 40ull << 20;
-            uint32_t band_rows = (uint32_t)std::max<uint64_t>(1, kMaxPaths / ((uint64_t)dp.width * epar));
+            // wavefront: the epochs are rendered in batches of `epar` epochs, every epoch of a batch in flight at once
+            // (one path slot per pixel and epoch), and - only for frames too large for that - in bands of rows.
+            // Both are functions of the frame and the epoch range alone, never of the row band a caller renders,
+            // so a band is bitwise the same rows of the full frame.
+            const uint32_t epar = wf_epochs_in_flight(dp.width, dp.height, epoch_count, ctx->hbm_bytes);
+            const uint64_t max_paths_mem = std::max<uint64_t>(1, (uint64_t)(0.4 * (double)ctx->hbm_bytes) / wf_workspace_bytes_per_path());
+            uint32_t band_rows = (uint32_t)std::max<uint64_t>(1, max_paths_mem / ((uint64_t)dp.width * epar));
             band_rows = std::min(band_rows, dp.row_count);
             const uint32_t max_paths = band_rows * dp.width * epar;
             rc = ensure(ctx, &ctx->d_wf, &ctx->d_wf_bytes, wf_workspace_bytes(max_paths));
             if (rc != B200RT_OK) return rc;
             ctx->last_rounds = 0;
-            for (uint32_t r = 0; r < dp.row_count; r += band_rows) {
-                DParams band = dp;
-                band.row_begin = dp.row_begin + r;
-                band.row_count = std::min(band_rows, dp.row_count - r);
-                uint32_t rounds = 0;
-                CU(launch_distributed_wavefront(ctx->scene, dc, band, d_accum, ctx->d_cnt, ctx->d_wf,
-                                                band.row_count * dp.width * epar, epar, ctx->sm_count, ctx->h_poll,
-                                                ctx->ev_poll, st, &rounds));
-                ctx->last_rounds += rounds;
+            for (uint32_t e0 = 0; e0 < epoch_count; e0 += epar) {
+                const uint32_t en = std::min(epar, epoch_count - e0);
+                for (uint32_t r = 0; r < dp.row_count; r += band_rows) {
+                    DParams band = dp;
+                    band.row_begin = dp.row_begin + r;
+                    band.row_count = std::min(band_rows, dp.row_count - r);
+                    band.epoch_begin = epoch_begin + e0;
+                    band.epoch_count = en;
+                    uint32_t rounds = 0;
+                    CU(launch_distributed_wavefront(ctx->scene, dc, band, d_accum, ctx->d_cnt, ctx->d_wf,
+                                                    band.row_count * dp.width * en, en, ctx->sm_count, ctx->h_poll,
+                                                    ctx->ev_poll, st, &rounds));
+                    ctx->last_rounds += rounds;
+                }
             }
         }
     }

@@ -47,7 +47,8 @@ struct WfBuffers {
 };
 
 size_t wf_workspace_bytes(uint32_t n_paths);
-uint32_t wf_epochs_in_flight(uint32_t width, uint32_t height, uint32_t epoch_count);
+size_t wf_workspace_bytes_per_path();
+uint32_t wf_epochs_in_flight(uint32_t width, uint32_t height, uint32_t epoch_count, size_t hbm_bytes);
 cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, const DParams& p, float* d_accum,
                                          DCounters* d_cnt, void* workspace, uint32_t n_paths, uint32_t epar, int sm_count,
                                          uint32_t* h_pinned_retired, cudaEvent_t ev_poll, cudaStream_t stream,
