@@ -196,7 +196,8 @@ def run_b200(args):
     scene_world = b.World.fixture()
     ctx.upload_scene(scene_world)
     cam = b.fixture_camera()
-    params = b.default_params(width=W, height=H, depth=depth, seed=0)
+    tracer_id = b.TRACER_WAVEFRONT if args.tracer == "wavefront" else b.TRACER_MEGAKERNEL
+    params = b.default_params(width=W, height=H, depth=depth, seed=0, tracer=tracer_id)
     # every launch, copy, collective and timing event of the bench goes on this one stream
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
@@ -276,22 +277,45 @@ def run_b200(args):
     ms_per_step = ms_total / args.steps
     value = samples_total / (ms_per_step * 1e-3) / 1e6
 
-    # per-launch duration of the dominant kernel (trace_kernel), measured live with CUDA events on its stream
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # per-launch duration of the dominant kernel, measured live with CUDA events on the launching stream.
+    #  * wavefront: the dominant kernel is wf_cast_kernel (World::cast for every ray of a round); the library brackets
+    #    each of its launches with events (b200rt_set_kernel_timing) during one extra step;
+    #  * megakernel / Whitted: one trace_kernel launch per step.
     barrier()
-    for a, c in kev:
-        if tracer == "distributed":
-            d_accum.zero_()
-            a.record()
-            ctx.render_distributed_device(cam, params, e0, en, d_accum.data_ptr(), stream)
-            c.record()
-        else:
-            a.record()
-            ctx.render_whitted_device(cam, p_rank, d_rgb.data_ptr(), 0, stream)
-            c.record()
-    barrier()
-    kernel_ms = [a.elapsed_time(c) for a, c in kev]
-    k_ms = sum(kernel_ms) / len(kernel_ms)
+    cast_launches = 0
+    logic_ms = None
+    wavefront = tracer == "distributed" and args.tracer == "wavefront"
+    if wavefront:
+        ctx.set_kernel_timing(True)
+        d_accum.zero_()
+        ctx.render_distributed_device(cam, params, e0, en, d_accum.data_ptr(), stream)
+        barrier()
+        kst = ctx.stats()
+        ctx.set_kernel_timing(False)
+        k_ms_total = kst["cast_kernel_ms"]
+        cast_launches = kst["cast_kernel_launches"]
+        logic_ms = kst["logic_kernel_ms"]
+        k_ms = k_ms_total / max(cast_launches, 1)
+        launches_per_step = kst["kernel_launches"]
+        step_kernel_ms = kst["kernel_ms"]
+    else:
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, c in kev:
+            if tracer == "distributed":
+                d_accum.zero_()
+                a.record()
+                ctx.render_distributed_device(cam, params, e0, en, d_accum.data_ptr(), stream)
+                c.record()
+            else:
+                a.record()
+                ctx.render_whitted_device(cam, p_rank, d_rgb.data_ptr(), 0, stream)
+                c.record()
+        barrier()
+        kernel_ms = [a.elapsed_time(c) for a, c in kev]
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        k_ms_total = k_ms
+        cast_launches = 1
+        step_kernel_ms = k_ms
 
     # ---- end-to-end through the host-buffer C ABI --------------------------------------------------------------
     e2e_steps = max(1, min(args.steps, 3))
@@ -315,16 +339,23 @@ def run_b200(args):
     peak_tflops = info["sm_count"] * 128 * 2 * sm_max_mhz * 1e6 / 1e12
     tri_pairs = st["tri_pair_tests"] / args.steps
     sph_pairs = st["sph_pair_tests"] / args.steps
-    flops = tri_pairs * FLOP_TRI + sph_pairs * FLOP_SPH
-    achieved = flops / (k_ms * 1e-3) / 1e12
+    flops = tri_pairs * FLOP_TRI + sph_pairs * FLOP_SPH          # algorithmic flop of one step on this rank
+    achieved = flops / (k_ms_total * 1e-3) / 1e12                # ... over the device time of the dominant kernel's launches
     live_peak, live_mhz = ctx.measure_fp32_peak()
+    kname = "wf_cast_kernel" if wavefront else f"trace_kernel<{tracer}>"
+    n_l = max(cast_launches, 1)
     roofline = {
-        "bound": "fp32", "kernel": f"trace_kernel<{tracer}>", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": kname, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": achieved / peak_tflops, "traffic": None,
         "peak_source": f"SMs({info['sm_count']}) x 128 lanes x 2 flop x sm_max_mhz({sm_max_mhz:.0f}, {peak_src} MEASURED_PEAKS.json)",
         "ffma_loop_tflops_live": live_peak, "frac_of_live_ffma_loop": achieved / live_peak if live_peak else None,
-        "pair_tests_per_launch": {"tri": tri_pairs, "sph": sph_pairs}, "kernel_ms": k_ms,
-        "casts_per_launch": st["casts"] / args.steps,
+        "launches_per_step": cast_launches, "avg_launch_ms": k_ms,
+        "algorithmic_flop_per_launch": flops / n_l,
+        "pair_tests_per_launch": {"tri": tri_pairs / n_l, "sph": sph_pairs / n_l}, "kernel_ms": k_ms_total,
+        "casts_per_launch": st["casts"] / args.steps / n_l,
+        "share_of_step": k_ms_total / step_kernel_ms if step_kernel_ms else None,
+        "other_kernels_ms": logic_ms,
+        "whole_step_frac": flops / (step_kernel_ms * 1e-3) / 1e12 / peak_tflops if step_kernel_ms else None,
     }
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only) ------------------
@@ -358,13 +389,13 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc + (" [REDUCED SIZE: dev run]" if reduced else ""), "width": W, "height": H,
                        "depth": depth, "epochs": epochs, "sharding": ("epochs" if tracer == "distributed" else "rows"),
-                       "cast_mode": "two_phase", "l2": "accumulation buffer (%.1f MB) exceeds L2; scene records are smem/L1 resident by design" % (W * H * 16 / 1e6)},
+                       "cast_mode": "two_phase", "tracer": args.tracer if tracer == "distributed" else "megakernel", "l2": "accumulation buffer (%.1f MB) exceeds L2; scene records are smem/L1 resident by design" % (W * H * 16 / 1e6)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
-            "casts_per_s": st["casts"] / args.steps / (k_ms * 1e-3),
-            "pair_tests_per_s": (tri_pairs + sph_pairs) / (k_ms * 1e-3),
+            "gpu_launches": int(launches_per_step) * args.steps, "clocks": clocks,
+            "casts_per_s_in_dominant_kernel": st["casts"] / args.steps / (k_ms_total * 1e-3),
+            "pair_tests_per_s_in_dominant_kernel": (tri_pairs + sph_pairs) / (k_ms_total * 1e-3),
         }
         print(json.dumps(line), flush=True)
     if world_size > 1:
@@ -384,6 +415,8 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--epochs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tracer", default="wavefront", choices=["wavefront", "megakernel"],
+                    help="GPU schedule of the stochastic tracer (same samples, same bits)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -103,6 +103,8 @@ class Stats(C.Structure):
         ("casts", C.c_uint64), ("tri_pair_tests", C.c_uint64), ("sph_pair_tests", C.c_uint64),
         ("exact_confirms", C.c_uint64), ("samples", C.c_uint64), ("kernel_ms", C.c_float), ("h2d_ms", C.c_float),
         ("d2h_ms", C.c_float), ("wavefront_rounds", C.c_uint32), ("certify_fallbacks", C.c_uint64),
+        ("cast_kernel_ms", C.c_float), ("logic_kernel_ms", C.c_float), ("cast_kernel_launches", C.c_uint32),
+        ("kernel_launches", C.c_uint32),
     ]
 
 
@@ -117,7 +119,7 @@ EXPORTED_SYMBOLS = [
     "b200rt_create", "b200rt_destroy", "b200rt_strerror", "b200rt_last_cuda_error", "b200rt_device_info",
     "b200rt_upload_scene", "b200rt_render_whitted", "b200rt_render_whitted_device", "b200rt_render_distributed",
     "b200rt_render_distributed_device", "b200rt_resolve_device", "b200rt_intersect", "b200rt_intersect_device",
-    "b200rt_get_stats", "b200rt_reset_stats", "b200rt_measure_fp32_peak", "b200rt_filter_bench", "b200rt_pipe_bench", "b200rt_world_new", "b200rt_world_free",
+    "b200rt_get_stats", "b200rt_reset_stats", "b200rt_set_kernel_timing", "b200rt_measure_fp32_peak", "b200rt_filter_bench", "b200rt_pipe_bench", "b200rt_world_new", "b200rt_world_free",
     "b200rt_world_push_object", "b200rt_world_push_triangle", "b200rt_world_push_flat_triangle",
     "b200rt_world_push_square", "b200rt_world_push_sphere", "b200rt_world_push_light", "b200rt_world_load_obj",
     "b200rt_world_scene", "b200rt_world_fixture", "b200rt_fixture_camera", "b200rt_default_params",
@@ -154,6 +156,7 @@ def load_library() -> C.CDLL:
         "b200rt_intersect_device": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp, vp]),
         "b200rt_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "b200rt_reset_stats": (C.c_int, [vp]),
+        "b200rt_set_kernel_timing": (C.c_int, [vp, C.c_int]),
         "b200rt_measure_fp32_peak": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "b200rt_filter_bench": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
         "b200rt_pipe_bench": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
@@ -446,6 +449,9 @@ class Context:
         s = Stats()
         _check(self._lib.b200rt_get_stats(self._h, C.byref(s)), "get_stats", self)
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def set_kernel_timing(self, enabled: bool) -> None:
+        _check(self._lib.b200rt_set_kernel_timing(self._h, 1 if enabled else 0), "set_kernel_timing", self)
 
     def reset_stats(self) -> None:
         _check(self._lib.b200rt_reset_stats(self._h), "reset_stats", self)

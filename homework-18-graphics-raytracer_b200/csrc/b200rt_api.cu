@@ -50,7 +50,9 @@ struct b200rt_ctx {
     void* d_wf = nullptr;   size_t d_wf_bytes = 0;
     uint32_t* h_poll = nullptr;
     cudaEvent_t ev_poll = nullptr;
-    uint32_t last_rounds = 0;
+    uint32_t last_rounds = 0, last_launches = 0;
+    bool kernel_timing = false;
+    WfKernelTiming wf_timing;
 
     b200rt_stats stats{};
 };
@@ -187,6 +189,10 @@ int fetch_counters(b200rt_ctx* ctx) {
     ctx->stats.samples = h.samples;
     ctx->stats.certify_fallbacks = h.fallbacks;
     ctx->stats.wavefront_rounds = ctx->last_rounds;
+    ctx->stats.cast_kernel_ms = (float)ctx->wf_timing.cast_ms;
+    ctx->stats.logic_kernel_ms = (float)ctx->wf_timing.logic_ms;
+    ctx->stats.cast_kernel_launches = (uint32_t)ctx->wf_timing.cast_launches;
+    ctx->stats.kernel_launches = ctx->last_launches;
     return B200RT_OK;
 }
 
@@ -253,6 +259,7 @@ int b200rt_destroy(b200rt_ctx* ctx) {
     if (ctx->d_wf) cudaFree(ctx->d_wf);
     if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
     if (ctx->ev_poll) cudaEventDestroy(ctx->ev_poll);
+    for (cudaEvent_t ev : ctx->wf_timing.pool) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -467,9 +474,13 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
     cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the CUDA default stream
     CU(cudaEventRecord(ctx->ev0, st));
     ctx->last_rounds = 0;
+    ctx->last_launches = 0;
+    ctx->wf_timing.cast_ms = ctx->wf_timing.logic_ms = 0.0;
+    ctx->wf_timing.cast_launches = 0;
     if (epoch_count) {
         if (params->tracer == B200RT_TRACER_MEGAKERNEL || params->cast_mode == B200RT_CAST_BRUTE_EXACT) {
             CU(launch_distributed(ctx->scene, dc, dp, d_accum, ctx->d_cnt, st));
+            ctx->last_launches = 1;
         } else {
             // wavefront: the epochs are rendered in batches of `epar` epochs, every epoch of a batch in flight at once
             // (one path slot per pixel and epoch), and - only for frames too large for that - in bands of rows.
@@ -494,7 +505,7 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
                     uint32_t rounds = 0;
                     CU(launch_distributed_wavefront(ctx->scene, dc, band, d_accum, ctx->d_cnt, ctx->d_wf,
                                                     band.row_count * dp.width * en, en, ctx->sm_count, ctx->h_poll,
-                                                    ctx->ev_poll, st, &rounds));
+                                                    ctx->ev_poll, st, &rounds, &ctx->last_launches, ctx->kernel_timing ? &ctx->wf_timing : nullptr));
                     ctx->last_rounds += rounds;
                 }
             }
@@ -576,6 +587,12 @@ int b200rt_get_stats(b200rt_ctx* ctx, b200rt_stats* out) {
     // kernel_ms of a *_device call: the events were recorded on the caller's stream
     if (cudaEventQuery(ctx->ev1) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev0, ctx->ev1);
     *out = ctx->stats;
+    return B200RT_OK;
+}
+
+int b200rt_set_kernel_timing(b200rt_ctx* ctx, int enabled) {
+    if (!ctx) return B200RT_ERR_INVALID;
+    ctx->kernel_timing = enabled != 0;
     return B200RT_OK;
 }
 

@@ -653,7 +653,7 @@ static WfBuffers wf_carve(void* workspace, uint32_t n_paths, uint32_t n_pixels, 
 cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, const DParams& p, float* d_accum,
                                          DCounters* d_cnt, void* workspace, uint32_t n_paths, uint32_t epar, int sm_count,
                                          uint32_t* h_pinned_retired, cudaEvent_t ev_poll, cudaStream_t stream,
-                                         uint32_t* rounds_out) {
+                                         uint32_t* rounds_out, uint32_t* launches_out, WfKernelTiming* timing) {
     const uint32_t n_pixels = p.width * p.row_count;
     const WfBuffers wb = wf_carve(workspace, n_paths, n_pixels, epar);
     cudaError_t e = cudaMemsetAsync(wb.ctl, 0, sizeof(WfControl), stream);
@@ -665,8 +665,23 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     uint32_t round = 0, buf = 0;
     uint32_t group = 8;
     for (;;) {
+        const uint32_t first_round_of_group = round;
         for (uint32_t g = 0; g < group; ++g, ++round, buf ^= 1u) {
+            // optional per-kernel timing (bench.py's roofline pass): events around every cast launch
+            cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+            if (timing) {
+                while (timing->pool.size() < 2 * (size_t)(round - first_round_of_group + 1)) {
+                    cudaEvent_t ev;
+                    e = cudaEventCreate(&ev);
+                    if (e != cudaSuccess) return e;
+                    timing->pool.push_back(ev);
+                }
+                ev_a = timing->pool[2 * (round - first_round_of_group)];
+                ev_b = timing->pool[2 * (round - first_round_of_group) + 1];
+                cudaEventRecord(ev_a, stream);
+            }
             wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+            if (timing) cudaEventRecord(ev_b, stream);
             wf_logic_kernel<WF_SEG_PRIMARY><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
             wf_logic_kernel<WF_SEG_SHADE><<<logic_blocks(LogicCfg<WF_SEG_SHADE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
             wf_logic_kernel<WF_SEG_BOUNCE><<<logic_blocks(LogicCfg<WF_SEG_BOUNCE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
@@ -680,12 +695,25 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
         if (e != cudaSuccess) return e;
         e = cudaEventSynchronize(ev_poll);
         if (e != cudaSuccess) return e;
+        if (timing) {
+            for (uint32_t g = 0; g < round - first_round_of_group; ++g) {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, timing->pool[2 * g], timing->pool[2 * g + 1]);
+                timing->cast_ms += ms;
+                timing->cast_launches += 1;
+                if (g + 1 < round - first_round_of_group) {       // cast end -> next cast start = the logic kernels of the round
+                    cudaEventElapsedTime(&ms, timing->pool[2 * g + 1], timing->pool[2 * g + 2]);
+                    timing->logic_ms += ms;
+                }
+            }
+        }
         if (*h_pinned_retired >= n_paths) break;
         if (group < 64) group *= 2;
         if (round > (1u << 21)) return cudaErrorLaunchTimeout;   // cannot happen: every path retires after <= epochs * (depth+1) * (14 + lights) rounds
     }
     wf_combine_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(wb, p, reinterpret_cast<float4*>(d_accum));
     if (rounds_out) *rounds_out = round;
+    if (launches_out) *launches_out += 2u + round * (p.depth <= 0 ? 6u : 5u);
     return cudaGetLastError();
 }
 

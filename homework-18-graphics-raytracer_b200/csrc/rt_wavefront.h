@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "rt_types.h"
 
 namespace b200rt {
@@ -46,12 +48,20 @@ struct WfBuffers {
     uint32_t n, n_pixels, epar;
 };
 
+// Per-kernel device times of a wavefront render (filled when the caller asks for them): CUDA events on the
+// launching stream around every wf_cast_kernel launch.
+struct WfKernelTiming {
+    std::vector<cudaEvent_t> pool;
+    double cast_ms = 0.0, logic_ms = 0.0;
+    uint64_t cast_launches = 0;
+};
+
 size_t wf_workspace_bytes(uint32_t n_paths);
 size_t wf_workspace_bytes_per_path();
 uint32_t wf_epochs_in_flight(uint32_t width, uint32_t height, uint32_t epoch_count, size_t hbm_bytes);
 cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, const DParams& p, float* d_accum,
                                          DCounters* d_cnt, void* workspace, uint32_t n_paths, uint32_t epar, int sm_count,
                                          uint32_t* h_pinned_retired, cudaEvent_t ev_poll, cudaStream_t stream,
-                                         uint32_t* rounds_out);
+                                         uint32_t* rounds_out, uint32_t* launches_out, WfKernelTiming* timing);
 
 }  // namespace b200rt

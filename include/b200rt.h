@@ -182,6 +182,11 @@ typedef struct b200rt_stats {
     float h2d_ms, d2h_ms;
     uint32_t wavefront_rounds;     /* cast + shading rounds of the last wavefront render        */
     uint64_t certify_fallbacks;    /* casts whose certified select fell back to the ordered walk */
+    /* only with b200rt_set_kernel_timing(ctx, 1): device time of the last wavefront render split by kernel */
+    float cast_kernel_ms;          /* sum over the wf_cast_kernel launches (World::cast)          */
+    float logic_kernel_ms;         /* sum over the shading / scatter kernels between them         */
+    uint32_t cast_kernel_launches;
+    uint32_t kernel_launches;      /* kernels launched by the last render call (always counted) */
 } b200rt_stats;
 
 typedef struct b200rt_ctx b200rt_ctx;
@@ -229,6 +234,9 @@ int b200rt_intersect_device(b200rt_ctx* ctx, const b200rt_ray* d_rays, size_t n,
                             b200rt_hit* d_hits, void* cuda_stream);
 
 int b200rt_get_stats(b200rt_ctx* ctx, b200rt_stats* out);
+/* Measure the wavefront tracer's kernels separately (CUDA events around every cast launch on the launching
+ * stream; a few microseconds of host work per round).  Off by default. */
+int b200rt_set_kernel_timing(b200rt_ctx* ctx, int enabled);
 int b200rt_reset_stats(b200rt_ctx* ctx);
 
 /* FP32-pipe calibration: runs a dependent-free FFMA loop on every SM and returns the measured
