@@ -219,6 +219,9 @@ RT_DI void filter_pair(const TriPair& c, float ox, float oy, float oz, float cf,
     keep_b = (ms.y >= 0.0f) | (fabsf(nd.y) < g);
 }
 constexpr float kCullK = 1099511627776.0f;   // 2^40
+#ifndef B200RT_FILTER_RAYS
+#define B200RT_FILTER_RAYS 2
+#endif
 
 struct CastStats {
     unsigned long long casts, confirms, fallbacks;
@@ -326,6 +329,31 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
     for (uint32_t tile = 0; tile < n_tiles; ++tile) {
         TriPair c;
         if (tile == 0) c = tile0; else load_tripair(sc.tri_filter, tile, lane, c);
+#if B200RT_FILTER_RAYS == 4
+        // four rays per iteration: four independent FFMA2 dependency chains in flight per warp
+        // (rays beyond n_act read stale slots of the 32-slot staging area, their masks are never used)
+#pragma unroll 1
+        for (uint32_t i0 = 0; i0 < n_act; i0 += 4u) {
+            const uint32_t i2 = min(i0 + 2u, 30u);                       // i0 = 28 is the last possible group: no overrun
+            const float4 ro0 = s_rays[2 * i0 + 0], rd0 = s_rays[2 * i0 + 1];   // broadcast reads
+            const float4 ro1 = s_rays[2 * i0 + 2], rd1 = s_rays[2 * i0 + 3];
+            const float4 ro2 = s_rays[2 * i2 + 0], rd2 = s_rays[2 * i2 + 1];
+            const float4 ro3 = s_rays[2 * i2 + 2], rd3 = s_rays[2 * i2 + 3];
+            bool ka0, kb0, ka1, kb1, ka2, kb2, ka3, kb3;
+            filter_pair(c, ro0.x, ro0.y, ro0.z, ro0.w, rd0.x, rd0.y, rd0.z, sc.filter_A, sc.filter_g, ka0, kb0);
+            filter_pair(c, ro1.x, ro1.y, ro1.z, ro1.w, rd1.x, rd1.y, rd1.z, sc.filter_A, sc.filter_g, ka1, kb1);
+            filter_pair(c, ro2.x, ro2.y, ro2.z, ro2.w, rd2.x, rd2.y, rd2.z, sc.filter_A, sc.filter_g, ka2, kb2);
+            filter_pair(c, ro3.x, ro3.y, ro3.z, ro3.w, rd3.x, rd3.y, rd3.z, sc.filter_A, sc.filter_g, ka3, kb3);
+            const unsigned ba0 = __ballot_sync(kFullMask, ka0), bb0 = __ballot_sync(kFullMask, kb0);
+            const unsigned ba1 = __ballot_sync(kFullMask, ka1), bb1 = __ballot_sync(kFullMask, kb1);
+            const unsigned ba2 = __ballot_sync(kFullMask, ka2), bb2 = __ballot_sync(kFullMask, kb2);
+            const unsigned ba3 = __ballot_sync(kFullMask, ka3), bb3 = __ballot_sync(kFullMask, kb3);
+            if (lane == 0u) {
+                *reinterpret_cast<uint4*>(s_mask + i0) = make_uint4(ba0, bb0, ba1, bb1);
+                *reinterpret_cast<uint4*>(s_mask + i2) = make_uint4(ba2, bb2, ba3, bb3);
+            }
+        }
+#else
         // two rays per iteration: two independent FFMA2 dependency chains in flight per warp
 #pragma unroll 1
         for (uint32_t i0 = 0; i0 < n_act; i0 += 2u) {
@@ -338,6 +366,7 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
             const unsigned ba1 = __ballot_sync(kFullMask, ka1), bb1 = __ballot_sync(kFullMask, kb1);
             if (lane == 0u) *reinterpret_cast<uint4*>(s_mask + i0) = make_uint4(ba0, bb0, ba1, bb1);   // one STS.128
         }
+#endif
         __syncwarp();
         if (active) {
             const uint2 m = s_mask[rank];
