@@ -343,10 +343,18 @@ def run_b200(args):
     achieved = flops / (k_ms_total * 1e-3) / 1e12                # ... over the device time of the dominant kernel's launches
     live_peak, live_mhz = ctx.measure_fp32_peak()
     kname = "wf_cast_kernel" if wavefront else f"trace_kernel<{tracer}>"
+    # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload only)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if wavefront and not (args.width or args.height) and world_size == 1 and kname in tj:
+            traffic = tj[kname]["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     n_l = max(cast_launches, 1)
     roofline = {
         "bound": "fp32", "kernel": kname, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved / peak_tflops, "traffic": None,
+        "frac": achieved / peak_tflops, "traffic": traffic,
         "peak_source": f"SMs({info['sm_count']}) x 128 lanes x 2 flop x sm_max_mhz({sm_max_mhz:.0f}, {peak_src} MEASURED_PEAKS.json)",
         "ffma_loop_tflops_live": live_peak, "frac_of_live_ffma_loop": achieved / live_peak if live_peak else None,
         "launches_per_step": cast_launches, "avg_launch_ms": k_ms,
@@ -389,7 +397,7 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc + (" [REDUCED SIZE: dev run]" if reduced else ""), "width": W, "height": H,
                        "depth": depth, "epochs": epochs, "sharding": ("epochs" if tracer == "distributed" else "rows"),
-                       "cast_mode": "two_phase", "tracer": args.tracer if tracer == "distributed" else "megakernel", "l2": "accumulation buffer (%.1f MB) exceeds L2; scene records are smem/L1 resident by design" % (W * H * 16 / 1e6)},
+                       "cast_mode": "two_phase", "tracer": args.tracer if tracer == "distributed" else "megakernel", "l2": "path state + ray buffers (%.1f GB per 16-epoch batch) and the accumulation buffer (%.1f MB) exceed L2; scene records stay in registers / L1" % (W * H * 16 * 392 / 1e9, W * H * 16 / 1e6)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
