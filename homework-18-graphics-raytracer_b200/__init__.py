@@ -119,6 +119,7 @@ EXPORTED_SYMBOLS = [
     "b200rt_create", "b200rt_destroy", "b200rt_strerror", "b200rt_last_cuda_error", "b200rt_device_info",
     "b200rt_upload_scene", "b200rt_render_whitted", "b200rt_render_whitted_device", "b200rt_render_distributed",
     "b200rt_render_distributed_device", "b200rt_resolve_device", "b200rt_intersect", "b200rt_intersect_device",
+    "b200rt_post_process", "b200rt_post_process_device", "b200rt_encode_srgb8", "b200rt_encode_srgb8_device",
     "b200rt_get_stats", "b200rt_reset_stats", "b200rt_set_kernel_timing", "b200rt_measure_fp32_peak", "b200rt_filter_bench", "b200rt_pipe_bench", "b200rt_world_new", "b200rt_world_free",
     "b200rt_world_push_object", "b200rt_world_push_triangle", "b200rt_world_push_flat_triangle",
     "b200rt_world_push_square", "b200rt_world_push_sphere", "b200rt_world_push_light", "b200rt_world_load_obj",
@@ -154,6 +155,10 @@ def load_library() -> C.CDLL:
         "b200rt_resolve_device": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
         "b200rt_intersect": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp]),
         "b200rt_intersect_device": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp, vp]),
+        "b200rt_post_process": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(C.c_float)]),
+        "b200rt_post_process_device": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
+        "b200rt_encode_srgb8": (C.c_int, [vp, vp, C.c_size_t, vp]),
+        "b200rt_encode_srgb8_device": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
         "b200rt_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "b200rt_reset_stats": (C.c_int, [vp]),
         "b200rt_set_kernel_timing": (C.c_int, [vp, C.c_int]),
@@ -444,6 +449,26 @@ class Context:
     def intersect_device(self, d_rays: int, n: int, d_hits: int, cast_mode: int = CAST_TWO_PHASE, stream: int = 0):
         _check(self._lib.b200rt_intersect_device(self._h, d_rays, n, cast_mode, d_hits, stream or None),
                "intersect_device", self)
+
+    def post_process(self, rgb: np.ndarray):
+        """main.rs:748-762 on the device (host buffers): returns (normalised copy, p98 divisor or 0)."""
+        out = np.ascontiguousarray(rgb, dtype=np.float32).copy()
+        p = C.c_float(0.0)
+        _check(self._lib.b200rt_post_process(self._h, out.ctypes.data, out.size // 3, C.byref(p)), "post_process", self)
+        return out, float(p.value)
+
+    def post_process_device(self, d_rgb: int, n_pixels: int, d_p98: int = 0, stream: int = 0):
+        _check(self._lib.b200rt_post_process_device(self._h, d_rgb, n_pixels, d_p98, stream), "post_process_device", self)
+
+    def encode_srgb8(self, rgb: np.ndarray) -> np.ndarray:
+        """image.rs:55-66 on the device (host buffers)."""
+        src = np.ascontiguousarray(rgb, dtype=np.float32)
+        out = np.empty(src.shape, dtype=np.uint8)
+        _check(self._lib.b200rt_encode_srgb8(self._h, src.ctypes.data, src.size, out.ctypes.data), "encode_srgb8", self)
+        return out
+
+    def encode_srgb8_device(self, d_rgb: int, n_values: int, d_out: int, stream: int = 0):
+        _check(self._lib.b200rt_encode_srgb8_device(self._h, d_rgb, n_values, d_out, stream), "encode_srgb8_device", self)
 
     def stats(self) -> dict:
         s = Stats()

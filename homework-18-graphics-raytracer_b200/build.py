@@ -79,6 +79,13 @@ def build_all(force: bool = False, verbose: bool = False) -> str:
              verbose)
     objs.append(o)
 
+    src = os.path.join(CSRC, "rt_image.cu")
+    o = obj("rt_image")
+    if force or _newer(o, [src] + headers):
+        _run([nvcc, *ARCH, *NVCC_COMMON, "-fmad=false", "-Xptxas", "-v", "-Xcompiler", "-fPIC", "-c", src, "-o", o],
+             verbose)
+    objs.append(o)
+
     src = os.path.join(CSRC, "rt_filter_bench.cu")
     o = obj("rt_filter_bench")
     if force or _newer(o, [src] + headers):

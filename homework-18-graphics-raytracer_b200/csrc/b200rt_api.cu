@@ -46,6 +46,7 @@ struct b200rt_ctx {
     void* d_out = nullptr;  size_t d_out_bytes = 0;
     void* d_aux = nullptr;  size_t d_aux_bytes = 0;
     DCounters* d_cnt = nullptr;
+    void* d_pp = nullptr;   // post_process control block
     // wavefront tracer: path state / ray queues in HBM, a pinned word and an event to poll the retired counter
     void* d_wf = nullptr;   size_t d_wf_bytes = 0;
     uint32_t* h_poll = nullptr;
@@ -239,6 +240,7 @@ int b200rt_create(int device_id, b200rt_ctx** out_ctx) {
         cudaEventCreateWithFlags(&ctx->ev_poll, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->h_poll, sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->d_cnt, sizeof(DCounters)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_pp, post_process_workspace_bytes() + sizeof(float)) != cudaSuccess ||
         cudaMemset(ctx->d_cnt, 0, sizeof(DCounters)) != cudaSuccess) {
         b200rt_destroy(ctx);
         return B200RT_ERR_CUDA;
@@ -256,6 +258,7 @@ int b200rt_destroy(b200rt_ctx* ctx) {
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_aux) cudaFree(ctx->d_aux);
     if (ctx->d_cnt) cudaFree(ctx->d_cnt);
+    if (ctx->d_pp) cudaFree(ctx->d_pp);
     if (ctx->d_wf) cudaFree(ctx->d_wf);
     if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
     if (ctx->ev_poll) cudaEventDestroy(ctx->ev_poll);
@@ -545,6 +548,53 @@ int b200rt_resolve_device(b200rt_ctx* ctx, const float* d_accum, float* d_out_rg
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the CUDA default stream
     CU(launch_resolve(d_accum, d_out_rgb, n_pixels, st));
+    return B200RT_OK;
+}
+
+int b200rt_post_process_device(b200rt_ctx* ctx, float* d_rgb, size_t n_pixels, float* d_p98_out, void* cuda_stream) {
+    if (!ctx || (n_pixels && !d_rgb)) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_post_process(d_rgb, n_pixels, ctx->d_pp, d_p98_out, ctx->sm_count, (cudaStream_t)cuda_stream));
+    return B200RT_OK;
+}
+
+int b200rt_post_process(b200rt_ctx* ctx, float* rgb, size_t n_pixels, float* p98_out) {
+    if (!ctx || (n_pixels && !rgb)) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, &ctx->d_out, &ctx->d_out_bytes, std::max<size_t>(n_pixels, 1) * 3 * sizeof(float));
+    if (rc != B200RT_OK) return rc;
+    float* d_p98 = reinterpret_cast<float*>(static_cast<unsigned char*>(ctx->d_pp) + post_process_workspace_bytes());
+    CU(cudaMemcpyAsync(ctx->d_out, rgb, n_pixels * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    rc = b200rt_post_process_device(ctx, (float*)ctx->d_out, n_pixels, d_p98, ctx->stream);
+    if (rc != B200RT_OK) return rc;
+    CU(cudaMemcpyAsync(rgb, ctx->d_out, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    float p98 = 0.0f;
+    CU(cudaMemcpyAsync(&p98, d_p98, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (p98_out) *p98_out = p98;
+    return B200RT_OK;
+}
+
+int b200rt_encode_srgb8_device(b200rt_ctx* ctx, const float* d_rgb, size_t n_values, uint8_t* d_out, void* cuda_stream) {
+    if (!ctx || (n_values && (!d_rgb || !d_out))) return B200RT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_encode_srgb8(d_rgb, n_values, d_out, ctx->sm_count, (cudaStream_t)cuda_stream));
+    return B200RT_OK;
+}
+
+int b200rt_encode_srgb8(b200rt_ctx* ctx, const float* rgb, size_t n_values, uint8_t* out) {
+    if (!ctx || (n_values && (!rgb || !out))) return B200RT_ERR_INVALID;
+    if (n_values == 0) return B200RT_OK;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, &ctx->d_out, &ctx->d_out_bytes, n_values * sizeof(float));
+    if (rc != B200RT_OK) return rc;
+    rc = ensure(ctx, &ctx->d_aux, &ctx->d_aux_bytes, n_values);
+    if (rc != B200RT_OK) return rc;
+    CU(cudaMemcpyAsync(ctx->d_out, rgb, n_values * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    rc = b200rt_encode_srgb8_device(ctx, (const float*)ctx->d_out, n_values, (uint8_t*)ctx->d_aux, ctx->stream);
+    if (rc != B200RT_OK) return rc;
+    CU(cudaMemcpyAsync(out, ctx->d_aux, n_values, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return B200RT_OK;
 }
 

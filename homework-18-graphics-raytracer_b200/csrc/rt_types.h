@@ -101,5 +101,9 @@ cudaError_t launch_filter_bench(int variant, const float4* d_recs, const float4*
                                 int iters, float A, float B, float g, cudaStream_t stream, unsigned long long* pairs);
 cudaError_t launch_pipe_bench(int variant, float* d_sink, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_fp32_peak(float* d_sink, int blocks, int threads, int iters, cudaStream_t stream);
+// rt_image.cu
+size_t post_process_workspace_bytes();
+cudaError_t launch_post_process(float* d_rgb, size_t n_pixels, void* d_workspace, float* d_p98_out, int sm_count, cudaStream_t stream);
+cudaError_t launch_encode_srgb8(const float* d_rgb, size_t n_values, uint8_t* d_out, int sm_count, cudaStream_t stream);
 
 }  // namespace b200rt

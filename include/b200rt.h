@@ -227,6 +227,17 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
 int b200rt_resolve_device(b200rt_ctx* ctx, const float* d_accum, float* d_out_rgb, size_t n_pixels,
                           void* cuda_stream);
 
+/* ---- image finishers --------------------------------------------------------- */
+/* post_process, main.rs:748-762: divide every channel by the 99th-percentile luma of the image (the element at
+ * index (len as f32 * 0.99) of the sorted NORMAL lumas), if it exceeds f32::EPSILON.  In place on [n_pixels][3]
+ * linear f32; exact (radix select instead of the sort).  *p98_out = the divisor, 0 if the image was left as is
+ * (p98_out may be NULL; for the _device variant it is a device pointer). */
+int b200rt_post_process(b200rt_ctx* ctx, float* rgb, size_t n_pixels, float* p98_out);
+int b200rt_post_process_device(b200rt_ctx* ctx, float* d_rgb, size_t n_pixels, float* d_p98_out, void* cuda_stream);
+/* image.rs:55-66: linear f32 -> sRGB u8 (palette Srgb::from_linear + into_format::<u8>), n_values = 3 * pixels. */
+int b200rt_encode_srgb8(b200rt_ctx* ctx, const float* rgb, size_t n_values, uint8_t* out);
+int b200rt_encode_srgb8_device(b200rt_ctx* ctx, const float* d_rgb, size_t n_values, uint8_t* d_out, void* cuda_stream);
+
 /* World::cast, main.rs:180-326, for n rays. */
 int b200rt_intersect(b200rt_ctx* ctx, const b200rt_ray* rays, size_t n, uint32_t cast_mode,
                      b200rt_hit* hits);
