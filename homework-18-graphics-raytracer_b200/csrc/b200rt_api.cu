@@ -89,7 +89,8 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
     const double u = 5.9604644775390625e-8;   // 2^-24
     const double S = 2.0 * ((double)origin_bound + (double)ctx->scene_radius + (double)ctx->max_edge);
     const double A = 64.0 * u * S, B = 128.0 * u * S;
-    std::vector<float4> rec((size_t)std::max(n_tiles, 1u) * 256, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<float4> rec((size_t)std::max(n_tiles, 1u) * 256 * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+    float4* plain = rec.data() + (size_t)std::max(n_tiles, 1u) * 256;   // second half: [tri][4] plain records
     auto up = [](double v) { float f = (float)v; if ((double)f < v) f = std::nextafter(f, INFINITY); return f; };
     for (uint32_t tile = 0; tile < n_tiles; ++tile) {
         for (uint32_t lane = 0; lane < 32; ++lane) {
@@ -117,6 +118,8 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
                     out[4 + 4 * k + 3] = up(-c + B);
                 }
                 if (ok) for (int q = 0; q < 16; ++q) vals[h][q] = out[q];
+                for (int k = 0; k < 4; ++k)
+                    plain[4 * (size_t)idx + k] = make_float4(vals[h][4 * k], vals[h][4 * k + 1], vals[h][4 * k + 2], vals[h][4 * k + 3]);
             }
             // interleave {a,b}: entry q -> float2; two entries per float4
             for (int k = 0; k < 8; ++k)
@@ -130,6 +133,7 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
     CU(cudaMemcpyAsync(ctx->d_filter, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->scene.tri_filter = reinterpret_cast<const float4*>(ctx->d_filter);
+    ctx->scene.tri_filter_plain = ctx->scene.tri_filter + (size_t)std::max(n_tiles, 1u) * 256;
     ctx->scene.origin_bound = origin_bound;
     ctx->scene.filter_A = up(A);
     ctx->scene.filter_g = 3.814697265625e-6f;   // 2^-18
@@ -192,6 +196,7 @@ int fetch_counters(b200rt_ctx* ctx) {
     ctx->stats.wavefront_rounds = ctx->last_rounds;
     ctx->stats.cast_kernel_ms = (float)ctx->wf_timing.cast_ms;
     ctx->stats.logic_kernel_ms = (float)ctx->wf_timing.logic_ms;
+    ctx->stats.filter_kernel_ms = (float)ctx->wf_timing.filter_ms;
     ctx->stats.cast_kernel_launches = (uint32_t)ctx->wf_timing.cast_launches;
     ctx->stats.kernel_launches = ctx->last_launches;
     return B200RT_OK;
@@ -263,6 +268,7 @@ int b200rt_destroy(b200rt_ctx* ctx) {
     if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
     if (ctx->ev_poll) cudaEventDestroy(ctx->ev_poll);
     for (cudaEvent_t ev : ctx->wf_timing.pool) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->wf_timing.pool_mid) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -375,6 +381,7 @@ int b200rt_upload_scene(b200rt_ctx* ctx, const b200rt_scene* s) {
     unsigned char* base = static_cast<unsigned char*>(ctx->d_scene_blob);
     DScene& d = ctx->scene;
     d.tri_filter = nullptr;
+    d.tri_filter_plain = nullptr;
     d.tri_exact = reinterpret_cast<const float4*>(base + off_exact);
     d.tri_attr = reinterpret_cast<const float4*>(base + off_attr);
     d.sph = reinterpret_cast<const float4*>(base + off_sph);
@@ -478,7 +485,7 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
     CU(cudaEventRecord(ctx->ev0, st));
     ctx->last_rounds = 0;
     ctx->last_launches = 0;
-    ctx->wf_timing.cast_ms = ctx->wf_timing.logic_ms = 0.0;
+    ctx->wf_timing.cast_ms = ctx->wf_timing.logic_ms = ctx->wf_timing.filter_ms = 0.0;
     ctx->wf_timing.cast_launches = 0;
     if (epoch_count) {
         if (params->tracer == B200RT_TRACER_MEGAKERNEL || params->cast_mode == B200RT_CAST_BRUTE_EXACT) {

@@ -172,6 +172,15 @@ RT_DI float rcp_approx(float x) {
 RT_DI float2 pk(float a, float b) { return make_float2(a, b); }
 RT_DI float2 bc2(float a) { return make_float2(a, a); }      // becomes a scalar-broadcast FFMA2 operand (R.F32)
 
+// Packed f32x2 values held as ONE 64-bit register pair from the moment they are built.  (As float2 the compiler
+// treats the halves as independent floats and re-packs them with MOVs before every FFMA2 that uses them.)
+typedef unsigned long long P2;
+RT_DI P2 p2_pack(float lo, float hi) { P2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+RT_DI P2 p2_bc(float a) { P2 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(a)); return r; }   // scalar-broadcast operand (R.F32)
+RT_DI void p2_unpack(P2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+RT_DI P2 p2_fma(P2 a, P2 b, P2 c) { P2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+RT_DI P2 p2_mul(P2 a, P2 b) { P2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // One lane's packed pair of filter records (triangles a | b in the .x | .y halves): 32 registers.
 struct TriPair {
     float2 nx, ny, nz, d;
@@ -301,6 +310,103 @@ RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand
     }
 }
 
+// ---- building blocks of the warp-collective cast ---------------------------------------------------------------
+// The 32 x 64-bit candidate masks of one tile for the rays staged in s_rays (warp-collective; __syncwarp() before
+// and after by the caller).
+RT_DI void filter_tile(const DScene& sc, float4* __restrict__ s_rays, const TriPair& c, uint32_t n_act, uint32_t lane) {
+    uint2* s_mask = cast_slot_masks(s_rays);
+#if B200RT_FILTER_RAYS == 4
+    // four rays per iteration: four independent FFMA2 dependency chains in flight per warp
+    // (rays beyond n_act read stale slots of the 32-slot staging area, their masks are never used)
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < n_act; i0 += 4u) {
+        const uint32_t i2 = min(i0 + 2u, 30u);                       // i0 = 28 is the last possible group: no overrun
+        const float4 ro0 = s_rays[2 * i0 + 0], rd0 = s_rays[2 * i0 + 1];   // broadcast reads
+        const float4 ro1 = s_rays[2 * i0 + 2], rd1 = s_rays[2 * i0 + 3];
+        const float4 ro2 = s_rays[2 * i2 + 0], rd2 = s_rays[2 * i2 + 1];
+        const float4 ro3 = s_rays[2 * i2 + 2], rd3 = s_rays[2 * i2 + 3];
+        bool ka0, kb0, ka1, kb1, ka2, kb2, ka3, kb3;
+        filter_pair(c, ro0.x, ro0.y, ro0.z, ro0.w, rd0.x, rd0.y, rd0.z, sc.filter_A, sc.filter_g, ka0, kb0);
+        filter_pair(c, ro1.x, ro1.y, ro1.z, ro1.w, rd1.x, rd1.y, rd1.z, sc.filter_A, sc.filter_g, ka1, kb1);
+        filter_pair(c, ro2.x, ro2.y, ro2.z, ro2.w, rd2.x, rd2.y, rd2.z, sc.filter_A, sc.filter_g, ka2, kb2);
+        filter_pair(c, ro3.x, ro3.y, ro3.z, ro3.w, rd3.x, rd3.y, rd3.z, sc.filter_A, sc.filter_g, ka3, kb3);
+        const unsigned ba0 = __ballot_sync(kFullMask, ka0), bb0 = __ballot_sync(kFullMask, kb0);
+        const unsigned ba1 = __ballot_sync(kFullMask, ka1), bb1 = __ballot_sync(kFullMask, kb1);
+        const unsigned ba2 = __ballot_sync(kFullMask, ka2), bb2 = __ballot_sync(kFullMask, kb2);
+        const unsigned ba3 = __ballot_sync(kFullMask, ka3), bb3 = __ballot_sync(kFullMask, kb3);
+        if (lane == 0u) {
+            *reinterpret_cast<uint4*>(s_mask + i0) = make_uint4(ba0, bb0, ba1, bb1);
+            *reinterpret_cast<uint4*>(s_mask + i2) = make_uint4(ba2, bb2, ba3, bb3);
+        }
+    }
+#else
+    // two rays per iteration: two independent FFMA2 dependency chains in flight per warp
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < n_act; i0 += 2u) {
+        const float4 ro0 = s_rays[2 * i0 + 0], rd0 = s_rays[2 * i0 + 1];   // broadcast reads
+        const float4 ro1 = s_rays[2 * i0 + 2], rd1 = s_rays[2 * i0 + 3];   // (odd count: a stale slot, its mask is unused)
+        bool ka0, kb0, ka1, kb1;
+        filter_pair(c, ro0.x, ro0.y, ro0.z, ro0.w, rd0.x, rd0.y, rd0.z, sc.filter_A, sc.filter_g, ka0, kb0);
+        filter_pair(c, ro1.x, ro1.y, ro1.z, ro1.w, rd1.x, rd1.y, rd1.z, sc.filter_A, sc.filter_g, ka1, kb1);
+        const unsigned ba0 = __ballot_sync(kFullMask, ka0), bb0 = __ballot_sync(kFullMask, kb0);
+        const unsigned ba1 = __ballot_sync(kFullMask, ka1), bb1 = __ballot_sync(kFullMask, kb1);
+        if (lane == 0u) *reinterpret_cast<uint4*>(s_mask + i0) = make_uint4(ba0, bb0, ba1, bb1);   // one STS.128
+    }
+#endif
+}
+
+// stage a ray in slot `slot` of the warp's staging area (with its face-cull factor)
+RT_DI void stage_ray(float4* __restrict__ s_rays, uint32_t slot, const DRay& ray) {
+    const float cf = ray.face == kFront ? -kCullK : (ray.face == kBack ? kCullK : 0.0f);
+    s_rays[2 * slot + 0] = make_float4(ray.o.x, ray.o.y, ray.o.z, cf);
+    s_rays[2 * slot + 1] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f);
+}
+
+// rays outside the filter's assumptions (|o| beyond the packed bound, |dir| != 1, non-finite) go through every pair exactly
+RT_DI bool ray_trusted(const DScene& sc, const DRay& ray, float& dd) {
+    const float oo = ray.o.x * ray.o.x + ray.o.y * ray.o.y + ray.o.z * ray.o.z;
+    dd = ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z;
+    return (oo <= sc.origin_bound * sc.origin_bound) && (fabsf(dd - 1.0f) <= 1e-3f);  // false for NaN/Inf
+}
+
+// this ray's candidates of one tile from its filter mask (padding lanes masked off; untrusted rays: every triangle)
+RT_DI unsigned long long tile_candidates(const DScene& sc, uint32_t tile, uint2 m, bool trust) {
+    const uint32_t left = sc.n_tris - tile * kTileTris;              // >= 1
+    const uint32_t v_lo = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
+    const uint32_t v_hi = left >= 64u ? 0xffffffffu : (left > 32u ? ((1u << (left - 32u)) - 1u) : 0u);
+    const uint32_t c_lo = trust ? (m.x & v_lo) : v_lo;
+    const uint32_t c_hi = trust ? (m.y & v_hi) : v_hi;
+    return ((unsigned long long)c_hi << 32) | (unsigned long long)c_lo;
+}
+
+// spheres (main.rs:264-324): a conservative pre-filter of main.rs:265-268 in fused arithmetic for 32 spheres at a
+// time — squared line-sphere distance |disp|^2 |dir|^2 - (disp.dir)^2 against r^2 with a 64u (r^2 + |disp|^2)
+// slack (both sides' rounding is <= 13u of that; NaNs pass) — then the exact test of the survivors in index
+// order.  Walking a mask lets lanes that pass DIFFERENT spheres run their exact tests in the same iteration.
+RT_DI void cast_spheres(const DScene& sc, const DRay& ray, bool trust, float dd, Best& best) {
+    for (uint32_t j0 = 0; j0 < sc.n_sph; j0 += 32u) {
+        const uint32_t nj = min(32u, sc.n_sph - j0);
+        uint32_t smask = 0u;
+#pragma unroll 4
+        for (uint32_t j = 0; j < nj; ++j) {
+            const float4 s4 = sc.sph[j0 + j];
+            const float ex = s4.x - ray.o.x, ey = s4.y - ray.o.y, ez = s4.z - ray.o.z;
+            const float b = __fmaf_rn(ez, ray.d.z, __fmaf_rn(ey, ray.d.y, ex * ray.d.x));
+            const float e2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex));
+            const float r2 = s4.w * s4.w;
+            const float d2 = __fmaf_rn(-b, b, e2 * dd);
+            const float bound = __fmaf_rn(3.8146973e-6f, r2 + e2, r2);
+            if (!(trust && d2 > bound)) smask |= 1u << j;
+        }
+#pragma unroll 1
+        while (smask) {
+            const uint32_t j = (uint32_t)__ffs((int)smask) - 1u;
+            smask &= smask - 1u;
+            sphere_exact_test(sc.sph[j0 + j], (int32_t)(sc.n_tris + j0 + j), ray, best);
+        }
+    }
+}
+
 // Warp-collective cast: EVERY lane of the warp must call it (converged).  `active` lanes carry a ray.
 // s_rays: this warp's kCastSlotFloat4 staging slot in shared memory.  tile0: the lane's records of tile 0,
 // loaded once per kernel (scenes of <= 64 triangles never reload them).
@@ -310,103 +416,26 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
     Best best;
     best_init(best);
     if (act == 0u) { hit.prim = -1; return; }
-    // stage the rays COMPACTED: the k-th active lane writes slot k, so the filter loop below is a plain counted
+    // stage the rays COMPACTED: the k-th active lane writes slot k, so the filter loop is a plain counted
     // loop over slots (no find-first-set / mask bookkeeping per iteration)
     const uint32_t n_act = (uint32_t)__popc(act);
     const uint32_t rank = (uint32_t)__popc(act & ((1u << lane) - 1u));
-    if (active) {
-        const float cf = ray.face == kFront ? -kCullK : (ray.face == kBack ? kCullK : 0.0f);
-        s_rays[2 * rank + 0] = make_float4(ray.o.x, ray.o.y, ray.o.z, cf);
-        s_rays[2 * rank + 1] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f);
-    }
-    uint2* s_mask = cast_slot_masks(s_rays);
-    // rays outside the filter's assumptions go through every pair exactly
-    const float oo = ray.o.x * ray.o.x + ray.o.y * ray.o.y + ray.o.z * ray.o.z;
-    const float dd = ray.d.x * ray.d.x + ray.d.y * ray.d.y + ray.d.z * ray.d.z;
-    const bool trust = (oo <= sc.origin_bound * sc.origin_bound) && (fabsf(dd - 1.0f) <= 1e-3f);  // false for NaN/Inf
+    if (active) stage_ray(s_rays, rank, ray);
+    const uint2* s_mask = cast_slot_masks(s_rays);
+    float dd;
+    const bool trust = ray_trusted(sc, ray, dd);
     __syncwarp();
     const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
     for (uint32_t tile = 0; tile < n_tiles; ++tile) {
         TriPair c;
         if (tile == 0) c = tile0; else load_tripair(sc.tri_filter, tile, lane, c);
-#if B200RT_FILTER_RAYS == 4
-        // four rays per iteration: four independent FFMA2 dependency chains in flight per warp
-        // (rays beyond n_act read stale slots of the 32-slot staging area, their masks are never used)
-#pragma unroll 1
-        for (uint32_t i0 = 0; i0 < n_act; i0 += 4u) {
-            const uint32_t i2 = min(i0 + 2u, 30u);                       // i0 = 28 is the last possible group: no overrun
-            const float4 ro0 = s_rays[2 * i0 + 0], rd0 = s_rays[2 * i0 + 1];   // broadcast reads
-            const float4 ro1 = s_rays[2 * i0 + 2], rd1 = s_rays[2 * i0 + 3];
-            const float4 ro2 = s_rays[2 * i2 + 0], rd2 = s_rays[2 * i2 + 1];
-            const float4 ro3 = s_rays[2 * i2 + 2], rd3 = s_rays[2 * i2 + 3];
-            bool ka0, kb0, ka1, kb1, ka2, kb2, ka3, kb3;
-            filter_pair(c, ro0.x, ro0.y, ro0.z, ro0.w, rd0.x, rd0.y, rd0.z, sc.filter_A, sc.filter_g, ka0, kb0);
-            filter_pair(c, ro1.x, ro1.y, ro1.z, ro1.w, rd1.x, rd1.y, rd1.z, sc.filter_A, sc.filter_g, ka1, kb1);
-            filter_pair(c, ro2.x, ro2.y, ro2.z, ro2.w, rd2.x, rd2.y, rd2.z, sc.filter_A, sc.filter_g, ka2, kb2);
-            filter_pair(c, ro3.x, ro3.y, ro3.z, ro3.w, rd3.x, rd3.y, rd3.z, sc.filter_A, sc.filter_g, ka3, kb3);
-            const unsigned ba0 = __ballot_sync(kFullMask, ka0), bb0 = __ballot_sync(kFullMask, kb0);
-            const unsigned ba1 = __ballot_sync(kFullMask, ka1), bb1 = __ballot_sync(kFullMask, kb1);
-            const unsigned ba2 = __ballot_sync(kFullMask, ka2), bb2 = __ballot_sync(kFullMask, kb2);
-            const unsigned ba3 = __ballot_sync(kFullMask, ka3), bb3 = __ballot_sync(kFullMask, kb3);
-            if (lane == 0u) {
-                *reinterpret_cast<uint4*>(s_mask + i0) = make_uint4(ba0, bb0, ba1, bb1);
-                *reinterpret_cast<uint4*>(s_mask + i2) = make_uint4(ba2, bb2, ba3, bb3);
-            }
-        }
-#else
-        // two rays per iteration: two independent FFMA2 dependency chains in flight per warp
-#pragma unroll 1
-        for (uint32_t i0 = 0; i0 < n_act; i0 += 2u) {
-            const float4 ro0 = s_rays[2 * i0 + 0], rd0 = s_rays[2 * i0 + 1];   // broadcast reads
-            const float4 ro1 = s_rays[2 * i0 + 2], rd1 = s_rays[2 * i0 + 3];   // (odd count: a stale slot, its mask is unused)
-            bool ka0, kb0, ka1, kb1;
-            filter_pair(c, ro0.x, ro0.y, ro0.z, ro0.w, rd0.x, rd0.y, rd0.z, sc.filter_A, sc.filter_g, ka0, kb0);
-            filter_pair(c, ro1.x, ro1.y, ro1.z, ro1.w, rd1.x, rd1.y, rd1.z, sc.filter_A, sc.filter_g, ka1, kb1);
-            const unsigned ba0 = __ballot_sync(kFullMask, ka0), bb0 = __ballot_sync(kFullMask, kb0);
-            const unsigned ba1 = __ballot_sync(kFullMask, ka1), bb1 = __ballot_sync(kFullMask, kb1);
-            if (lane == 0u) *reinterpret_cast<uint4*>(s_mask + i0) = make_uint4(ba0, bb0, ba1, bb1);   // one STS.128
-        }
-#endif
+        filter_tile(sc, s_rays, c, n_act, lane);
         __syncwarp();
-        if (active) {
-            const uint2 m = s_mask[rank];
-            const uint32_t base = tile * kTileTris;
-            const uint32_t left = sc.n_tris - base;                      // >= 1
-            const uint32_t v_lo = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
-            const uint32_t v_hi = left >= 64u ? 0xffffffffu : (left > 32u ? ((1u << (left - 32u)) - 1u) : 0u);
-            const uint32_t c_lo = trust ? (m.x & v_lo) : v_lo;
-            const uint32_t c_hi = trust ? (m.y & v_hi) : v_hi;
-            const unsigned long long cand = ((unsigned long long)c_hi << 32) | (unsigned long long)c_lo;
-            confirm_tile(sc, base, cand, trust, ray, best, cs);
-        }
+        if (active) confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, s_mask[rank], trust), trust, ray, best, cs);
         __syncwarp();   // masks (and, after the last tile, the ray slots) are free again
     }
     if (active) {
-        // spheres (main.rs:264-324): a conservative pre-filter of main.rs:265-268 in fused arithmetic for 32 spheres at a
-        // time — squared line-sphere distance |disp|^2 |dir|^2 - (disp.dir)^2 against r^2 with a 64u (r^2 + |disp|^2)
-        // slack (both sides' rounding is <= 13u of that; NaNs pass) — then the exact test of the survivors in index
-        // order.  Walking a mask lets lanes that pass DIFFERENT spheres run their exact tests in the same iteration.
-        for (uint32_t j0 = 0; j0 < sc.n_sph; j0 += 32u) {
-            const uint32_t nj = min(32u, sc.n_sph - j0);
-            uint32_t smask = 0u;
-#pragma unroll 4
-            for (uint32_t j = 0; j < nj; ++j) {
-                const float4 s4 = sc.sph[j0 + j];
-                const float ex = s4.x - ray.o.x, ey = s4.y - ray.o.y, ez = s4.z - ray.o.z;
-                const float b = __fmaf_rn(ez, ray.d.z, __fmaf_rn(ey, ray.d.y, ex * ray.d.x));
-                const float e2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex));
-                const float r2 = s4.w * s4.w;
-                const float d2 = __fmaf_rn(-b, b, e2 * dd);
-                const float bound = __fmaf_rn(3.8146973e-6f, r2 + e2, r2);
-                if (!(trust && d2 > bound)) smask |= 1u << j;
-            }
-#pragma unroll 1
-            while (smask) {
-                const uint32_t j = (uint32_t)__ffs((int)smask) - 1u;
-                smask &= smask - 1u;
-                sphere_exact_test(sc.sph[j0 + j], (int32_t)(sc.n_tris + j0 + j), ray, best);
-            }
-        }
+        cast_spheres(sc, ray, trust, dd, best);
         finalize_hit(sc, best, hit, want_attrs);
         cs.casts += 1ull;
     } else {

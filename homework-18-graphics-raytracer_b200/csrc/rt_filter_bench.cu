@@ -232,6 +232,50 @@ cudaError_t launch_pipe_bench(int variant, float* d_sink, int blocks, int iters,
 }
 
 // returns the number of ray x triangle pair tests performed
+// ---------------- variants 4 / 5: rays in lanes, triangle records in CONSTANT memory -----------------------------
+// Every lane owns RAYS rays; the 64 plain records {n,d}{m0,w0}{m1,w1}{m2,w2} are warp-uniform and come from the
+// constant bank / uniform registers, so an FFMA reads two registers (ray component, accumulator), not three.
+__constant__ float4 c_recs[4 * kT];
+
+template <int RAYS, int UNROLL>
+__global__ void __launch_bounds__(256) filter_bench_const(const float4* __restrict__ rays, uint32_t* __restrict__ out, int iters,
+                                                          float A, float B, float g) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float ox[RAYS], oy[RAYS], oz[RAYS], dx[RAYS], dy[RAYS], dz[RAYS];
+#pragma unroll
+    for (int r = 0; r < RAYS; ++r) {
+        const float4 o = rays[2 * (tid * RAYS + r)], d = rays[2 * (tid * RAYS + r) + 1];
+        ox[r] = o.x; oy[r] = o.y; oz[r] = o.z; dx[r] = d.x; dy[r] = d.y; dz[r] = d.z;
+    }
+    uint32_t acc = 0u;
+    for (int it = 0; it < iters; ++it) {
+        unsigned long long mask[RAYS];
+#pragma unroll
+        for (int r = 0; r < RAYS; ++r) mask[r] = 0ull;
+#pragma unroll UNROLL
+        for (int i = 0; i < kT; ++i) {
+            const float4 q0 = c_recs[4 * i + 0], q1 = c_recs[4 * i + 1], q2 = c_recs[4 * i + 2], q3 = c_recs[4 * i + 3];
+#pragma unroll
+            for (int r = 0; r < RAYS; ++r) {
+                const float nd = __fmaf_rn(q0.z, dz[r], __fmaf_rn(q0.y, dy[r], q0.x * dx[r]));
+                const float num = __fmaf_rn(-q0.z, oz[r], __fmaf_rn(-q0.y, oy[r], __fmaf_rn(-q0.x, ox[r], q0.w)));
+                const float rc = rcp_approx(nd);
+                const float t = num * rc;
+                const float px = __fmaf_rn(t, dx[r], ox[r]), py = __fmaf_rn(t, dy[r], oy[r]), pz = __fmaf_rn(t, dz[r], oz[r]);
+                const float e0 = __fmaf_rn(q1.z, pz, __fmaf_rn(q1.y, py, __fmaf_rn(q1.x, px, q1.w)));
+                const float e1 = __fmaf_rn(q2.z, pz, __fmaf_rn(q2.y, py, __fmaf_rn(q2.x, px, q2.w)));
+                const float e2 = __fmaf_rn(q3.z, pz, __fmaf_rn(q3.y, py, __fmaf_rn(q3.x, px, q3.w)));
+                const float m = __fmaf_rn(A, fabsf(rc), fminf(fminf(fminf(e0, e1), e2), t));
+                const bool keep = (m >= 0.0f) | (fabsf(nd) < g);
+                if (keep) mask[r] |= 1ull << i;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RAYS; ++r) { acc ^= (uint32_t)mask[r] ^ (uint32_t)(mask[r] >> 32); ox[r] += 1e-3f; }
+    }
+    out[tid] = acc;
+}
+
 cudaError_t launch_filter_bench(int variant, const float4* d_recs, const float4* d_rays, uint32_t* d_out, int blocks,
                                 int iters, float A, float B, float g, cudaStream_t stream, unsigned long long* pairs) {
     const unsigned long long threads = (unsigned long long)blocks * 256ull;
@@ -240,6 +284,15 @@ cudaError_t launch_filter_bench(int variant, const float4* d_recs, const float4*
         case 1: filter_bench_v1<<<blocks, 256, 0, stream>>>(d_recs, d_rays, d_out, iters, A, B, g); *pairs = threads * kT * iters; break;
         case 2: filter_bench_rp<1><<<blocks, 256, 0, stream>>>(d_recs, d_rays, d_out, iters, A, B, g); *pairs = threads * 2 * kT * iters; break;
         case 3: filter_bench_rp<2><<<blocks, 256, 0, stream>>>(d_recs, d_rays, d_out, iters, A, B, g); *pairs = threads * 4 * kT * iters; break;
+        case 4: case 5: case 6: case 7: {
+            cudaError_t e = cudaMemcpyToSymbolAsync(c_recs, d_recs, sizeof(float4) * 4 * kT, 0, cudaMemcpyDeviceToDevice, stream);
+            if (e != cudaSuccess) return e;
+            if (variant == 4) { filter_bench_const<1, 4><<<blocks, 256, 0, stream>>>(d_rays, d_out, iters, A, B, g); *pairs = threads * kT * iters; }
+            if (variant == 5) { filter_bench_const<2, 4><<<blocks, 256, 0, stream>>>(d_rays, d_out, iters, A, B, g); *pairs = threads * 2 * kT * iters; }
+            if (variant == 6) { filter_bench_const<1, 64><<<blocks, 256, 0, stream>>>(d_rays, d_out, iters, A, B, g); *pairs = threads * kT * iters; }
+            if (variant == 7) { filter_bench_const<2, 64><<<blocks, 256, 0, stream>>>(d_rays, d_out, iters, A, B, g); *pairs = threads * 2 * kT * iters; }
+            break;
+        }
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -48,6 +48,7 @@ struct DLight {  // lights.rs:6-30
 
 struct DScene {
     const float4* tri_filter;
+    const float4* tri_filter_plain;   // [tri][4]: the same filter records, one triangle after the other (rays-in-lanes cast)
     const float4* tri_exact;
     const float4* tri_attr;
     const float4* sph;

@@ -26,6 +26,7 @@
 //   work[2][4n]  cast work items (path << 3 | slot)                                     32 B
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <string>
 
 #include "rt_cast.cuh"
 #include "rt_shade.cuh"
@@ -165,6 +166,254 @@ __global__ void __launch_bounds__(128, WF_CAST_MIN_BLOCKS) wf_cast_kernel(const 
             } else {
                 wb.sres[(size_t)pid * 4u + (slot - 1u)] = make_float2(__int_as_float(h.prim), h.t);
             }
+        }
+    }
+    if (cnt) {
+        unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+            n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
+        }
+        if (lane == 0u && n_conf) atomicAdd(&cnt->confirms, n_conf);
+        if (lane == 0u && n_fb) atomicAdd(&cnt->fallbacks, n_fb);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicAdd(&cnt->casts, (unsigned long long)n_work);
+            atomicAdd(&cnt->tri_pairs, (unsigned long long)n_work * sc.n_tris);
+            atomicAdd(&cnt->sph_pairs, (unsigned long long)n_work * sc.n_sph);
+        }
+    }
+}
+
+// ---- cast, rays in lanes (scenes of one tile: <= 64 triangles) -----------------------------------------------------
+// In a wavefront round every lane has work, so the roles of the transposed cast can be swapped back: every lane owns
+// FOUR rays, packed as two FFMA2 pairs, and the CTA's 64 filter records sit in 4 KB of shared memory; each record is
+// read once per warp as four broadcast LDS.128 and feeds 2 x 21 FFMA2 (128 ray x triangle pairs per record read).
+// Measured on B200 (tools/filter_bench.py, the filter loop alone): 53.5 % of the FP32 roofline in this form against
+// 42 % for the transposed form, whose FFMA2 read three live register pairs each.  Keep / reject is the sign bit of
+// max(min(e0,e1,e2,t,c) + A|r|, g - |nd|), shifted into a per-ray mask (no predicates, no ballots).
+// The packed ray operands are 64-bit values built ONCE per block of rays (P2, rt_cast.cuh): as float2 arrays the
+// compiler re-packed them from scattered registers before every use (77 MOVs per 168 FFMA2 issue slots in the loop).
+// Phase 2 (certified select, spheres, attributes) then runs per lane for its four rays, which it reads back from a
+// per-thread shared-memory slot (no dynamically indexed register arrays, no local memory).
+#ifndef WF_CAST_RL_MIN_BLOCKS
+#define WF_CAST_RL_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf,
+                                                                               DCounters* __restrict__ cnt) {
+    __shared__ float4 s_tile[4 * kTileTris];
+    __shared__ float4 s_ro[4][128];    // {origin, ray meta}   of ray j of thread t
+    __shared__ float4 s_rd[4][128];    // {direction, work item}
+    __shared__ uint2 s_mk[4][128];     // candidate mask
+    const uint32_t lane = threadIdx.x & 31u, tid = threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
+    const uint32_t n_work = wb.ctl->c[buf].work;
+    if (n_work == 0u) return;
+    for (uint32_t i = threadIdx.x; i < 4u * kTileTris; i += blockDim.x) s_tile[i] = sc.tri_filter_plain[i];
+    __syncthreads();
+    const uint32_t* __restrict__ work = wb.work + (size_t)buf * 4u * wb.n;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    const P2 A2 = p2_bc(sc.filter_A);
+    const float g = sc.filter_g;
+    // exactly 1.0f, but opaque to ptxas: a packed multiply by it MATERIALISES each ray operand in its own aligned
+    // register pair (a plain pack is coalesced with the LDG.128 destination quads and re-packed inside the loop)
+    const P2 one2 = p2_bc(__fmaf_rn(sc.filter_g, 0.0f, 1.0f));
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 128u; base < n_work; base += warps_total * 128u) {
+        // this lane's four rays: work items base + lane + 32 j
+        P2 ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], cf[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            DRay r[2];
+            float c[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * k + h;
+                const uint32_t idx = base + lane + 32u * (uint32_t)j;
+                r[h].o = mk3(0.f, 0.f, 0.f); r[h].d = mk3(0.f, 0.f, 1.f); r[h].face = kFront; r[h].ex_prim = -1; r[h].ex_face = kFront;
+                uint32_t item = 0xffffffffu;
+                if (idx < n_work) {
+                    item = work[idx];
+                    const PathMem pm{wb.st, wb.req, item >> 3};
+                    if ((item & 7u) == 0u) pm.get_ray(r[h]);
+                    else pm.get_shadow_ray((item & 7u) - 1u, r[h]);
+                }
+                c[h] = r[h].face == kFront ? -kCullK : (r[h].face == kBack ? kCullK : 0.0f);
+                s_ro[j][tid] = make_float4(r[h].o.x, r[h].o.y, r[h].o.z, u2f(pack_ray_meta(r[h].face, r[h].ex_prim, r[h].ex_face)));
+                s_rd[j][tid] = make_float4(r[h].d.x, r[h].d.y, r[h].d.z, u2f(item));
+            }
+            ox[k] = p2_mul(p2_pack(r[0].o.x, r[1].o.x), one2); oy[k] = p2_mul(p2_pack(r[0].o.y, r[1].o.y), one2);
+            oz[k] = p2_mul(p2_pack(r[0].o.z, r[1].o.z), one2);
+            dx[k] = p2_mul(p2_pack(r[0].d.x, r[1].d.x), one2); dy[k] = p2_mul(p2_pack(r[0].d.y, r[1].d.y), one2);
+            dz[k] = p2_mul(p2_pack(r[0].d.z, r[1].d.z), one2);
+            cf[k] = p2_mul(p2_pack(c[0], c[1]), one2);
+        }
+        // phase 1: reject masks (bit set = rejected), triangle i in bit (31 - i) of its half
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            uint32_t rj0 = 0u, rj1 = 0u, rj2 = 0u, rj3 = 0u;
+#pragma unroll 2
+            for (int i = 0; i < 32; ++i) {
+                const float4* q = s_tile + 4 * (32 * half + i);
+                const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const P2 nd = p2_fma(p2_bc(q0.z), dz[k], p2_fma(p2_bc(q0.y), dy[k], p2_mul(p2_bc(q0.x), dx[k])));
+                    const P2 num = p2_fma(p2_bc(-q0.z), oz[k], p2_fma(p2_bc(-q0.y), oy[k], p2_fma(p2_bc(-q0.x), ox[k], p2_bc(q0.w))));
+                    float nda, ndb;
+                    p2_unpack(nd, nda, ndb);
+                    const float ra = rcp_approx(nda), rb = rcp_approx(ndb);
+                    const P2 t = p2_mul(num, p2_pack(ra, rb));
+                    const P2 cull = p2_mul(nd, cf[k]);
+                    const P2 px = p2_fma(t, dx[k], ox[k]), py = p2_fma(t, dy[k], oy[k]), pz = p2_fma(t, dz[k], oz[k]);
+                    const P2 e0 = p2_fma(p2_bc(q1.z), pz, p2_fma(p2_bc(q1.y), py, p2_fma(p2_bc(q1.x), px, p2_bc(q1.w))));
+                    const P2 e1 = p2_fma(p2_bc(q2.z), pz, p2_fma(p2_bc(q2.y), py, p2_fma(p2_bc(q2.x), px, p2_bc(q2.w))));
+                    const P2 e2 = p2_fma(p2_bc(q3.z), pz, p2_fma(p2_bc(q3.y), py, p2_fma(p2_bc(q3.x), px, p2_bc(q3.w))));
+                    float e0a, e0b, e1a, e1b, e2a, e2b, ta, tb, ca, cb;
+                    p2_unpack(e0, e0a, e0b); p2_unpack(e1, e1a, e1b); p2_unpack(e2, e2a, e2b); p2_unpack(t, ta, tb); p2_unpack(cull, ca, cb);
+                    const float ma = fminf(fminf(fminf(e0a, e1a), e2a), fminf(ta, ca));
+                    const float mb = fminf(fminf(fminf(e0b, e1b), e2b), fminf(tb, cb));
+                    const P2 ms = p2_fma(A2, p2_pack(fabsf(ra), fabsf(rb)), p2_pack(ma, mb));
+                    float msa, msb;
+                    p2_unpack(ms, msa, msb);
+                    // keep iff ms >= 0 or |nd| < g  <=>  max(ms, g - |nd|) is not negative (NaN ms: the second operand decides)
+                    const float ka = fmaxf(msa, g - fabsf(nda)), kb = fmaxf(msb, g - fabsf(ndb));
+                    if (k == 0) { rj0 = __funnelshift_l(__float_as_uint(ka), rj0, 1); rj1 = __funnelshift_l(__float_as_uint(kb), rj1, 1); }
+                    else        { rj2 = __funnelshift_l(__float_as_uint(ka), rj2, 1); rj3 = __funnelshift_l(__float_as_uint(kb), rj3, 1); }
+                }
+            }
+            const uint32_t k0 = ~__brev(rj0), k1 = ~__brev(rj1), k2 = ~__brev(rj2), k3 = ~__brev(rj3);
+            if (half == 0) { s_mk[0][tid].x = k0; s_mk[1][tid].x = k1; s_mk[2][tid].x = k2; s_mk[3][tid].x = k3; }
+            else           { s_mk[0][tid].y = k0; s_mk[1][tid].y = k1; s_mk[2][tid].y = k2; s_mk[3][tid].y = k3; }
+        }
+        // phase 2, ray by ray (every thread reads only its own slots: no barrier)
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const float4 a = s_ro[j][tid], b = s_rd[j][tid];
+            const uint32_t item = f2u(b.w);
+            if (item == 0xffffffffu) continue;
+            const uint32_t pid = item >> 3, slot = item & 7u;
+            const uint32_t meta = f2u(a.w);
+            DRay r;
+            r.o = mk3(a); r.d = mk3(b);
+            r.face = meta & 3u; r.ex_face = (meta >> 2) & 3u; r.ex_prim = (int32_t)(meta >> 4) - 1;
+            float dd;
+            const bool trust = ray_trusted(sc, r, dd);
+            Best best;
+            best_init(best);
+            confirm_tile(sc, 0u, tile_candidates(sc, 0u, s_mk[j][tid], trust), trust, r, best, cs);
+            cast_spheres(sc, r, trust, dd, best);
+            DHit h;
+            h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
+            finalize_hit(sc, best, h, slot == 0u);
+            if (slot == 0u) {
+                const uint32_t m2 = h.prim >= 0 ? (h.face | (h.object << 8)) : 0u;
+                wb.res[(size_t)pid * 2u + 0u] = make_float4(__int_as_float(h.prim), u2f(m2), h.t, h.uv.x);
+                wb.res[(size_t)pid * 2u + 1u] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.uv.y);
+            } else {
+                wb.sres[(size_t)pid * 4u + (slot - 1u)] = make_float2(__int_as_float(h.prim), h.t);
+            }
+        }
+    }
+    if (cnt) {
+        unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+            n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
+        }
+        if (lane == 0u && n_conf) atomicAdd(&cnt->confirms, n_conf);
+        if (lane == 0u && n_fb) atomicAdd(&cnt->fallbacks, n_fb);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicAdd(&cnt->casts, (unsigned long long)n_work);
+            atomicAdd(&cnt->tri_pairs, (unsigned long long)n_work * sc.n_tris);
+            atomicAdd(&cnt->sph_pairs, (unsigned long long)n_work * sc.n_sph);
+        }
+    }
+}
+
+// ---- cast, split in two kernels (scenes of <= kSplitMaxTiles tiles) ------------------------------------------------
+// wf_filter_kernel   phase 1 alone: the packed-FFMA2 filter loop for every ray of the round, nothing else.  Few
+//                    registers (the lane's triangle pair + two rays in flight), so 6 warps per sub-partition hide the
+//                    FFMA2 / MUFU dependency latencies that the fused kernel (4 warps, 128 registers) cannot: this is
+//                    the FP32-roofline kernel.  Output: the 64-bit candidate mask of every (ray, tile), 8 B per ray.
+// wf_owner_kernel    phase 2 for every ray: certified select + exact test, spheres, hit attributes.  Plain per-lane code.
+#ifndef WF_FILTER_MIN_BLOCKS
+#define WF_FILTER_MIN_BLOCKS 6
+#endif
+#ifndef WF_OWNER_MIN_BLOCKS
+#define WF_OWNER_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(128, WF_FILTER_MIN_BLOCKS) wf_filter_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    __shared__ float4 s_rays_all[4][kCastSlotFloat4];
+    float4* s_rays = s_rays_all[warp];
+    // the counters the logic kernels of this round append to
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
+    const uint32_t n_work = wb.ctl->c[buf].work;
+    if (n_work == 0u) return;
+    TriPair tile0;
+    load_tripair(sc.tri_filter, 0, lane, tile0);
+    const uint32_t* __restrict__ work = wb.work + (size_t)buf * 4u * wb.n;
+    const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
+    const uint2* s_mask = cast_slot_masks(s_rays);
+    const uint32_t stride = gridDim.x * 4u * 32u;
+    for (uint32_t base = (blockIdx.x * 4u + warp) * 32u; base < n_work; base += stride) {
+        const uint32_t idx = base + lane;
+        const bool active = idx < n_work;
+        if (active) {
+            const uint32_t item = work[idx];
+            const PathMem pm{wb.st, wb.req, item >> 3};
+            DRay r;
+            if ((item & 7u) == 0u) pm.get_ray(r);
+            else pm.get_shadow_ray((item & 7u) - 1u, r);
+            stage_ray(s_rays, lane, r);
+        }
+        __syncwarp();
+        const uint32_t n_act = min(32u, n_work - base);
+        for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+            TriPair c;
+            if (tile == 0) c = tile0; else load_tripair(sc.tri_filter, tile, lane, c);
+            filter_tile(sc, s_rays, c, n_act, lane);
+            __syncwarp();
+            if (active) wb.masks[(size_t)idx * n_tiles + tile] = s_mask[lane];
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, WF_OWNER_MIN_BLOCKS) wf_owner_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf,
+                                                                          DCounters* __restrict__ cnt) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_work = wb.ctl->c[buf].work;
+    const uint32_t* __restrict__ work = wb.work + (size_t)buf * 4u * wb.n;
+    const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_work; idx += gridDim.x * blockDim.x) {
+        const uint32_t item = work[idx];
+        const uint32_t pid = item >> 3, slot = item & 7u;
+        const PathMem pm{wb.st, wb.req, pid};
+        DRay r;
+        if (slot == 0u) pm.get_ray(r);
+        else pm.get_shadow_ray(slot - 1u, r);
+        float dd;
+        const bool trust = ray_trusted(sc, r, dd);
+        Best best;
+        best_init(best);
+        for (uint32_t tile = 0; tile < n_tiles; ++tile)
+            confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, wb.masks[(size_t)idx * n_tiles + tile], trust), trust, r, best, cs);
+        cast_spheres(sc, r, trust, dd, best);
+        DHit h;
+        h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
+        finalize_hit(sc, best, h, slot == 0u);
+        if (slot == 0u) {
+            const uint32_t meta = h.prim >= 0 ? (h.face | (h.object << 8)) : 0u;
+            wb.res[(size_t)pid * 2u + 0u] = make_float4(__int_as_float(h.prim), u2f(meta), h.t, h.uv.x);
+            wb.res[(size_t)pid * 2u + 1u] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.uv.y);
+        } else {
+            wb.sres[(size_t)pid * 4u + (slot - 1u)] = make_float2(__int_as_float(h.prim), h.t);
         }
     }
     if (cnt) {
@@ -610,7 +859,7 @@ __global__ void wf_combine_kernel(const WfBuffers wb, const DParams p, float4* _
 
 // ---- host side -----------------------------------------------------------------------------------------------
 size_t wf_workspace_bytes_per_path() {
-    return (size_t)kStateRows * 16 + WF_REQ_ROWS * 16 + 32 + 32 + 2 * WF_SEG_COUNT * 4 + 2 * 4 * 4;
+    return (size_t)kStateRows * 16 + WF_REQ_ROWS * 16 + 32 + 32 + 2 * WF_SEG_COUNT * 4 + 2 * 4 * 4 + 4 * WF_SPLIT_MAX_TILES * 8;
 }
 size_t wf_workspace_bytes(uint32_t n_paths) {
     return sizeof(WfControl) + 256 + (size_t)n_paths * wf_workspace_bytes_per_path() + 16 * 64;
@@ -647,6 +896,7 @@ static WfBuffers wf_carve(void* workspace, uint32_t n_paths, uint32_t n_pixels, 
     wb.sres = reinterpret_cast<float2*>(b + off);              off = align(off + n * 32);
     wb.q = reinterpret_cast<uint32_t*>(b + off);               off = align(off + n * 2 * WF_SEG_COUNT * 4);
     wb.work = reinterpret_cast<uint32_t*>(b + off);            off = align(off + n * 2 * 4 * 4);
+    wb.masks = reinterpret_cast<uint2*>(b + off);              off = align(off + n * 4 * WF_SPLIT_MAX_TILES * 8);
     wb.n = n_paths; wb.n_pixels = n_pixels; wb.epar = epar;
     return wb;
 }
@@ -660,6 +910,13 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     cudaError_t e = cudaMemsetAsync(wb.ctl, 0, sizeof(WfControl), stream);
     if (e != cudaSuccess) return e;
     const int cast_blocks = sm_count * WF_CAST_MIN_BLOCKS;
+    // small scenes: phase 1 and phase 2 of the cast as two kernels (B200RT_WF_FUSED_CAST=1 keeps them fused: tuning)
+    const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
+    // B200RT_WF_CAST = rl (default for one-tile scenes) | fused (default otherwise) | split : tuning / measurement
+    const char* cast_env = getenv("B200RT_WF_CAST");
+    const std::string cast_sel = cast_env ? cast_env : "";
+    const bool rays_in_lanes = n_tiles == 1 && (cast_sel.empty() || cast_sel == "rl");
+    const bool split = !rays_in_lanes && n_tiles >= 1 && n_tiles <= WF_SPLIT_MAX_TILES && cast_sel == "split";
     auto logic_blocks = [&](int min_blocks) { return sm_count * min_blocks; };
     // round 0: every slot opens its first sample
     wf_logic_kernel<WF_SEG_INIT><<<logic_blocks(LogicCfg<WF_SEG_INIT>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, 1u, d_cnt);
@@ -677,11 +934,25 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                     if (e != cudaSuccess) return e;
                     timing->pool.push_back(ev);
                 }
+                while (timing->pool_mid.size() < (size_t)(round - first_round_of_group + 1)) {
+                    cudaEvent_t ev;
+                    e = cudaEventCreate(&ev);
+                    if (e != cudaSuccess) return e;
+                    timing->pool_mid.push_back(ev);
+                }
                 ev_a = timing->pool[2 * (round - first_round_of_group)];
                 ev_b = timing->pool[2 * (round - first_round_of_group) + 1];
                 cudaEventRecord(ev_a, stream);
             }
-            wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+            if (rays_in_lanes) {
+                wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+            } else if (split) {
+                wf_filter_kernel<<<sm_count * WF_FILTER_MIN_BLOCKS, 128, 0, stream>>>(sc, wb, buf);
+                if (timing) cudaEventRecord(timing->pool_mid[round - first_round_of_group], stream);
+                wf_owner_kernel<<<sm_count * WF_OWNER_MIN_BLOCKS, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+            } else {
+                wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+            }
             if (timing) cudaEventRecord(ev_b, stream);
             wf_logic_kernel<WF_SEG_PRIMARY><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
             wf_logic_kernel<WF_SEG_SHADE><<<logic_blocks(LogicCfg<WF_SEG_SHADE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
@@ -702,6 +973,10 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                 cudaEventElapsedTime(&ms, timing->pool[2 * g], timing->pool[2 * g + 1]);
                 timing->cast_ms += ms;
                 timing->cast_launches += 1;
+                if (split) {
+                    cudaEventElapsedTime(&ms, timing->pool[2 * g], timing->pool_mid[g]);
+                    timing->filter_ms += ms;
+                }
                 if (g + 1 < round - first_round_of_group) {       // cast end -> next cast start = the logic kernels of the round
                     cudaEventElapsedTime(&ms, timing->pool[2 * g + 1], timing->pool[2 * g + 2]);
                     timing->logic_ms += ms;
@@ -714,7 +989,7 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     }
     wf_combine_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(wb, p, reinterpret_cast<float4*>(d_accum));
     if (rounds_out) *rounds_out = round;
-    if (launches_out) *launches_out += 2u + round * (p.depth <= 0 ? 6u : 5u);
+    if (launches_out) *launches_out += 2u + round * ((p.depth <= 0 ? 6u : 5u) + (split ? 1u : 0u));
     return cudaGetLastError();
 }
 

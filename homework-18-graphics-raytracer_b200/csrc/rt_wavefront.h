@@ -32,6 +32,7 @@ struct WfControl {
 };
 
 constexpr int WF_STATE_ROWS = 12;   // float4 rows of path state (192 B = 6 sectors)
+constexpr int WF_SPLIT_MAX_TILES = 2;  // scenes of up to 128 triangles run the cast as filter kernel + owner kernel
 constexpr int WF_REQ_ROWS = 6;      // path ray (2) + 4 shadow directions (96 B = 3 sectors)
 #ifndef WF_LOGIC_MIN_BLOCKS
 #define WF_LOGIC_MIN_BLOCKS 2
@@ -45,14 +46,15 @@ struct WfBuffers {
     float2* sres;            // [n][4]
     uint32_t* q;             // [2][WF_SEG_COUNT][n]
     uint32_t* work;          // [2][4n]
+    uint2* masks;            // [4n][n_tiles] candidate masks between wf_filter_kernel and wf_owner_kernel
     uint32_t n, n_pixels, epar;
 };
 
 // Per-kernel device times of a wavefront render (filled when the caller asks for them): CUDA events on the
 // launching stream around every wf_cast_kernel launch.
 struct WfKernelTiming {
-    std::vector<cudaEvent_t> pool;
-    double cast_ms = 0.0, logic_ms = 0.0;
+    std::vector<cudaEvent_t> pool, pool_mid;
+    double cast_ms = 0.0, logic_ms = 0.0, filter_ms = 0.0;
     uint64_t cast_launches = 0;
 };
 

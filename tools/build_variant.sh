@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/.."
 mkdir -p tools/_variants/obj_$1
 C=homework-18-graphics-raytracer_b200/csrc
-for f in rt_kernels rt_wavefront rt_filter_bench b200rt_api; do
+for f in rt_kernels rt_wavefront rt_image rt_filter_bench b200rt_api; do
   extra=""; [ $f = b200rt_api ] && extra="-Xcompiler -ffp-contract=off"
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -I include -I $C -fmad=false $2 -Xcompiler -fPIC $extra -c $C/$f.cu -o tools/_variants/obj_$1/$f.o &
 done

@@ -8,7 +8,7 @@ peak, mhz = ctx.measure_fp32_peak()
 print("ffma loop TFLOP/s", peak, "eff MHz", mhz, info)
 nominal = info['sm_count']*128*2*1.965e9/1e12
 for bps in (2, 4, 8):
-    for v in (0, 1, 2, 3):
+    for v in (0, 1, 2, 3, 4, 5, 6, 7):
         ms, pairs = ctx.filter_bench(v, bps, 256)
         tf = pairs*36/ (ms*1e-3)/1e12
         print(f"variant {v} blocks/SM {bps}: {ms:.3f} ms  {pairs/ms/1e6:.1f} Gpairs/s  algorithmic {tf:.2f} TFLOP/s = {100*tf/nominal:.1f}% of {nominal:.1f}")
