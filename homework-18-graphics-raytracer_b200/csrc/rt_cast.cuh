@@ -245,8 +245,9 @@ RT_DI uint2* cast_slot_masks(float4* s_rays) { return reinterpret_cast<uint2*>(s
 //
 // CERTIFIED SELECT.  The reference walks the candidates in index order through the exact test.  Here each
 // candidate is first classified with a few instructions:
-//   * face culling and the exclusion (main.rs:185-200) depend only on the sign of n.dir, evaluated with the
-//     reference's own non-fused dot product: culled / excluded candidates are dropped, exactly as the walk would;
+//   * face culling and the exclusion (main.rs:185-200) depend only on the sign of n.dir, which the fused dot product
+//     shares with the reference's whenever |n.dir| >= g: culled / excluded candidates are dropped, exactly as the
+//     walk would;
 //   * the filter's estimate t_i (|t_i - t_exact| <= delta_i = A/|nd|, the bound the filter itself relies on)
 //     drops candidates with t_i + delta_i < 0 (main.rs:205) or t_i - delta_i > best.t (main.rs:229-233);
 //   * near-parallel candidates (|nd| < g) have no usable estimate: set U.
@@ -256,8 +257,11 @@ RT_DI uint2* cast_slot_masks(float4* s_rays) { return reinterpret_cast<uint2*>(s
 // strict distance test whatever their inside test says, and no tie with them is possible.  A NaN distance (ray
 // inside a triangle's plane, 0/0 at main.rs:204) makes the walk order-dependent (main.rs:229-231 accepts NaN),
 // so it, like any overlap of bounds, restores `best` and takes the reference's walk over all candidates.
+//   planes: the {n, d} rows (stride 4 float4) of the tile's triangles for the classification — sc.tri_exact, or a
+//   shared-memory copy of the plain filter records, whose first row holds the same bits (degenerate triangles are
+//   all-zero there: n.dir = 0, set U).
 RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand, bool certify, const DRay& ray,
-                        Best& best, CastStats& cs) {
+                        Best& best, CastStats& cs, const float4* __restrict__ planes) {
     if (cand == 0ull) return;
     unsigned long long todo = cand;
     bool fast = false;
@@ -270,12 +274,22 @@ RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand
         while (rem) {
             const uint32_t i = (uint32_t)__ffsll((long long)rem) - 1u;
             rem &= rem - 1ull;
-            const float4 q0 = sc.tri_exact[4 * (size_t)(base + i)];
-            const bool bf = dot(mk3(q0), ray.d) > 0.0f;                               // primitives.rs:45, the reference's bits
+            const float4 q0 = planes[4 * i];
+            const float nd = __fmaf_rn(q0.z, ray.d.z, __fmaf_rn(q0.y, ray.d.y, q0.x * ray.d.x));
+            if (!(fabsf(nd) >= sc.filter_g)) {
+                // near-parallel: only the reference's own non-fused dot knows the face (exactly 0 for axis-aligned
+                // walls against an axis-aligned light: front faces, which every shadow ray culls — main.rs:185-188)
+                const bool bfx = dot(mk3(q0), ray.d) > 0.0f;                          // primitives.rs:45
+                if ((bfx && ray.face == kFront) || (!bfx && ray.face == kBack)) continue;
+                if (excluded(ray, (int32_t)(base + i), bfx)) continue;
+                amb |= 1ull << i;
+                continue;
+            }
+            // |nd| >= g = 2^-18 is 16x the rounding of either form of the dot product (|n| = 1, |dir|^2 within 1e-3 of 1):
+            // the sign of the fused nd is the sign of the reference's non-fused n.dir (primitives.rs:45)
+            const bool bf = nd > 0.0f;
             if ((bf && ray.face == kFront) || (!bf && ray.face == kBack)) continue;   // main.rs:185-188
             if (excluded(ray, (int32_t)(base + i), bf)) continue;                     // main.rs:190-200
-            const float nd = __fmaf_rn(q0.z, ray.d.z, __fmaf_rn(q0.y, ray.d.y, q0.x * ray.d.x));
-            if (!(fabsf(nd) >= sc.filter_g)) { amb |= 1ull << i; continue; }
             const float num = __fmaf_rn(q0.z, -ray.o.z, __fmaf_rn(q0.y, -ray.o.y, __fmaf_rn(q0.x, -ray.o.x, q0.w)));
             const float r = rcp_approx(nd);
             const float t = num * r, delta = sc.filter_A * fabsf(r);
@@ -431,7 +445,8 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
         if (tile == 0) c = tile0; else load_tripair(sc.tri_filter, tile, lane, c);
         filter_tile(sc, s_rays, c, n_act, lane);
         __syncwarp();
-        if (active) confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, s_mask[rank], trust), trust, ray, best, cs);
+        if (active) confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, s_mask[rank], trust), trust, ray, best, cs,
+                                 sc.tri_exact + 4 * (size_t)(tile * kTileTris));
         __syncwarp();   // masks (and, after the last tile, the ray slots) are free again
     }
     if (active) {
