@@ -342,7 +342,9 @@ def run_b200(args):
     flops = tri_pairs * FLOP_TRI + sph_pairs * FLOP_SPH          # algorithmic flop of one step on this rank
     achieved = flops / (k_ms_total * 1e-3) / 1e12                # ... over the device time of the dominant kernel's launches
     live_peak, live_mhz = ctx.measure_fp32_peak()
-    kname = "wf_cast_kernel" if wavefront else f"trace_kernel<{tracer}>"
+    # scenes of one 64-triangle tile run the rays-in-lanes cast kernel (rt_wavefront.cu), larger ones the warp-transposed one
+    kname = (("wf_cast_rl_kernel" if scene_world.scene().n_triangles <= 64 else "wf_cast_kernel") if wavefront
+             else f"trace_kernel<{tracer}>")
     # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload only)
     traffic = None
     try:
@@ -397,7 +399,7 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc + (" [REDUCED SIZE: dev run]" if reduced else ""), "width": W, "height": H,
                        "depth": depth, "epochs": epochs, "sharding": ("epochs" if tracer == "distributed" else "rows"),
-                       "cast_mode": "two_phase", "tracer": args.tracer if tracer == "distributed" else "megakernel", "l2": "path state + ray buffers (%.1f GB per 16-epoch batch) and the accumulation buffer (%.1f MB) exceed L2; scene records stay in registers / L1" % (W * H * 16 * 392 / 1e9, W * H * 16 / 1e6)},
+                       "cast_mode": "two_phase", "tracer": args.tracer if tracer == "distributed" else "megakernel", "l2": "path state + ray buffers (%.1f GB per 16-epoch batch) and the accumulation buffer (%.1f MB) exceed L2; scene records stay in registers / L1" % (W * H * 16 * 440 / 1e9, W * H * 16 / 1e6)},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},

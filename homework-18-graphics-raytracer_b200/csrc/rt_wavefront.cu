@@ -23,7 +23,7 @@
 //   res [n][2]   result of the path ray {prim, meta, t, uv.x}{normal, uv.y}             32 B
 //   sres[n][4]   float2 {prim, t} per shadow ray                                        32 B
 //   q   [2][6][n] path ids per consumer segment (double buffered by round parity)       48 B
-//   work[2][4n]  cast work items (path << 3 | slot)                                     32 B
+//   work[2][5n]  cast work items (path << 3 | slot): the path ray + up to 4 shadow rays  40 B
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include <string>
@@ -64,7 +64,11 @@ enum : uint32_t {
     F_TIR = 1u << 5,            // refraction step in flight is a total-internal-reflection bounce (else the first inside ray)
     F_NEED_SHIFT = 6,           // 4 bits: lights of the current chunk with a shadow ray in flight
     F_LI0_SHIFT = 10,           // 12 bits: first light of the current chunk
-    F_PARTIAL = 1u << 22        // ROW_HI_POS holds the get_shade sum of earlier chunks
+    F_PARTIAL = 1u << 22,       // ROW_HI_POS holds the get_shade sum of earlier chunks
+    // fused levels (scenes of <= 4 lights): the next level's select / scatter ran when the hit was reached, and its
+    // ray travels in the same round as the hit's shadow rays
+    F_PRE = 1u << 23,           // a path ray (bounce, or the first inside ray of get_refract) is in flight with the shadow rays
+    F_BLACK = 1u << 24          // the next level ends the sample black (main.rs:559-561 / 366-368): close it after get_shade
 };
 enum : uint32_t { SH_FINAL = 0, SH_NEXT_MIX = 1, SH_NEXT_REFR = 2 };
 
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(128, WF_CAST_MIN_BLOCKS) wf_cast_kernel(const 
         tile0.nx = tile0.ny = tile0.nz = tile0.d = tile0.m0x = tile0.m0y = tile0.m0z = tile0.w0 = tile0.m1x = tile0.m1y = tile0.m1z =
             tile0.w1 = tile0.m2x = tile0.m2y = tile0.m2z = tile0.w2 = z;
     }
-    const uint32_t* __restrict__ work = wb.work + (size_t)buf * 4u * wb.n;
+    const uint32_t* __restrict__ work = wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n;
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
     const uint32_t stride = gridDim.x * 4u * 32u;
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(128, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_kernel(
     if (n_work == 0u) return;
     for (uint32_t i = threadIdx.x; i < 4u * kTileTris; i += blockDim.x) s_tile[i] = sc.tri_filter_plain[i];
     __syncthreads();
-    const uint32_t* __restrict__ work = wb.work + (size_t)buf * 4u * wb.n;
+    const uint32_t* __restrict__ work = wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n;
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
     const P2 A2 = p2_bc(sc.filter_A);
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(128, WF_FILTER_MIN_BLOCKS) wf_filter_kernel(co
     if (n_work == 0u) return;
     TriPair tile0;
     load_tripair(sc.tri_filter, 0, lane, tile0);
-    const uint32_t* __restrict__ work = wb.work + (size_t)buf * 4u * wb.n;
+    const uint32_t* __restrict__ work = wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n;
     const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
     const uint2* s_mask = cast_slot_masks(s_rays);
     const uint32_t stride = gridDim.x * 4u * 32u;
@@ -415,7 +419,7 @@ __global__ void __launch_bounds__(128, WF_OWNER_MIN_BLOCKS) wf_owner_kernel(cons
                                                                           DCounters* __restrict__ cnt) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n_work = wb.ctl->c[buf].work;
-    const uint32_t* __restrict__ work = wb.work + (size_t)buf * 4u * wb.n;
+    const uint32_t* __restrict__ work = wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n;
     const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
@@ -466,12 +470,16 @@ __global__ void __launch_bounds__(128, WF_OWNER_MIN_BLOCKS) wf_owner_kernel(cons
 
 // One instantiation per segment: each is a small kernel (the code of the other segments is compiled out), so it keeps
 // few registers and many warps in flight — these kernels are bound by the latency of gathering path rows from HBM.
-template <int SEG> struct LogicCfg { static constexpr int kMinBlocks = 3; };
-template <> struct LogicCfg<WF_SEG_INIT> { static constexpr int kMinBlocks = 4; };
-template <> struct LogicCfg<WF_SEG_REFR> { static constexpr int kMinBlocks = 4; };
+#ifndef WF_FUSED_SHADE_MIN_BLOCKS
+#define WF_FUSED_SHADE_MIN_BLOCKS 2
+#endif
+template <int SEG, bool FUSED = false> struct LogicCfg { static constexpr int kMinBlocks = 3; };
+template <> struct LogicCfg<WF_SEG_INIT, false> { static constexpr int kMinBlocks = 4; };
+template <> struct LogicCfg<WF_SEG_REFR, false> { static constexpr int kMinBlocks = 4; };
+template <> struct LogicCfg<WF_SEG_SHADE, true> { static constexpr int kMinBlocks = WF_FUSED_SHADE_MIN_BLOCKS; };   // shade + arrival + next level in one pass
 
-template <int SEG>
-__global__ void __launch_bounds__(256, LogicCfg<SEG>::kMinBlocks) wf_logic_kernel(const DScene sc, const DCamera cam, const DParams p,
+template <int SEG, bool FUSED>
+__global__ void __launch_bounds__(256, LogicCfg<SEG, FUSED>::kMinBlocks) wf_logic_kernel(const DScene sc, const DCamera cam, const DParams p,
                                                           const WfBuffers wb, const uint32_t buf,
                                                           DCounters* __restrict__ cnt) {
     constexpr int seg = SEG;
@@ -503,6 +511,8 @@ __global__ void __launch_bounds__(256, LogicCfg<SEG>::kMinBlocks) wf_logic_kerne
         uint32_t h_rayface = kFront;
         f3 shade = mk3(0.f, 0.f, 0.f);
         bool do_level = false, do_shade_begin = false, do_finish = false;
+        bool pre_level = false;     // fused levels: do_level runs for the level AFTER the pending get_shade (depth - 1)
+        bool pre_ray = false;       // ... and requested a path ray that travels with the shadow rays
         bool w_hit = false, w_dirs = false, w_acc = false, w_pend = false, w_rng = false;   // rows to write back
         int out = OUT_NONE;
         DRay ray;
@@ -533,53 +543,101 @@ __global__ void __launch_bounds__(256, LogicCfg<SEG>::kMinBlocks) wf_logic_kerne
                 const float4 r4 = pm.ld(ROW_PEND);
                 pend = mk3(r4); rf_travel = r4.w;
             }
-            if (seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE) {
+            if (seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE || (FUSED && seg == WF_SEG_BOUNCE)) {
                 const float4 r = pm.ld(ROW_RNG);
                 rng.b[0] = f2u(r.x); rng.b[1] = f2u(r.y); rng.b[2] = f2u(r.z); rng.b[3] = f2u(r.w);
             }
         }
 
         // ---- consume the finished cast(s) ----------------------------------------------------------------------------
+        // a path ray reached a new hit (main.rs:564-574 / 583-593 / 603-608): BRDF probe / decay of the CURRENT material,
+        // then the hit is replaced and its get_shade starts
+        auto arrive = [&](const DHit& hc) {
+            const uint32_t ray_type = (flags >> F_RAYTYPE_SHIFT) & 3u;
+            const MatEval mat = material_approx(sc.materials, h.object, h.uv);
+            uint32_t purpose;
+            if (ray_type == 2u) {
+                pend = mk3(nl_powf(mat.opaque_decay, rf_travel), 0.f, 0.f);
+                purpose = SH_NEXT_REFR;
+            } else {
+                pend = ray_type == 0u ? get_diffuse(mat, h.normal, ray.d)                    // main.rs:566-570
+                                      : get_specular(mat, h.normal, -h_dir_orig, ray.d);     // main.rs:585-589
+                purpose = SH_NEXT_MIX;
+            }
+            w_pend = true;
+            flags = (flags & ~((3u << F_PURPOSE_SHIFT) | F_PRE | F_BLACK)) | (purpose << F_PURPOSE_SHIFT);
+            h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face; w_hit = true; w_dirs = true;
+            do_shade_begin = true;
+            // fused levels: distributed_ray_trace's next level at this hit draws its branch and direction now (the
+            // sample's draw order is unchanged: nothing else draws in between) and its ray is cast with the shadow rays
+            if (FUSED && depth - 1 > 0) { do_level = true; pre_level = true; }
+        };
+        // one step of get_refract after an inside ray came back (main.rs:371-402)
+        auto refract_step = [&](const float4 a, const float4 b) {
+            const int32_t hprim = __float_as_int(a.x);
+            if (hprim < 0) { if (seg == WF_SEG_REFR) acc = mk3(pm.ld(ROW_ACC)); do_finish = true; return; }   // Infinite
+            const uint32_t meta = f2u(a.y);
+            const uint32_t hi_face = meta & 1u;
+            const f3 hi_pos = ray.o + ray.d * a.z, hi_normal = mk3(b);
+            uint32_t rf_retry;
+            if (!(flags & F_TIR)) { rf_travel = distance(hi_pos, h.pos); rf_retry = 0u; }       // main.rs:375
+            else {
+                const float4 prev = pm.ld(ROW_HI_POS);
+                rf_travel = rf_travel + distance(mk3(prev), hi_pos);                            // main.rs:385
+                rf_retry = f2u(prev.w) + 1u;                                                    // main.rs:387
+            }
+            const float rf_k = sc.materials[h.object].refraction_index;
+            f3 rout;
+            const bool have_out = refract_dir(hi_normal, ray.d, 1.0f / rf_k, rout);             // main.rs:376 / 386
+            if (!have_out && rf_travel <= p.refract_max_distance && rf_retry < p.tir_retries) {  // main.rs:378
+                pm.sv(ROW_HI_POS, make_float4(hi_pos.x, hi_pos.y, hi_pos.z, u2f(rf_retry)));
+                ray = make_reflect(hi_pos, hi_normal, ray.d, ray.face, hprim, hi_face);         // main.rs:379-381
+                flags |= F_TIR;
+                w_pend = true;
+                out = OUT_REFR;
+            } else if (!have_out) {
+                if (seg == WF_SEG_REFR) acc = mk3(pm.ld(ROW_ACC));
+                do_finish = true;                                                  // Trapped
+            } else {                                                               // main.rs:392-402, then 603
+                DRay e;
+                e.o = hi_pos; e.d = normalize(rout); e.face = kFront; e.ex_prim = hprim; e.ex_face = kBack;
+                ray = e;
+                w_pend = true;
+                out = OUT_BOUNCE;
+            }
+        };
+        auto load_path_hit = [&](float4& a, float4& b, DHit& hc) {
+            pm.get_ray(ray);
+            a = wb.res[(size_t)pid * 2u]; b = wb.res[(size_t)pid * 2u + 1u];
+            hc.prim = __float_as_int(a.x);
+            const uint32_t meta = f2u(a.y);
+            hc.face = meta & 1u; hc.object = meta >> 8; hc.t = a.z;
+            hc.pos = ray.o + ray.d * hc.t;                                         // main.rs:210 / 304
+            hc.normal = mk3(b); hc.uv.x = a.w; hc.uv.y = b.w;
+        };
+
         if (seg == WF_SEG_INIT) {
             do_finish = valid;
         } else if (seg == WF_SEG_PRIMARY || seg == WF_SEG_BOUNCE) {
             if (valid) {
-                pm.get_ray(ray);
-                const float4 a = wb.res[(size_t)pid * 2u], b = wb.res[(size_t)pid * 2u + 1u];
+                float4 a, b;
                 DHit hc;
-                hc.prim = __float_as_int(a.x);
-                const uint32_t meta = f2u(a.y);
-                hc.face = meta & 1u; hc.object = meta >> 8; hc.t = a.z;
-                hc.pos = ray.o + ray.d * hc.t;                                         // main.rs:210 / 304
-                hc.normal = mk3(b); hc.uv.x = a.w; hc.uv.y = b.w;
+                load_path_hit(a, b, hc);
                 const bool hit = hc.prim >= 0;
                 if (seg == WF_SEG_PRIMARY) {                                           // main.rs:1150-1155
                     // a fresh sample: acc = 0, T = 1 (set when the sample was opened; not stored until they change)
                     w_acc = true;
                     if (!hit) do_finish = true;
                     else { h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face; w_hit = true; w_dirs = true; do_level = true; }
-                } else {                                                               // main.rs:564-574 / 583-593 / 603-608
+                } else {
                     const uint32_t ray_type = (flags >> F_RAYTYPE_SHIFT) & 3u;
                     if (!hit) {
                         if (ray_type == 2u) { acc = mk3(pm.ld(ROW_ACC)); do_finish = true; }                 // main.rs:606-608
-                        else { flags = (flags & ~(3u << F_PURPOSE_SHIFT)) | (SH_FINAL << F_PURPOSE_SHIFT); do_shade_begin = true; }
-                    } else {
-                        // probe / decay of the CURRENT material, before the hit is replaced
-                        const MatEval mat = material_approx(sc.materials, h.object, h.uv);
-                        uint32_t purpose;
-                        if (ray_type == 2u) {
-                            pend = mk3(nl_powf(mat.opaque_decay, rf_travel), 0.f, 0.f);
-                            purpose = SH_NEXT_REFR;
-                        } else {
-                            pend = ray_type == 0u ? get_diffuse(mat, h.normal, ray.d)                    // main.rs:566-570
-                                                  : get_specular(mat, h.normal, -h_dir_orig, ray.d);     // main.rs:585-589
-                            purpose = SH_NEXT_MIX;
+                        else {                                                                               // main.rs:572-574 / 591-593
+                            flags = (flags & ~((3u << F_PURPOSE_SHIFT) | F_PRE | F_BLACK)) | (SH_FINAL << F_PURPOSE_SHIFT);
+                            do_shade_begin = true;
                         }
-                        w_pend = true;
-                        flags = (flags & ~(3u << F_PURPOSE_SHIFT)) | (purpose << F_PURPOSE_SHIFT);
-                        h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face; w_hit = true; w_dirs = true;
-                        do_shade_begin = true;
-                    }
+                    } else arrive(hc);
                 }
             }
         } else if (seg == WF_SEG_SHB) {
@@ -587,45 +645,28 @@ __global__ void __launch_bounds__(256, LogicCfg<SEG>::kMinBlocks) wf_logic_kerne
         } else if (seg == WF_SEG_REFR) {                                               // main.rs:371-402
             if (valid) {
                 pm.get_ray(ray);
-                const float4 a = wb.res[(size_t)pid * 2u], b = wb.res[(size_t)pid * 2u + 1u];
-                const int32_t hprim = __float_as_int(a.x);
-                if (hprim < 0) { acc = mk3(pm.ld(ROW_ACC)); do_finish = true; }        // Infinite
-                else {
-                    const uint32_t meta = f2u(a.y);
-                    const uint32_t hi_face = meta & 1u;
-                    const f3 hi_pos = ray.o + ray.d * a.z, hi_normal = mk3(b);
-                    uint32_t rf_retry;
-                    if (!(flags & F_TIR)) { rf_travel = distance(hi_pos, h.pos); rf_retry = 0u; }       // main.rs:375
-                    else {
-                        const float4 prev = pm.ld(ROW_HI_POS);
-                        rf_travel = rf_travel + distance(mk3(prev), hi_pos);                            // main.rs:385
-                        rf_retry = f2u(prev.w) + 1u;                                                    // main.rs:387
-                    }
-                    const float rf_k = sc.materials[h.object].refraction_index;
-                    f3 rout;
-                    const bool have_out = refract_dir(hi_normal, ray.d, 1.0f / rf_k, rout);             // main.rs:376 / 386
-                    if (!have_out && rf_travel <= p.refract_max_distance && rf_retry < p.tir_retries) {  // main.rs:378
-                        pm.sv(ROW_HI_POS, make_float4(hi_pos.x, hi_pos.y, hi_pos.z, u2f(rf_retry)));
-                        ray = make_reflect(hi_pos, hi_normal, ray.d, ray.face, hprim, hi_face);         // main.rs:379-381
-                        flags |= F_TIR;
-                        w_pend = true;
-                        out = OUT_REFR;
-                    } else if (!have_out) {
-                        acc = mk3(pm.ld(ROW_ACC)); do_finish = true;                   // Trapped
-                    } else {                                                           // main.rs:392-402, then 603
-                        DRay e;
-                        e.o = hi_pos; e.d = normalize(rout); e.face = kFront; e.ex_prim = hprim; e.ex_face = kBack;
-                        ray = e;
-                        w_pend = true;
-                        out = OUT_BOUNCE;
-                    }
-                }
+                refract_step(wb.res[(size_t)pid * 2u], wb.res[(size_t)pid * 2u + 1u]);
             }
         } else {   // WF_SEG_SHADE: the shadow rays of the current light chunk are back (main.rs:435-461)
             if (valid) {
                 const MatEval mat = material_approx(sc.materials, h.object, h.uv);
                 const f3 nadj = adjust_normal(mat, h.normal);
                 const uint32_t li0 = (flags >> F_LI0_SHIFT) & 0xfffu, need = (flags >> F_NEED_SHIFT) & 15u;
+                const uint32_t purpose = (flags >> F_PURPOSE_SHIFT) & 3u;
+                // fused levels: the path ray that travelled with these shadow rays
+                const bool pre = FUSED && (flags & F_PRE);
+                const uint32_t ray_type = (flags >> F_RAYTYPE_SHIFT) & 3u;
+                float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+                DHit hc;
+                hc.prim = -1; hc.face = 0; hc.object = 0; hc.t = 0.f; hc.pos = hc.normal = mk3(0.f, 0.f, 0.f); hc.uv.x = hc.uv.y = 0.f;
+                if (pre) load_path_hit(ra, rb, hc);
+                // a bounce ray that left the scene ends the sample with get_shade of THIS hit seen along the scattered
+                // direction (main.rs:572-574 / 591-593): same shadow rays, a second specular term
+                const bool want_final = pre && ray_type != 2u && hc.prim < 0;
+                f3 shade2 = mk3(0.f, 0.f, 0.f);
+                // view direction of the Phong probe (main.rs:449-456): the hit's ray direction — the scattered one only for
+                // the get_shade that closes a sample after a missed bounce (hit.ray.direction is replaced at main.rs:552)
+                const f3 view = purpose == SH_FINAL ? -h_dir : -h_dir_orig;
                 if (flags & F_PARTIAL) shade = mk3(pm.ld(ROW_HI_POS));
 #pragma unroll 1
                 for (uint32_t s = 0; s < 4u; ++s) {
@@ -641,43 +682,51 @@ __global__ void __launch_bounds__(256, LogicCfg<SEG>::kMinBlocks) wf_logic_kerne
                         } else occluded = true;
                     }
                     if (!occluded) {
-                        const f3 view = -h_dir, ldir = -L.dir;
+                        const f3 ldir = -L.dir;
                         const f3 diffuse = get_diffuse(mat, nadj, ldir) * L.color;         // main.rs:458
                         const f3 specular = get_specular(mat, nadj, view, ldir) * L.color; // main.rs:459
                         shade = shade + diffuse * (1.0f - mat.shiness) + specular * mat.shiness;  // main.rs:461
+                        if (FUSED && want_final) {
+                            const f3 specular2 = get_specular(mat, nadj, -h_dir, ldir) * L.color;
+                            shade2 = shade2 + diffuse * (1.0f - mat.shiness) + specular2 * mat.shiness;
+                        }
                     }
                 }
-                if (li0 + 4u < sc.n_lights) {     // more lights: next chunk
+                if (!FUSED && li0 + 4u < sc.n_lights) {     // more lights: next chunk
                     pm.sv(ROW_HI_POS, make_float4(shade.x, shade.y, shade.z, 0.f));
                     flags = (flags & ~((0xfffu << F_LI0_SHIFT) | (15u << F_NEED_SHIFT))) | ((li0 + 4u) << F_LI0_SHIFT) | F_PARTIAL;
                     do_shade_begin = true;
                 } else {
-                    const uint32_t purpose = (flags >> F_PURPOSE_SHIFT) & 3u;
                     w_acc = true;
                     if (purpose == SH_FINAL) {
                         acc = acc + T * shade;
                         do_finish = true;
-                    } else if (purpose == SH_NEXT_MIX) {
-                        // mix(get_shade(next), x*probe, 0.5) = a + (x*probe - a)*0.5   (main.rs:571, 590)
-                        acc = acc + T * (shade - shade * 0.5f);
-                        T = T * (pend * 0.5f);
-                        a_shade = shade; flags |= F_A_KNOWN; depth -= 1;
-                        do_level = true;
                     } else {
-                        // (x + get_shade(next)) * decay^distance   (main.rs:605)
-                        acc = acc + T * (shade * pend.x);
-                        T = T * pend.x;
+                        if (purpose == SH_NEXT_MIX) {
+                            // mix(get_shade(next), x*probe, 0.5) = a + (x*probe - a)*0.5   (main.rs:571, 590)
+                            acc = acc + T * (shade - shade * 0.5f);
+                            T = T * (pend * 0.5f);
+                        } else {
+                            // (x + get_shade(next)) * decay^distance   (main.rs:605)
+                            acc = acc + T * (shade * pend.x);
+                            T = T * pend.x;
+                        }
                         a_shade = shade; flags |= F_A_KNOWN; depth -= 1;
-                        do_level = true;
+                        if (!FUSED) do_level = true;
+                        else if (depth <= 0) { acc = acc + T * a_shade; do_finish = true; }       // main.rs:525-527
+                        else if (flags & F_BLACK) do_finish = true;                               // main.rs:559-561, 366-368
+                        else if (ray_type == 2u) refract_step(ra, rb);                            // first inside ray of get_refract
+                        else if (hc.prim < 0) { acc = acc + T * shade2; do_finish = true; }       // main.rs:572-574 / 591-593
+                        else arrive(hc);
                     }
                 }
             }
         }
 
         // ---- top of distributed_ray_trace for the current hit (main.rs:521-554), then the bounce ray ---------------------
-        if (seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE) {
+        if (seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE || (FUSED && seg == WF_SEG_BOUNCE)) {
             if (do_level) {
-                if (depth <= 0) {
+                if (!pre_level && depth <= 0) {
                     if (flags & F_A_KNOWN) { acc = acc + T * a_shade; do_finish = true; }    // main.rs:525-527
                     else {                                                                    // depth 0 at the primary hit
                         flags = (flags & ~(3u << F_PURPOSE_SHIFT)) | (SH_FINAL << F_PURPOSE_SHIFT);
@@ -709,16 +758,18 @@ __global__ void __launch_bounds__(256, LogicCfg<SEG>::kMinBlocks) wf_logic_kerne
                     w_dirs = true; w_rng = true;
                     flags = (flags & ~((3u << F_RAYTYPE_SHIFT) | F_TIR)) | (ray_type << F_RAYTYPE_SHIFT);
                     const float cosine = -dot(h.normal, h_dir);                        // main.rs:559 / 578 / 597
-                    if (cosine <= 0.0f) do_finish = true;                              // black
+                    // pre_level: the sample still owes the get_shade of this hit; what the level decides is kept in the flags
+                    if (cosine <= 0.0f) { if (pre_level) flags |= F_BLACK; else do_finish = true; }   // black
                     else if (ray_type == 2u) {                                         // get_refract, main.rs:354-368
                         f3 rin;
                         if (refract_dir(h.normal, h_dir, mat.refraction_index, rin)) {
                             ray.o = h.pos; ray.d = normalize(rin); ray.face = kBack; ray.ex_prim = h.prim; ray.ex_face = kFront;
-                            out = OUT_REFR;
-                        } else do_finish = true;                                       // Trapped
+                            if (pre_level) { pre_ray = true; flags |= F_PRE; } else out = OUT_REFR;
+                        } else if (pre_level) flags |= F_BLACK;                        // Trapped
+                        else do_finish = true;
                     } else {
                         ray = make_reflect(h.pos, h.normal, h_dir, h_rayface, h.prim, h.face);   // main.rs:563 / 582
-                        out = OUT_BOUNCE;
+                        if (pre_level) { pre_ray = true; flags |= F_PRE; } else out = OUT_BOUNCE;
                     }
                 }
             }
@@ -730,8 +781,9 @@ __global__ void __launch_bounds__(256, LogicCfg<SEG>::kMinBlocks) wf_logic_kerne
             if (do_shade_begin) {
                 const MatEval mat = material_approx(sc.materials, h.object, h.uv);
                 const f3 nadj = adjust_normal(mat, h.normal);
-                uint32_t li0 = (seg == WF_SEG_SHADE) ? ((flags >> F_LI0_SHIFT) & 0xfffu) : 0u;
-                if (seg != WF_SEG_SHADE) flags &= ~F_PARTIAL;
+                // (fused levels run scenes of one light chunk: get_shade always starts at light 0)
+                uint32_t li0 = (seg == WF_SEG_SHADE && !FUSED) ? ((flags >> F_LI0_SHIFT) & 0xfffu) : 0u;
+                if (seg != WF_SEG_SHADE || FUSED) flags &= ~F_PARTIAL;
                 uint32_t need = 0u;
                 // chunks without any shadow ray are skipped here (their lights contribute nothing, main.rs:418-421)
                 for (;;) {
@@ -812,13 +864,13 @@ __global__ void __launch_bounds__(256, LogicCfg<SEG>::kMinBlocks) wf_logic_kerne
                 pm.sv(ROW_HDIR0, make_float4(h_dir_orig.x, h_dir_orig.y, h_dir_orig.z, h.uv.y));
             }
             if (w_rng) pm.sv(ROW_RNG, make_float4(u2f(rng.b[0]), u2f(rng.b[1]), u2f(rng.b[2]), u2f(rng.b[3])));
-            if (out == OUT_PRIMARY || out == OUT_BOUNCE || out == OUT_REFR) pm.put_ray(ray);
+            if (out == OUT_PRIMARY || out == OUT_BOUNCE || out == OUT_REFR || pre_ray) pm.put_ray(ray);
         }
         // ---- route: every reservation of this chunk (5 queues, the cast work list, the retired counter) is one
         // atomic issued by a different lane, so the warp pays one round trip to L2 instead of seven
         {
             const bool path_ray = out == OUT_PRIMARY || out == OUT_BOUNCE || out == OUT_REFR;
-            const uint32_t n_items = !valid ? 0u : (path_ray ? 1u : (out == OUT_SHADE ? n_shadow : 0u));
+            const uint32_t n_items = !valid ? 0u : (path_ray ? 1u : (out == OUT_SHADE ? n_shadow + (pre_ray ? 1u : 0u) : 0u));
             uint32_t incl = n_items;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -851,12 +903,13 @@ __global__ void __launch_bounds__(256, LogicCfg<SEG>::kMinBlocks) wf_logic_kerne
             const uint32_t work_base = __shfl_sync(kFullMask, my_base, 0) + (incl - n_items);
             if (valid && my_seg != 0)
                 wb.q[((size_t)nbuf * WF_SEG_COUNT + my_seg) * wb.n + seg_base + (uint32_t)__popc(seg_mask & ((1u << lane) - 1u))] = pid;
-            uint32_t* w = wb.work + (size_t)nbuf * 4u * wb.n;
+            uint32_t* w = wb.work + (size_t)nbuf * WF_WORK_PER_PATH * wb.n;
             if (n_items) {
                 if (path_ray) w[work_base] = pid << 3;
                 else {
                     const uint32_t need = (flags >> F_NEED_SHIFT) & 15u;
                     uint32_t at = work_base;
+                    if (pre_ray) w[at++] = pid << 3;
 #pragma unroll
                     for (uint32_t sl = 0; sl < 4u; ++sl)
                         if ((need >> sl) & 1u) w[at++] = (pid << 3) | (sl + 1u);
@@ -887,8 +940,14 @@ __global__ void wf_combine_kernel(const WfBuffers wb, const DParams p, float4* _
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
+// the candidate masks between wf_filter_kernel and wf_owner_kernel exist only in the (tuning) split-cast mode
+static bool wf_split_selected() {
+    const char* e = getenv("B200RT_WF_CAST");
+    return e && std::string(e) == "split";
+}
 size_t wf_workspace_bytes_per_path() {
-    return (size_t)kStateRows * 16 + WF_REQ_ROWS * 16 + 32 + 32 + 2 * WF_SEG_COUNT * 4 + 2 * 4 * 4 + 4 * WF_SPLIT_MAX_TILES * 8;
+    return (size_t)kStateRows * 16 + WF_REQ_ROWS * 16 + 32 + 32 + 2 * WF_SEG_COUNT * 4 + 2 * WF_WORK_PER_PATH * 4 +
+           (wf_split_selected() ? WF_WORK_PER_PATH * WF_SPLIT_MAX_TILES * 8 : 0);
 }
 size_t wf_workspace_bytes(uint32_t n_paths) {
     return sizeof(WfControl) + 256 + (size_t)n_paths * wf_workspace_bytes_per_path() + 16 * 64;
@@ -924,8 +983,8 @@ static WfBuffers wf_carve(void* workspace, uint32_t n_paths, uint32_t n_pixels, 
     wb.res = reinterpret_cast<float4*>(b + off);               off = align(off + n * 32);
     wb.sres = reinterpret_cast<float2*>(b + off);              off = align(off + n * 32);
     wb.q = reinterpret_cast<uint32_t*>(b + off);               off = align(off + n * 2 * WF_SEG_COUNT * 4);
-    wb.work = reinterpret_cast<uint32_t*>(b + off);            off = align(off + n * 2 * 4 * 4);
-    wb.masks = reinterpret_cast<uint2*>(b + off);              off = align(off + n * 4 * WF_SPLIT_MAX_TILES * 8);
+    wb.work = reinterpret_cast<uint32_t*>(b + off);            off = align(off + n * 2 * WF_WORK_PER_PATH * 4);
+    wb.masks = reinterpret_cast<uint2*>(b + off);              off = align(off + (wf_split_selected() ? n * WF_WORK_PER_PATH * WF_SPLIT_MAX_TILES * 8 : 0));
     wb.n = n_paths; wb.n_pixels = n_pixels; wb.epar = epar;
     return wb;
 }
@@ -946,9 +1005,13 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     const std::string cast_sel = cast_env ? cast_env : "";
     const bool rays_in_lanes = n_tiles == 1 && (cast_sel.empty() || cast_sel == "rl");
     const bool split = !rays_in_lanes && n_tiles >= 1 && n_tiles <= WF_SPLIT_MAX_TILES && cast_sel == "split";
+    // fused levels (one light chunk): a hit's shadow rays and the next level's ray are cast in the same round, and one
+    // kernel pass per level consumes both (B200RT_WF_FUSED_LEVELS=0: one pass per cast, as for scenes of > 4 lights)
+    const char* fused_env = getenv("B200RT_WF_FUSED_LEVELS");
+    const bool fused = sc.n_lights <= 4u && !(fused_env && fused_env[0] == '0');
     auto logic_blocks = [&](int min_blocks) { return sm_count * min_blocks; };
     // round 0: every slot opens its first sample
-    wf_logic_kernel<WF_SEG_INIT><<<logic_blocks(LogicCfg<WF_SEG_INIT>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, 1u, d_cnt);
+    wf_logic_kernel<WF_SEG_INIT, false><<<logic_blocks(LogicCfg<WF_SEG_INIT>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, 1u, d_cnt);
     uint32_t round = 0, buf = 0;
     uint32_t group = 8;
     for (;;) {
@@ -983,12 +1046,17 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                 wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
             }
             if (timing) cudaEventRecord(ev_b, stream);
-            wf_logic_kernel<WF_SEG_PRIMARY><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-            wf_logic_kernel<WF_SEG_SHADE><<<logic_blocks(LogicCfg<WF_SEG_SHADE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-            wf_logic_kernel<WF_SEG_BOUNCE><<<logic_blocks(LogicCfg<WF_SEG_BOUNCE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-            wf_logic_kernel<WF_SEG_REFR><<<logic_blocks(LogicCfg<WF_SEG_REFR>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            wf_logic_kernel<WF_SEG_PRIMARY, false><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            if (fused) {
+                wf_logic_kernel<WF_SEG_SHADE, true><<<logic_blocks(LogicCfg<WF_SEG_SHADE, true>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+                wf_logic_kernel<WF_SEG_BOUNCE, true><<<logic_blocks(LogicCfg<WF_SEG_BOUNCE, true>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            } else {
+                wf_logic_kernel<WF_SEG_SHADE, false><<<logic_blocks(LogicCfg<WF_SEG_SHADE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+                wf_logic_kernel<WF_SEG_BOUNCE, false><<<logic_blocks(LogicCfg<WF_SEG_BOUNCE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            }
+            wf_logic_kernel<WF_SEG_REFR, false><<<logic_blocks(LogicCfg<WF_SEG_REFR>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
             if (p.depth <= 0)   // get_shade of depth-0 primary hits (the only source of this segment)
-                wf_logic_kernel<WF_SEG_SHB><<<logic_blocks(LogicCfg<WF_SEG_SHB>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+                wf_logic_kernel<WF_SEG_SHB, false><<<logic_blocks(LogicCfg<WF_SEG_SHB>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
         }
         e = cudaMemcpyAsync(h_pinned_retired, &wb.ctl->retired, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess) return e;

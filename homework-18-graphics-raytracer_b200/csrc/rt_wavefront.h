@@ -33,6 +33,7 @@ struct WfControl {
 
 constexpr int WF_STATE_ROWS = 12;   // float4 rows of path state (192 B = 6 sectors)
 constexpr int WF_SPLIT_MAX_TILES = 2;  // scenes of up to 128 triangles run the cast as filter kernel + owner kernel
+constexpr uint32_t WF_WORK_PER_PATH = 5u;   // cast items a path can request in one round: its path ray + 4 shadow rays
 constexpr int WF_REQ_ROWS = 6;      // path ray (2) + 4 shadow directions (96 B = 3 sectors)
 #ifndef WF_LOGIC_MIN_BLOCKS
 #define WF_LOGIC_MIN_BLOCKS 2
@@ -45,8 +46,8 @@ struct WfBuffers {
     float4* res;             // [n][2]
     float2* sres;            // [n][4]
     uint32_t* q;             // [2][WF_SEG_COUNT][n]
-    uint32_t* work;          // [2][4n]
-    uint2* masks;            // [4n][n_tiles] candidate masks between wf_filter_kernel and wf_owner_kernel
+    uint32_t* work;          // [2][WF_WORK_PER_PATH n]
+    uint2* masks;            // [WF_WORK_PER_PATH n][n_tiles] candidate masks between wf_filter_kernel and wf_owner_kernel
     uint32_t n, n_pixels, epar;
 };
 

@@ -4,6 +4,8 @@ Tolerances (BASELINE.json north_star): deterministic scenes — identical hit-pr
 |a-b| <= 1e-4 * max(|a|,|b|,1e-3) per channel; stochastic scenes — converged-mean PSNR >= 40 dB at
 equal sample count (and, because oracle and GPU share the Philox sample stream, near-identical
 individual samples)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -196,10 +198,23 @@ def test_tracers_and_cast_modes_bitwise(b200rt, gpu_ctx):
         p = b200rt.default_params(width=3840, height=2160, seed=11, tracer=tr, cast_mode=cm, row_begin=700, row_count=600)
         gpu_ctx.reset_stats()
         out[name] = (gpu_ctx.render_distributed(cam, p, 0, 3), gpu_ctx.stats())
-    for name in ("wave", "mega"):
-        assert out[name][1]["casts"] == out["brute"][1]["casts"]
+    # the wavefront with one kernel pass per cast (the flow for scenes of > 4 lights) casts exactly the megakernel's rays
+    os.environ["B200RT_WF_FUSED_LEVELS"] = "0"
+    try:
+        p = b200rt.default_params(width=3840, height=2160, seed=11, tracer=b200rt.TRACER_WAVEFRONT,
+                                  cast_mode=b200rt.CAST_TWO_PHASE, row_begin=700, row_count=600)
+        gpu_ctx.reset_stats()
+        out["wave_unfused"] = (gpu_ctx.render_distributed(cam, p, 0, 3), gpu_ctx.stats())
+    finally:
+        del os.environ["B200RT_WF_FUSED_LEVELS"]
+    for name in ("wave", "wave_unfused", "mega"):
         assert out[name][1]["samples"] == out["brute"][1]["samples"]
         assert np.array_equal(out[name][0].view(np.uint32), out["brute"][0].view(np.uint32)), name
+    for name in ("wave_unfused", "mega"):
+        assert out[name][1]["casts"] == out["brute"][1]["casts"]
+    # fused levels: the get_shade that closes a sample after a missed bounce (main.rs:572-574) reuses the shadow rays
+    # the hit already cast instead of casting them again
+    assert 0.8 * out["brute"][1]["casts"] < out["wave"][1]["casts"] < out["brute"][1]["casts"]
     assert out["wave"][1]["wavefront_rounds"] > 0 and out["mega"][1]["wavefront_rounds"] == 0
 
 
