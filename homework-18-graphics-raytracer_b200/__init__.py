@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Optional, Sequence
+from typing import Callable, Optional, Sequence
 
 import numpy as np
 
@@ -120,6 +120,7 @@ EXPORTED_SYMBOLS = [
     "b200rt_upload_scene", "b200rt_render_whitted", "b200rt_render_whitted_device", "b200rt_render_distributed",
     "b200rt_render_distributed_device", "b200rt_resolve_device", "b200rt_intersect", "b200rt_intersect_device",
     "b200rt_post_process", "b200rt_post_process_device", "b200rt_encode_srgb8", "b200rt_encode_srgb8_device",
+    "b200rt_write_png_rgb8",
     "b200rt_get_stats", "b200rt_reset_stats", "b200rt_set_kernel_timing", "b200rt_measure_fp32_peak", "b200rt_filter_bench", "b200rt_pipe_bench", "b200rt_world_new", "b200rt_world_free",
     "b200rt_world_push_object", "b200rt_world_push_triangle", "b200rt_world_push_flat_triangle",
     "b200rt_world_push_square", "b200rt_world_push_sphere", "b200rt_world_push_light", "b200rt_world_load_obj",
@@ -159,6 +160,7 @@ def load_library() -> C.CDLL:
         "b200rt_post_process_device": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
         "b200rt_encode_srgb8": (C.c_int, [vp, vp, C.c_size_t, vp]),
         "b200rt_encode_srgb8_device": (C.c_int, [vp, vp, C.c_size_t, vp, vp]),
+        "b200rt_write_png_rgb8": (C.c_int, [C.c_char_p, vp, C.c_uint32, C.c_uint32]),
         "b200rt_get_stats": (C.c_int, [vp, C.POINTER(Stats)]),
         "b200rt_reset_stats": (C.c_int, [vp]),
         "b200rt_set_kernel_timing": (C.c_int, [vp, C.c_int]),
@@ -185,6 +187,14 @@ def load_library() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def write_png(path: str, rgb8: np.ndarray) -> None:
+    """write_to_file, main.rs:764-776: [h][w][3] u8 -> RGB8 PNG via tmp.png + rename (host only)."""
+    img = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    if img.ndim != 3 or img.shape[2] != 3:
+        raise ValueError("write_png expects [height][width][3] u8")
+    _check(load_library().b200rt_write_png_rgb8(os.fsencode(path), img.ctypes.data, img.shape[1], img.shape[0]), "write_png")
 
 
 def strerror(code: int) -> str:
@@ -497,3 +507,39 @@ class Context:
         t, mhz = C.c_double(), C.c_double()
         _check(self._lib.b200rt_measure_fp32_peak(self._h, C.byref(t), C.byref(mhz)), "measure_fp32_peak", self)
         return t.value, mhz.value
+
+
+def render_main(ctx: "Context", cam: Camera, params: Params, epochs: int, out_path: Optional[str] = None,
+                on_frame: Optional[Callable[[int, np.ndarray], None]] = None) -> np.ndarray:
+    """The render part of the reference's `main()` (main.rs:1086-1173) on top of the C ABI, every stage on the GPU.
+
+      1. the deterministic Whitted frame is added into `img` (main.rs:1089-1109), `post_process`ed in place (main.rs:1113)
+         and written (main.rs:1114);
+      2. every epoch adds its accepted samples (main.rs:1157-1167: a sample with a zero / subnormal / NaN / inf channel
+         is dropped — the {sum, count} accumulator of one epoch holds exactly the accepted sample) into the SAME,
+         already normalised image, which is normalised again by its p99 luma and written again (main.rs:1171-1172):
+         the reference's progressive renormalisation chain ("accumulation quirk").
+
+    `on_frame(k, img_u8)` is called after each write (k = 0 for the Whitted frame, 1.. for the epochs).  Returns the final
+    linear image.  The epochs use the shared Philox sample stream, not rand 0.5's ISAAC."""
+    h, w = params.height, params.width
+    img = np.zeros((h, w, 3), dtype=np.float32)
+
+    def finish(k: int) -> None:
+        nonlocal img
+        img, _ = ctx.post_process(img)                                   # main.rs:748-762
+        if out_path is not None or on_frame is not None:
+            u8 = ctx.encode_srgb8(img)                                   # image.rs:55-66
+            if out_path is not None:
+                write_png(out_path, u8)                                  # main.rs:764-776
+            if on_frame is not None:
+                on_frame(k, u8)
+
+    rgb, _ = ctx.render_whitted(cam, params, want_prim_id=False)
+    img = img + rgb                                                      # main.rs:1107
+    finish(0)
+    for i in range(epochs):                                              # main.rs:1129
+        acc = ctx.render_distributed(cam, params, i, 1)
+        img = img + acc[..., :3]                                         # main.rs:1165
+        finish(i + 1)
+    return img

@@ -7,6 +7,8 @@
 //   load_obj()  (tobj: first model, fan triangulation)          main.rs:778-807
 //   the scene literal and camera of main()                      main.rs:810-1083
 // Built with -ffp-contract=off: every float here rounds exactly like the Rust code.
+#include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -403,3 +405,87 @@ int b200rt_world_fixture(b200rt_world* w, const char* obj_path) {
 }
 
 }  // extern "C"
+
+// ---- write_to_file (main.rs:764-776): RGB8 PNG written to a temporary next to the target, then renamed over it ----
+// (the reference writes ./tmp.png and renames: a reader of `name` never sees a half-written image).  The png crate's
+// deflate is not reproduced: the IDAT stream uses stored (uncompressed) deflate blocks, which every decoder reads;
+// parity is on the decoded pixels.
+namespace {
+
+uint32_t crc32_update(uint32_t crc, const unsigned char* data, size_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        init = true;
+    }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ data[i]) & 0xffu] ^ (crc >> 8);
+    return crc;
+}
+
+void put_be32(std::vector<unsigned char>& v, uint32_t x) {
+    v.push_back((unsigned char)(x >> 24)); v.push_back((unsigned char)(x >> 16));
+    v.push_back((unsigned char)(x >> 8)); v.push_back((unsigned char)x);
+}
+
+bool write_chunk(FILE* f, const char type[4], const std::vector<unsigned char>& data) {
+    std::vector<unsigned char> head;
+    put_be32(head, (uint32_t)data.size());
+    head.insert(head.end(), type, type + 4);
+    uint32_t crc = crc32_update(0xffffffffu, head.data() + 4, 4);
+    crc = crc32_update(crc, data.data(), data.size()) ^ 0xffffffffu;
+    std::vector<unsigned char> tail;
+    put_be32(tail, crc);
+    return std::fwrite(head.data(), 1, head.size(), f) == head.size() &&
+           (data.empty() || std::fwrite(data.data(), 1, data.size(), f) == data.size()) &&
+           std::fwrite(tail.data(), 1, 4, f) == 4;
+}
+
+}  // namespace
+
+extern "C" int b200rt_write_png_rgb8(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height) {
+    if (!path || !rgb || width == 0 || height == 0) return B200RT_ERR_INVALID;
+    // raw scanlines: filter byte 0 + 3 * width samples
+    const size_t stride = 1 + 3 * (size_t)width;
+    std::vector<unsigned char> raw(stride * height);
+    for (uint32_t y = 0; y < height; ++y) {
+        raw[y * stride] = 0;
+        std::memcpy(&raw[y * stride + 1], rgb + (size_t)y * 3 * width, 3 * (size_t)width);
+    }
+    // zlib stream of stored blocks
+    std::vector<unsigned char> z;
+    z.reserve(raw.size() + raw.size() / 65535 * 5 + 16);
+    z.push_back(0x78); z.push_back(0x01);
+    uint32_t a = 1, b = 0;   // Adler-32
+    size_t at = 0;
+    do {
+        const size_t n = std::min<size_t>(65535, raw.size() - at);
+        z.push_back(at + n == raw.size() ? 1 : 0);
+        z.push_back((unsigned char)(n & 0xff)); z.push_back((unsigned char)(n >> 8));
+        z.push_back((unsigned char)(~n & 0xff)); z.push_back((unsigned char)((~n >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + at, raw.begin() + at + n);
+        for (size_t i = at; i < at + n; ++i) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+        at += n;
+    } while (at < raw.size());
+    put_be32(z, (b << 16) | a);
+
+    const std::string target(path);
+    const size_t slash = target.find_last_of('/');
+    const std::string tmp = (slash == std::string::npos ? std::string("./") : target.substr(0, slash + 1)) + "tmp.png";   // main.rs:767
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return B200RT_ERR_IO;
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::vector<unsigned char> ihdr;
+    put_be32(ihdr, width); put_be32(ihdr, height);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);   // 8-bit RGB (main.rs:770)
+    bool ok = std::fwrite(sig, 1, 8, f) == 8 && write_chunk(f, "IHDR", ihdr) && write_chunk(f, "IDAT", z) &&
+              write_chunk(f, "IEND", std::vector<unsigned char>());
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) { std::remove(tmp.c_str()); return B200RT_ERR_IO; }
+    if (std::rename(tmp.c_str(), target.c_str()) != 0) { std::remove(tmp.c_str()); return B200RT_ERR_IO; }   // main.rs:774-775
+    return B200RT_OK;
+}

@@ -239,6 +239,9 @@ int b200rt_post_process_device(b200rt_ctx* ctx, float* d_rgb, size_t n_pixels, f
 /* image.rs:55-66: linear f32 -> sRGB u8 (palette Srgb::from_linear + into_format::<u8>), n_values = 3 * pixels. */
 int b200rt_encode_srgb8(b200rt_ctx* ctx, const float* rgb, size_t n_values, uint8_t* out);
 int b200rt_encode_srgb8_device(b200rt_ctx* ctx, const float* d_rgb, size_t n_values, uint8_t* d_out, void* cuda_stream);
+/* write_to_file, main.rs:764-776 (next row N4): [height][width][3] sRGB u8 -> an RGB8 PNG, written to tmp.png in the
+ * target's directory and renamed over `path` (a reader never sees a partial file).  Host-only: no context, no GPU. */
+int b200rt_write_png_rgb8(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height);
 
 /* World::cast, main.rs:180-326, for n rays. */
 int b200rt_intersect(b200rt_ctx* ctx, const b200rt_ray* rays, size_t n, uint32_t cast_mode,
