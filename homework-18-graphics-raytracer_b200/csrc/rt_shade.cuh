@@ -65,6 +65,7 @@ RT_DI f3 get_specular(const MatEval& m, f3 n, f3 view, f3 l) {
 struct DirLight {  // lights.rs:6-11
     bool has_origin;
     f3 origin, dir, color;
+    float angular;   // spot lights: (1 - angle/spread)^(softness + eps), lights.rs:62-64 (1 otherwise)
 };
 
 // lights.rs:48-93
@@ -74,6 +75,7 @@ RT_DI bool approx_light(const DLight& L, f3 position, DirLight& out) {
         out.origin = mk3(L.origin);
         out.dir = mk3(L.direction);
         out.color = mk3(L.color);
+        out.angular = 1.0f;
         return true;
     }
     const f3 origin = mk3(L.origin);
@@ -88,6 +90,7 @@ RT_DI bool approx_light(const DLight& L, f3 position, DirLight& out) {
         out.origin = origin;
         out.dir = normalize(position - origin);
         out.color = mk3(L.color) * angular * dist_att;
+        out.angular = angular;
         return true;
     }
     if (L.kind == B200RT_LIGHT_POINT) {
@@ -96,9 +99,30 @@ RT_DI bool approx_light(const DLight& L, f3 position, DirLight& out) {
         out.origin = origin;
         out.dir = normalize(offset);
         out.color = mk3(L.color) * dist_att;
+        out.angular = 1.0f;
         return true;
     }
     return false;
+}
+
+// The same Directional as approx_light() for a light that is known to reach `position`, from what the wavefront kept
+// when it requested the shadow ray: its direction (dir = normalize(position - origin), lights.rs:66 / 80) and the spot's
+// angular factor.  Skips the atan2 / powf / normalize of the second evaluation; every value has the bits of the first.
+RT_DI void approx_light_cached(const DLight& L, f3 position, f3 dir, float angular, DirLight& out) {
+    out.dir = dir;
+    out.angular = angular;
+    if (L.kind == B200RT_LIGHT_DIRECTIONAL) {
+        out.has_origin = L.has_origin != 0u;
+        out.origin = mk3(L.origin);
+        out.color = mk3(L.color);
+        return;
+    }
+    const f3 origin = mk3(L.origin);
+    const f3 offset = position - origin;
+    const float dist_att = 1.0f / (magnitude(offset) + kF32Epsilon);
+    out.has_origin = true;
+    out.origin = origin;
+    out.color = L.kind == B200RT_LIGHT_SPOT ? mk3(L.color) * angular * dist_att : mk3(L.color) * dist_att;
 }
 
 // main.rs:328-341 (normal = hit.at.normal, l = hit.ray.direction)

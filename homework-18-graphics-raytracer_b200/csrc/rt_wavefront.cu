@@ -94,7 +94,9 @@ struct PathMem {
         const uint32_t m = f2u(a.w);
         r.o = mk3(a); r.d = mk3(b); r.face = m & 3u; r.ex_face = (m >> 2) & 3u; r.ex_prim = (int32_t)(m >> 4) - 1;
     }
-    RT_DI void put_shadow_dir(uint32_t s, f3 d) const { req[(size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + s] = make_float4(d.x, d.y, d.z, 0.0f); }
+    // .w: the spot light's angular factor, so that get_shade does not evaluate the light a second time
+    RT_DI void put_shadow_dir(uint32_t s, f3 d, float angular = 0.0f) const { req[(size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + s] = make_float4(d.x, d.y, d.z, angular); }
+    RT_DI float4 get_shadow_dir(uint32_t s) const { return req[(size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + s]; }
     // shadow ray of light slot s (main.rs:423-431): from the current hit, back faces only, the hit primitive excluded
     RT_DI void get_shadow_ray(uint32_t s, DRay& r) const {
         const float4 a = ld(ROW_HPOS), b = req[(size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + s];
@@ -473,13 +475,17 @@ __global__ void __launch_bounds__(128, WF_OWNER_MIN_BLOCKS) wf_owner_kernel(cons
 #ifndef WF_FUSED_SHADE_MIN_BLOCKS
 #define WF_FUSED_SHADE_MIN_BLOCKS 2
 #endif
-template <int SEG, bool FUSED = false> struct LogicCfg { static constexpr int kMinBlocks = 3; };
-template <> struct LogicCfg<WF_SEG_INIT, false> { static constexpr int kMinBlocks = 4; };
-template <> struct LogicCfg<WF_SEG_REFR, false> { static constexpr int kMinBlocks = 4; };
-template <> struct LogicCfg<WF_SEG_SHADE, true> { static constexpr int kMinBlocks = WF_FUSED_SHADE_MIN_BLOCKS; };   // shade + arrival + next level in one pass
+#ifndef WF_FUSED_SHADE_THREADS
+#define WF_FUSED_SHADE_THREADS 256
+#endif
+template <int SEG, bool FUSED = false> struct LogicCfg { static constexpr int kMinBlocks = 3, kThreads = 256; };
+template <> struct LogicCfg<WF_SEG_INIT, false> { static constexpr int kMinBlocks = 4, kThreads = 256; };
+template <> struct LogicCfg<WF_SEG_REFR, false> { static constexpr int kMinBlocks = 4, kThreads = 256; };
+// shade + arrival + next level in one pass
+template <> struct LogicCfg<WF_SEG_SHADE, true> { static constexpr int kMinBlocks = WF_FUSED_SHADE_MIN_BLOCKS, kThreads = WF_FUSED_SHADE_THREADS; };
 
 template <int SEG, bool FUSED>
-__global__ void __launch_bounds__(256, LogicCfg<SEG, FUSED>::kMinBlocks) wf_logic_kernel(const DScene sc, const DCamera cam, const DParams p,
+__global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, FUSED>::kMinBlocks) wf_logic_kernel(const DScene sc, const DCamera cam, const DParams p,
                                                           const WfBuffers wb, const uint32_t buf,
                                                           DCounters* __restrict__ cnt) {
     constexpr int seg = SEG;
@@ -672,7 +678,8 @@ __global__ void __launch_bounds__(256, LogicCfg<SEG, FUSED>::kMinBlocks) wf_logi
                 for (uint32_t s = 0; s < 4u; ++s) {
                     if (!((need >> s) & 1u)) continue;
                     DirLight L;
-                    approx_light(sc.lights[li0 + s], h.pos, L);
+                    const float4 sd = pm.get_shadow_dir(s);                            // {-L.dir, angular} kept by get_shade's entry
+                    approx_light_cached(sc.lights[li0 + s], h.pos, -mk3(sd), sd.w, L);
                     const float2 sr = wb.sres[(size_t)pid * 4u + s];
                     bool occluded = false;
                     if (__float_as_int(sr.x) >= 0) {
@@ -793,7 +800,7 @@ __global__ void __launch_bounds__(256, LogicCfg<SEG, FUSED>::kMinBlocks) wf_logi
                         if (!approx_light(sc.lights[li0 + s], h.pos, L)) continue;
                         const float cosine = -dot(L.dir, nadj);                        // main.rs:420
                         if (cosine <= 0.0f) continue;
-                        pm.put_shadow_dir(s, -L.dir);                                  // main.rs:423-431
+                        pm.put_shadow_dir(s, -L.dir, L.angular);                       // main.rs:423-431
                         need |= 1u << s;
                     }
                     if (need || li0 + 4u >= sc.n_lights) break;
@@ -1048,7 +1055,7 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
             if (timing) cudaEventRecord(ev_b, stream);
             wf_logic_kernel<WF_SEG_PRIMARY, false><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
             if (fused) {
-                wf_logic_kernel<WF_SEG_SHADE, true><<<logic_blocks(LogicCfg<WF_SEG_SHADE, true>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+                wf_logic_kernel<WF_SEG_SHADE, true><<<logic_blocks(LogicCfg<WF_SEG_SHADE, true>::kMinBlocks), LogicCfg<WF_SEG_SHADE, true>::kThreads, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
                 wf_logic_kernel<WF_SEG_BOUNCE, true><<<logic_blocks(LogicCfg<WF_SEG_BOUNCE, true>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
             } else {
                 wf_logic_kernel<WF_SEG_SHADE, false><<<logic_blocks(LogicCfg<WF_SEG_SHADE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
