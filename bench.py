@@ -216,17 +216,21 @@ def run_b200(args):
                 dist.all_reduce(d_accum, op=dist.ReduceOp.SUM)
 
         def step_e2e():
-            # host-buffer C-ABI entry: pinned accumulators travel H2D, are added to, and travel back
             h_accum.zero_()
-            ctx.render_distributed(cam, params, e0, en, h_accum.numpy())
-            if world_size > 1:
+            if world_size == 1:
+                # host-buffer C-ABI entry: pinned accumulators travel H2D, are added to, and travel back
+                ctx.render_distributed(cam, params, e0, en, h_accum.numpy())
+            else:
+                # N > 1: the ranks' accumulators are summed on the devices, so the caller does the copies around the
+                # device-pointer entry of the same C ABI: pinned H2D, render, all-reduce, D2H of the reduced image
                 d_accum.copy_(h_accum, non_blocking=True)
+                ctx.render_distributed_device(cam, params, e0, en, d_accum.data_ptr(), stream)
                 dist.all_reduce(d_accum, op=dist.ReduceOp.SUM)
                 h_accum.copy_(d_accum, non_blocking=True)
                 torch.cuda.synchronize()
             return float(h_accum[H // 2, W // 2, 3])
 
-        h2d = d2h = W * H * 16 * (2 if world_size > 1 else 1)
+        h2d = d2h = W * H * 16
         launches_per_step = 1
     else:
         r0, rn = shard(H, rank, world_size)

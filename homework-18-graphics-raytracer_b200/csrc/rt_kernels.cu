@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "rt_cast.cuh"
+#include "rt_cast_rl.cuh"
 #include "rt_shade.cuh"
 #include "rt_types.h"
 
@@ -619,6 +620,64 @@ __global__ void __launch_bounds__(128, 4) intersect_kernel(const DScene sc, cons
     }
 }
 
+// K2 for scenes of one tile: the rays-in-lanes cast (rt_cast_rl.cuh) over the caller's AoS rays, persistent CTAs.
+#ifndef INTERSECT_RL_MIN_BLOCKS
+#define INTERSECT_RL_MIN_BLOCKS 6
+#endif
+namespace {
+struct ApiRayIO {
+    const b200rt_ray* __restrict__ rays;
+    b200rt_hit* __restrict__ hits;
+    RT_DI bool load(uint32_t idx, DRay& r, uint32_t& tag) const {
+        const b200rt_ray in = rays[idx];
+        r.o = mk3(in.origin); r.d = mk3(in.direction); r.face = in.face_direction;
+        r.ex_prim = in.exclude_prim; r.ex_face = in.exclude_face;
+        tag = idx;
+        return true;
+    }
+    RT_DI void prefetch(uint32_t) const {}
+    RT_DI bool want_attrs(uint32_t) const { return true; }
+    RT_DI void store(uint32_t tag, const DHit& h) const {
+        b200rt_hit o;
+        o.prim_id = h.prim;
+        const bool hit = h.prim >= 0;
+        o.object_index = hit ? h.object : 0u;
+        o.face_direction = hit ? h.face : 0u;
+        o.distance = hit ? h.t : 0.0f;
+        o.position[0] = hit ? h.pos.x : 0.f; o.position[1] = hit ? h.pos.y : 0.f; o.position[2] = hit ? h.pos.z : 0.f;
+        o.normal[0] = hit ? h.normal.x : 0.f; o.normal[1] = hit ? h.normal.y : 0.f; o.normal[2] = hit ? h.normal.z : 0.f;
+        o.uv[0] = hit ? h.uv.x : 0.f; o.uv[1] = hit ? h.uv.y : 0.f;
+        hits[tag] = o;
+    }
+};
+}  // namespace
+__global__ void __launch_bounds__(kRlThreads, INTERSECT_RL_MIN_BLOCKS) intersect_rl_kernel(const DScene sc, const b200rt_ray* __restrict__ rays,
+                                                                                          uint32_t n, b200rt_hit* __restrict__ hits,
+                                                                                          DCounters* __restrict__ cnt) {
+    __shared__ RlShared sh;
+    const uint32_t lane = threadIdx.x & 31u;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    const ApiRayIO io{rays, hits};
+    cast_rays_in_lanes<false>(sc, io, n, sh, cs);
+    if (cnt) {
+        unsigned long long n_casts = cs.casts, n_conf = cs.confirms, n_fb = cs.fallbacks;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_casts += __shfl_xor_sync(0xffffffffu, n_casts, o);
+            n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+            n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
+        }
+        if (lane == 0u && n_casts) {
+            if (n_fb) atomicAdd(&cnt->fallbacks, n_fb);
+            atomicAdd(&cnt->casts, n_casts);
+            atomicAdd(&cnt->tri_pairs, n_casts * sc.n_tris);
+            atomicAdd(&cnt->sph_pairs, n_casts * sc.n_sph);
+            atomicAdd(&cnt->confirms, n_conf);
+        }
+    }
+}
+
 // photon.rs:18-21
 __global__ void resolve_kernel(const float4* __restrict__ accum, float* __restrict__ rgb, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -675,6 +734,17 @@ cudaError_t launch_intersect(const DScene& sc, const b200rt_ray* d_rays, size_t 
                              b200rt_hit* d_hits, DCounters* d_cnt, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + 127) / 128);
+    // one-tile scenes: rays in lanes (B200RT_INTERSECT=transposed keeps the warp-transposed kernel: measurement)
+    const char* sel = getenv("B200RT_INTERSECT");
+    if (cast_mode != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded == (uint32_t)kTileTris && sc.tri_filter_plain &&
+        n < 0xffffffffull && !(sel && sel[0] == 't')) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * INTERSECT_RL_MIN_BLOCKS, (n + 511) / 512);
+        intersect_rl_kernel<<<grid, kRlThreads, 0, stream>>>(sc, d_rays, (uint32_t)n, d_hits, d_cnt);
+        return cudaGetLastError();
+    }
     if (cast_mode == B200RT_CAST_BRUTE_EXACT)
         intersect_kernel<B200RT_CAST_BRUTE_EXACT><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_cnt);
     else

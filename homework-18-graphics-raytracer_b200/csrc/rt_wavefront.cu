@@ -29,6 +29,7 @@
 #include <string>
 
 #include "rt_cast.cuh"
+#include "rt_cast_rl.cuh"
 #include "rt_shade.cuh"
 #include "rt_types.h"
 #include "rt_wavefront.h"
@@ -191,17 +192,10 @@ __global__ void __launch_bounds__(128, WF_CAST_MIN_BLOCKS) wf_cast_kernel(const 
     }
 }
 
-// ---- cast, rays in lanes (scenes of one tile: <= 64 triangles) -----------------------------------------------------
-// In a wavefront round every lane has work, so the roles of the transposed cast can be swapped back: every lane owns
-// FOUR rays, packed as two FFMA2 pairs, and the CTA's 64 filter records sit in 4 KB of shared memory; each record is
-// read once per warp as four broadcast LDS.128 and feeds 2 x 21 FFMA2 (128 ray x triangle pairs per record read).
-// Measured on B200 (tools/filter_bench.py, the filter loop alone): 53.5 % of the FP32 roofline in this form against
-// 42 % for the transposed form, whose FFMA2 read three live register pairs each.  Keep / reject is the sign bit of
-// max(min(e0,e1,e2,t,c) + A|r|, g - |nd|), shifted into a per-ray mask (no predicates, no ballots).
-// The packed ray operands are 64-bit values built ONCE per block of rays (P2, rt_cast.cuh): as float2 arrays the
-// compiler re-packed them from scattered registers before every use (77 MOVs per 168 FFMA2 issue slots in the loop).
-// Phase 2 (certified select, spheres, attributes) then runs per lane for its four rays, which it reads back from a
-// per-thread shared-memory slot (no dynamically indexed register arrays, no local memory).
+// ---- cast, rays in lanes (scenes of one tile: <= 64 triangles): rt_cast_rl.cuh ---------------------------------------
+// The work list of the round is the ray source: item = path << 3 | slot; slot 0 = the path ray, 1..4 = shadow rays whose
+// origin / exclusion is the path's current hit.  The items of the warp's NEXT block are re-read after the filter loop to
+// pull their rows into L2 while phase 2 runs (the chain work[] -> path -> rows is two DRAM round trips otherwise).
 #ifndef WF_CAST_RL_PREFETCH
 #define WF_CAST_RL_PREFETCH 1
 #endif
@@ -209,147 +203,52 @@ RT_DI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" 
 #ifndef WF_CAST_RL_MIN_BLOCKS
 #define WF_CAST_RL_MIN_BLOCKS 6   // measured on B200, cast of a 16-epoch 4K batch: 4 -> 108.1 ms, 5 -> 103.1, 6 -> 101.1 (latency-bound phase 2)
 #endif
-__global__ void __launch_bounds__(128, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf,
-                                                                               DCounters* __restrict__ cnt) {
-    __shared__ float4 s_tile[4 * kTileTris];
-    __shared__ float4 s_ro[4][128];    // {origin, ray meta}   of ray j of thread t
-    __shared__ float4 s_rd[4][128];    // {direction, work item}
-    __shared__ uint2 s_mk[4][128];     // candidate mask
-    const uint32_t lane = threadIdx.x & 31u, tid = threadIdx.x;
+namespace {
+struct WfRayIO {
+    WfBuffers wb;
+    const uint32_t* __restrict__ work;
+    RT_DI bool load(uint32_t idx, DRay& r, uint32_t& tag) const {
+        const uint32_t item = work[idx];
+        const PathMem pm{wb.st, wb.req, item >> 3};
+        if ((item & 7u) == 0u) pm.get_ray(r);
+        else pm.get_shadow_ray((item & 7u) - 1u, r);
+        tag = item;
+        return true;
+    }
+    RT_DI void prefetch(uint32_t idx) const {
+        const uint32_t item = work[idx];
+        const size_t pid = item >> 3;
+        const uint32_t slot = item & 7u;
+        if (slot == 0u) prefetch_l2(wb.req + pid * WF_REQ_ROWS + REQ_O);
+        else {
+            prefetch_l2(wb.st + pid * kStateRows + ROW_HPOS);
+            prefetch_l2(wb.req + pid * WF_REQ_ROWS + REQ_SHADOW_D + (slot - 1u));
+        }
+    }
+    RT_DI bool want_attrs(uint32_t tag) const { return (tag & 7u) == 0u; }   // shadow rays: main.rs:435-447
+    RT_DI void store(uint32_t tag, const DHit& h) const {
+        const uint32_t pid = tag >> 3, slot = tag & 7u;
+        if (slot == 0u) {
+            const uint32_t m2 = h.prim >= 0 ? (h.face | (h.object << 8)) : 0u;
+            wb.res[(size_t)pid * 2u + 0u] = make_float4(__int_as_float(h.prim), u2f(m2), h.t, h.uv.x);
+            wb.res[(size_t)pid * 2u + 1u] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.uv.y);
+        } else {
+            wb.sres[(size_t)pid * 4u + (slot - 1u)] = make_float2(__int_as_float(h.prim), h.t);
+        }
+    }
+};
+}  // namespace
+__global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf,
+                                                                                      DCounters* __restrict__ cnt) {
+    __shared__ RlShared sh;
+    const uint32_t lane = threadIdx.x & 31u;
     if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
     const uint32_t n_work = wb.ctl->c[buf].work;
     if (n_work == 0u) return;
-    for (uint32_t i = threadIdx.x; i < 4u * kTileTris; i += blockDim.x) s_tile[i] = sc.tri_filter_plain[i];
-    __syncthreads();
-    const uint32_t* __restrict__ work = wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n;
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
-    const P2 A2 = p2_bc(sc.filter_A);
-    const float g = sc.filter_g;
-    // exactly 1.0f, but opaque to ptxas: a packed multiply by it MATERIALISES each ray operand in its own aligned
-    // register pair (a plain pack is coalesced with the LDG.128 destination quads and re-packed inside the loop)
-    const P2 one2 = p2_bc(__fmaf_rn(sc.filter_g, 0.0f, 1.0f));
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 128u; base < n_work; base += warps_total * 128u) {
-        // this lane's four rays: work items base + lane + 32 j
-        P2 ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], cf[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            DRay r[2];
-            float c[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = 2 * k + h;
-                const uint32_t idx = base + lane + 32u * (uint32_t)j;
-                r[h].o = mk3(0.f, 0.f, 0.f); r[h].d = mk3(0.f, 0.f, 1.f); r[h].face = kFront; r[h].ex_prim = -1; r[h].ex_face = kFront;
-                uint32_t item = 0xffffffffu;
-                if (idx < n_work) {
-                    item = work[idx];
-                    const PathMem pm{wb.st, wb.req, item >> 3};
-                    if ((item & 7u) == 0u) pm.get_ray(r[h]);
-                    else pm.get_shadow_ray((item & 7u) - 1u, r[h]);
-                }
-                c[h] = r[h].face == kFront ? -kCullK : (r[h].face == kBack ? kCullK : 0.0f);
-                s_ro[j][tid] = make_float4(r[h].o.x, r[h].o.y, r[h].o.z, u2f(pack_ray_meta(r[h].face, r[h].ex_prim, r[h].ex_face)));
-                s_rd[j][tid] = make_float4(r[h].d.x, r[h].d.y, r[h].d.z, u2f(item));
-            }
-            ox[k] = p2_mul(p2_pack(r[0].o.x, r[1].o.x), one2); oy[k] = p2_mul(p2_pack(r[0].o.y, r[1].o.y), one2);
-            oz[k] = p2_mul(p2_pack(r[0].o.z, r[1].o.z), one2);
-            dx[k] = p2_mul(p2_pack(r[0].d.x, r[1].d.x), one2); dy[k] = p2_mul(p2_pack(r[0].d.y, r[1].d.y), one2);
-            dz[k] = p2_mul(p2_pack(r[0].d.z, r[1].d.z), one2);
-            cf[k] = p2_mul(p2_pack(c[0], c[1]), one2);
-        }
-#if WF_CAST_RL_PREFETCH
-        // the work items of this warp's NEXT block: fetched now, used after the filter loop to pull the rays' rows
-        // into L2 while phase 2 runs (the chain work[] -> path -> rows is two DRAM round trips otherwise)
-        uint32_t nitem[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t idx = base + warps_total * 128u + lane + 32u * (uint32_t)j;
-            nitem[j] = idx < n_work ? work[idx] : 0xffffffffu;
-        }
-#endif
-        // phase 1: reject masks (bit set = rejected), triangle i in bit (31 - i) of its half
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            uint32_t rj0 = 0u, rj1 = 0u, rj2 = 0u, rj3 = 0u;
-#pragma unroll 2
-            for (int i = 0; i < 32; ++i) {
-                const float4* q = s_tile + 4 * (32 * half + i);
-                const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const P2 nd = p2_fma(p2_bc(q0.z), dz[k], p2_fma(p2_bc(q0.y), dy[k], p2_mul(p2_bc(q0.x), dx[k])));
-                    const P2 num = p2_fma(p2_bc(-q0.z), oz[k], p2_fma(p2_bc(-q0.y), oy[k], p2_fma(p2_bc(-q0.x), ox[k], p2_bc(q0.w))));
-                    float nda, ndb;
-                    p2_unpack(nd, nda, ndb);
-                    const float ra = rcp_approx(nda), rb = rcp_approx(ndb);
-                    const P2 t = p2_mul(num, p2_pack(ra, rb));
-                    const P2 cull = p2_mul(nd, cf[k]);
-                    const P2 px = p2_fma(t, dx[k], ox[k]), py = p2_fma(t, dy[k], oy[k]), pz = p2_fma(t, dz[k], oz[k]);
-                    const P2 e0 = p2_fma(p2_bc(q1.z), pz, p2_fma(p2_bc(q1.y), py, p2_fma(p2_bc(q1.x), px, p2_bc(q1.w))));
-                    const P2 e1 = p2_fma(p2_bc(q2.z), pz, p2_fma(p2_bc(q2.y), py, p2_fma(p2_bc(q2.x), px, p2_bc(q2.w))));
-                    const P2 e2 = p2_fma(p2_bc(q3.z), pz, p2_fma(p2_bc(q3.y), py, p2_fma(p2_bc(q3.x), px, p2_bc(q3.w))));
-                    float e0a, e0b, e1a, e1b, e2a, e2b, ta, tb, ca, cb;
-                    p2_unpack(e0, e0a, e0b); p2_unpack(e1, e1a, e1b); p2_unpack(e2, e2a, e2b); p2_unpack(t, ta, tb); p2_unpack(cull, ca, cb);
-                    const float ma = fminf(fminf(fminf(e0a, e1a), e2a), fminf(ta, ca));
-                    const float mb = fminf(fminf(fminf(e0b, e1b), e2b), fminf(tb, cb));
-                    const P2 ms = p2_fma(A2, p2_pack(fabsf(ra), fabsf(rb)), p2_pack(ma, mb));
-                    float msa, msb;
-                    p2_unpack(ms, msa, msb);
-                    // keep iff ms >= 0 or |nd| < g  <=>  max(ms, g - |nd|) is not negative (NaN ms: the second operand decides)
-                    const float ka = fmaxf(msa, g - fabsf(nda)), kb = fmaxf(msb, g - fabsf(ndb));
-                    if (k == 0) { rj0 = __funnelshift_l(__float_as_uint(ka), rj0, 1); rj1 = __funnelshift_l(__float_as_uint(kb), rj1, 1); }
-                    else        { rj2 = __funnelshift_l(__float_as_uint(ka), rj2, 1); rj3 = __funnelshift_l(__float_as_uint(kb), rj3, 1); }
-                }
-            }
-            const uint32_t k0 = ~__brev(rj0), k1 = ~__brev(rj1), k2 = ~__brev(rj2), k3 = ~__brev(rj3);
-            if (half == 0) { s_mk[0][tid].x = k0; s_mk[1][tid].x = k1; s_mk[2][tid].x = k2; s_mk[3][tid].x = k3; }
-            else           { s_mk[0][tid].y = k0; s_mk[1][tid].y = k1; s_mk[2][tid].y = k2; s_mk[3][tid].y = k3; }
-        }
-#if WF_CAST_RL_PREFETCH
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (nitem[j] != 0xffffffffu) {
-                const size_t npid = nitem[j] >> 3;
-                const uint32_t nslot = nitem[j] & 7u;
-                if (nslot == 0u) prefetch_l2(wb.req + npid * WF_REQ_ROWS + REQ_O);
-                else {
-                    prefetch_l2(wb.st + npid * kStateRows + ROW_HPOS);
-                    prefetch_l2(wb.req + npid * WF_REQ_ROWS + REQ_SHADOW_D + (nslot - 1u));
-                }
-            }
-        }
-#endif
-        // phase 2, ray by ray (every thread reads only its own slots: no barrier)
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-            const float4 a = s_ro[j][tid], b = s_rd[j][tid];
-            const uint32_t item = f2u(b.w);
-            if (item == 0xffffffffu) continue;
-            const uint32_t pid = item >> 3, slot = item & 7u;
-            const uint32_t meta = f2u(a.w);
-            DRay r;
-            r.o = mk3(a); r.d = mk3(b);
-            r.face = meta & 3u; r.ex_face = (meta >> 2) & 3u; r.ex_prim = (int32_t)(meta >> 4) - 1;
-            float dd;
-            const bool trust = ray_trusted(sc, r, dd);
-            Best best;
-            best_init(best);
-            confirm_tile(sc, 0u, tile_candidates(sc, 0u, s_mk[j][tid], trust), trust, r, best, cs, s_tile);
-            cast_spheres(sc, r, trust, dd, best);
-            DHit h;
-            h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
-            finalize_hit(sc, best, h, slot == 0u);
-            if (slot == 0u) {
-                const uint32_t m2 = h.prim >= 0 ? (h.face | (h.object << 8)) : 0u;
-                wb.res[(size_t)pid * 2u + 0u] = make_float4(__int_as_float(h.prim), u2f(m2), h.t, h.uv.x);
-                wb.res[(size_t)pid * 2u + 1u] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.uv.y);
-            } else {
-                wb.sres[(size_t)pid * 4u + (slot - 1u)] = make_float2(__int_as_float(h.prim), h.t);
-            }
-        }
-    }
+    const WfRayIO io{wb, wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n};
+    cast_rays_in_lanes<WF_CAST_RL_PREFETCH != 0>(sc, io, n_work, sh, cs);
     if (cnt) {
         unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
 #pragma unroll
@@ -1044,7 +943,7 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                 cudaEventRecord(ev_a, stream);
             }
             if (rays_in_lanes) {
-                wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+                wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
             } else if (split) {
                 wf_filter_kernel<<<sm_count * WF_FILTER_MIN_BLOCKS, 128, 0, stream>>>(sc, wb, buf);
                 if (timing) cudaEventRecord(timing->pool_mid[round - first_round_of_group], stream);
