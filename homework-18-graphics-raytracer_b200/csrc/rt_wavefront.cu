@@ -428,6 +428,18 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         const uint32_t px = pix % p.width, py = p.row_begin + pix / p.width;
 
         // ---- load: only the rows this segment reads -----------------------------------------------------------------
+        // rows that are read further down, behind decisions taken on the first ones (the shadow results and directions
+        // inside the light loop, the path ray and its hit): pulled into L2 now, so that the later loads do not each
+        // expose a DRAM round trip to the 4 warps per sub-partition this kernel runs with
+        if (valid && seg == WF_SEG_SHADE) {
+            prefetch_l2(wb.sres + (size_t)pid * 4u);
+            prefetch_l2(wb.req + (size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D);
+            prefetch_l2(wb.req + (size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + 2);
+            if (FUSED) {
+                prefetch_l2(wb.req + (size_t)pid * WF_REQ_ROWS + REQ_O);
+                prefetch_l2(wb.res + (size_t)pid * 2u);
+            }
+        }
         if (valid && seg != WF_SEG_INIT) {
             const float4 r0 = pm.ld(ROW_CTRL);
             flags = f2u(r0.x); depth = __float_as_int(r0.y); rng.draws = f2u(r0.z); sample_idx = f2u(r0.w);
@@ -573,13 +585,17 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 // the get_shade that closes a sample after a missed bounce (hit.ray.direction is replaced at main.rs:552)
                 const f3 view = purpose == SH_FINAL ? -h_dir : -h_dir_orig;
                 if (flags & F_PARTIAL) shade = mk3(pm.ld(ROW_HI_POS));
+                // the four shadow results of the path: one 32-byte sector, read before the loop
+                const float4 sr01 = reinterpret_cast<const float4*>(wb.sres)[(size_t)pid * 2u];
+                const float4 sr23 = reinterpret_cast<const float4*>(wb.sres)[(size_t)pid * 2u + 1u];
 #pragma unroll 1
                 for (uint32_t s = 0; s < 4u; ++s) {
                     if (!((need >> s) & 1u)) continue;
                     DirLight L;
                     const float4 sd = pm.get_shadow_dir(s);                            // {-L.dir, angular} kept by get_shade's entry
                     approx_light_cached(sc.lights[li0 + s], h.pos, -mk3(sd), sd.w, L);
-                    const float2 sr = wb.sres[(size_t)pid * 4u + s];
+                    const float2 sr = s == 0u ? make_float2(sr01.x, sr01.y) : s == 1u ? make_float2(sr01.z, sr01.w)
+                                    : s == 2u ? make_float2(sr23.x, sr23.y) : make_float2(sr23.z, sr23.w);
                     bool occluded = false;
                     if (__float_as_int(sr.x) >= 0) {
                         if (L.has_origin) {
