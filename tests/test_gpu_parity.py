@@ -254,3 +254,35 @@ def test_wavefront_depth0_and_many_lights(b200rt, oracle, gpu_ctx, fixture_world
     assert (acc[..., 3] != o_acc[..., 3]).sum() <= 3
     assert (rel_err(acc[..., :3], o_acc[..., :3]).max(axis=2) > 1e-3).mean() < 2e-3
     ctx.close()
+
+
+@pytest.mark.parametrize("extra", [1, 2])
+def test_wavefront_fused_levels_light_counts(b200rt, gpu_ctx, extra):
+    """Fused levels cast a hit's shadow rays and the next level's ray in one round: 4 lights = 4 shadow rays + the path
+    ray = 5 work items per path (the capacity of the work list); 5 lights take the one-pass-per-cast flow (two chunks).
+    Both must reproduce the megakernel: same samples, sums to fp32 summation order (several epochs in flight)."""
+    cam = b200rt.fixture_camera()
+    w = b200rt.World.fixture()
+    w.push_light(b200rt.point_light([1.5, 2.5, 1.0], [0.4, 0.3, 0.5]))
+    if extra == 2:
+        w.push_light(b200rt.spot_light([0.5, 3.0, 1.5], [0.0, -1.0, -0.2], 0.9, 2.0, [0.6, 0.6, 0.4]))
+    ctx = b200rt.Context(0)
+    ctx.upload_scene(w)
+    try:
+        for (wd, ht, ep, depth) in ((200, 150, 3, 5), (96, 64, 2, 2), (64, 48, 2, 1)):
+            p = b200rt.default_params(width=wd, height=ht, seed=6, depth=depth)
+            ctx.reset_stats()
+            acc = ctx.render_distributed(cam, p, 0, ep)
+            st = ctx.stats()
+            ctx.reset_stats()
+            mega = ctx.render_distributed(cam, b200rt.copy_params(p, tracer=b200rt.TRACER_MEGAKERNEL), 0, ep)
+            st_m = ctx.stats()
+            assert np.array_equal(acc[..., 3], mega[..., 3])
+            np.testing.assert_allclose(acc[..., :3], mega[..., :3], rtol=2e-6, atol=1e-7)
+            assert st["samples"] == st_m["samples"]
+            if extra == 1:
+                assert st["casts"] <= st_m["casts"]          # fused: closing get_shade reuses the shadow rays
+            else:
+                assert st["casts"] == st_m["casts"]          # > 4 lights: the megakernel's casts exactly
+    finally:
+        ctx.close()
