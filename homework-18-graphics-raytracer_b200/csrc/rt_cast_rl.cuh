@@ -37,6 +37,49 @@ RT_DI uint32_t rl_pack_ray_meta(uint32_t face, int32_t ex_prim, uint32_t ex_face
     return face | (ex_face << 2) | ((uint32_t)(ex_prim + 1) << 4);
 }
 
+// Phase 1 for one 64-triangle tile in shared memory and this lane's four rays (two packed pairs): keep[j] = the 64-bit
+// candidate mask of ray j (bit i = triangle i of the tile).
+RT_DI void rl_filter_tile(const float4* __restrict__ tile, const P2 (&ox)[2], const P2 (&oy)[2], const P2 (&oz)[2],
+                          const P2 (&dx)[2], const P2 (&dy)[2], const P2 (&dz)[2], const P2 (&cf)[2], const P2 A2,
+                          const float g, uint32_t (&keep)[4][2]) {
+    // reject masks (bit set = rejected), triangle i in bit (31 - i) of its half
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t rj0 = 0u, rj1 = 0u, rj2 = 0u, rj3 = 0u;
+#pragma unroll 2
+        for (int i = 0; i < 32; ++i) {
+            const float4* q = tile + 4 * (32 * half + i);
+            const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const P2 nd = p2_fma(p2_bc(q0.z), dz[k], p2_fma(p2_bc(q0.y), dy[k], p2_mul(p2_bc(q0.x), dx[k])));
+                const P2 num = p2_fma(p2_bc(-q0.z), oz[k], p2_fma(p2_bc(-q0.y), oy[k], p2_fma(p2_bc(-q0.x), ox[k], p2_bc(q0.w))));
+                float nda, ndb;
+                p2_unpack(nd, nda, ndb);
+                const float ra = rcp_approx(nda), rb = rcp_approx(ndb);
+                const P2 t = p2_mul(num, p2_pack(ra, rb));
+                const P2 cull = p2_mul(nd, cf[k]);
+                const P2 px = p2_fma(t, dx[k], ox[k]), py = p2_fma(t, dy[k], oy[k]), pz = p2_fma(t, dz[k], oz[k]);
+                const P2 e0 = p2_fma(p2_bc(q1.z), pz, p2_fma(p2_bc(q1.y), py, p2_fma(p2_bc(q1.x), px, p2_bc(q1.w))));
+                const P2 e1 = p2_fma(p2_bc(q2.z), pz, p2_fma(p2_bc(q2.y), py, p2_fma(p2_bc(q2.x), px, p2_bc(q2.w))));
+                const P2 e2 = p2_fma(p2_bc(q3.z), pz, p2_fma(p2_bc(q3.y), py, p2_fma(p2_bc(q3.x), px, p2_bc(q3.w))));
+                float e0a, e0b, e1a, e1b, e2a, e2b, ta, tb, ca, cb;
+                p2_unpack(e0, e0a, e0b); p2_unpack(e1, e1a, e1b); p2_unpack(e2, e2a, e2b); p2_unpack(t, ta, tb); p2_unpack(cull, ca, cb);
+                const float ma = fminf(fminf(fminf(e0a, e1a), e2a), fminf(ta, ca));
+                const float mb = fminf(fminf(fminf(e0b, e1b), e2b), fminf(tb, cb));
+                const P2 ms = p2_fma(A2, p2_pack(fabsf(ra), fabsf(rb)), p2_pack(ma, mb));
+                float msa, msb;
+                p2_unpack(ms, msa, msb);
+                // keep iff ms >= 0 or |nd| < g  <=>  max(ms, g - |nd|) is not negative (NaN ms: the second operand decides)
+                const float ka = fmaxf(msa, g - fabsf(nda)), kb = fmaxf(msb, g - fabsf(ndb));
+                if (k == 0) { rj0 = __funnelshift_l(__float_as_uint(ka), rj0, 1); rj1 = __funnelshift_l(__float_as_uint(kb), rj1, 1); }
+                else        { rj2 = __funnelshift_l(__float_as_uint(ka), rj2, 1); rj3 = __funnelshift_l(__float_as_uint(kb), rj3, 1); }
+            }
+        }
+        keep[0][half] = ~__brev(rj0); keep[1][half] = ~__brev(rj1); keep[2][half] = ~__brev(rj2); keep[3][half] = ~__brev(rj3);
+    }
+}
+
 // CTA-collective (kRlThreads threads): casts rays [0, n_work) of `io`, 128 rays per warp and iteration, work split over
 // the whole grid.  Call once per kernel; n_work may be 0.
 template <bool PREFETCH, class IO>
@@ -79,44 +122,11 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, IO io, const uint32_t n_work, Rl
             dz[k] = p2_mul(p2_pack(r[0].d.z, r[1].d.z), one2);
             cf[k] = p2_mul(p2_pack(c[0], c[1]), one2);
         }
-        // phase 1: reject masks (bit set = rejected), triangle i in bit (31 - i) of its half
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            uint32_t rj0 = 0u, rj1 = 0u, rj2 = 0u, rj3 = 0u;
-#pragma unroll 2
-            for (int i = 0; i < 32; ++i) {
-                const float4* q = sh.tile + 4 * (32 * half + i);
-                const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+        // phase 1: the candidate masks of this lane's four rays
+        uint32_t keep[4][2];
+        rl_filter_tile(sh.tile, ox, oy, oz, dx, dy, dz, cf, A2, g, keep);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const P2 nd = p2_fma(p2_bc(q0.z), dz[k], p2_fma(p2_bc(q0.y), dy[k], p2_mul(p2_bc(q0.x), dx[k])));
-                    const P2 num = p2_fma(p2_bc(-q0.z), oz[k], p2_fma(p2_bc(-q0.y), oy[k], p2_fma(p2_bc(-q0.x), ox[k], p2_bc(q0.w))));
-                    float nda, ndb;
-                    p2_unpack(nd, nda, ndb);
-                    const float ra = rcp_approx(nda), rb = rcp_approx(ndb);
-                    const P2 t = p2_mul(num, p2_pack(ra, rb));
-                    const P2 cull = p2_mul(nd, cf[k]);
-                    const P2 px = p2_fma(t, dx[k], ox[k]), py = p2_fma(t, dy[k], oy[k]), pz = p2_fma(t, dz[k], oz[k]);
-                    const P2 e0 = p2_fma(p2_bc(q1.z), pz, p2_fma(p2_bc(q1.y), py, p2_fma(p2_bc(q1.x), px, p2_bc(q1.w))));
-                    const P2 e1 = p2_fma(p2_bc(q2.z), pz, p2_fma(p2_bc(q2.y), py, p2_fma(p2_bc(q2.x), px, p2_bc(q2.w))));
-                    const P2 e2 = p2_fma(p2_bc(q3.z), pz, p2_fma(p2_bc(q3.y), py, p2_fma(p2_bc(q3.x), px, p2_bc(q3.w))));
-                    float e0a, e0b, e1a, e1b, e2a, e2b, ta, tb, ca, cb;
-                    p2_unpack(e0, e0a, e0b); p2_unpack(e1, e1a, e1b); p2_unpack(e2, e2a, e2b); p2_unpack(t, ta, tb); p2_unpack(cull, ca, cb);
-                    const float ma = fminf(fminf(fminf(e0a, e1a), e2a), fminf(ta, ca));
-                    const float mb = fminf(fminf(fminf(e0b, e1b), e2b), fminf(tb, cb));
-                    const P2 ms = p2_fma(A2, p2_pack(fabsf(ra), fabsf(rb)), p2_pack(ma, mb));
-                    float msa, msb;
-                    p2_unpack(ms, msa, msb);
-                    // keep iff ms >= 0 or |nd| < g  <=>  max(ms, g - |nd|) is not negative (NaN ms: the second operand decides)
-                    const float ka = fmaxf(msa, g - fabsf(nda)), kb = fmaxf(msb, g - fabsf(ndb));
-                    if (k == 0) { rj0 = __funnelshift_l(__float_as_uint(ka), rj0, 1); rj1 = __funnelshift_l(__float_as_uint(kb), rj1, 1); }
-                    else        { rj2 = __funnelshift_l(__float_as_uint(ka), rj2, 1); rj3 = __funnelshift_l(__float_as_uint(kb), rj3, 1); }
-                }
-            }
-            const uint32_t k0 = ~__brev(rj0), k1 = ~__brev(rj1), k2 = ~__brev(rj2), k3 = ~__brev(rj3);
-            if (half == 0) { sh.mk[0][tid].x = k0; sh.mk[1][tid].x = k1; sh.mk[2][tid].x = k2; sh.mk[3][tid].x = k3; }
-            else           { sh.mk[0][tid].y = k0; sh.mk[1][tid].y = k1; sh.mk[2][tid].y = k2; sh.mk[3][tid].y = k3; }
-        }
+        for (int j = 0; j < 4; ++j) sh.mk[j][tid] = make_uint2(keep[j][0], keep[j][1]);
         if (PREFETCH && blk + warps_total < n_blocks) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -139,6 +149,168 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, IO io, const uint32_t n_work, Rl
             Best best;
             best_init(best);
             confirm_tile(sc, 0u, tile_candidates(sc, 0u, sh.mk[j][tid], trust), trust, r, best, cs, sh.tile);
+            cast_spheres(sc, r, trust, dd, best);
+            DHit h;
+            h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
+            finalize_hit(sc, best, h, io.want_attrs(tag));
+            cs.casts += 1ull;
+            io.store(tag, h);
+        }
+    }
+}
+
+// ---- scenes of more than one tile ------------------------------------------------------------------------------------
+// The same loop with the tiles of plain records STREAMED through shared memory: every tile is one contiguous 4 KB
+// block, fetched by one TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx, issued by thread 0) into a two-deep
+// ring while the CTA filters the previous tile; an mbarrier per buffer tells the CTA the bytes have landed.  The four
+// warps of a CTA walk the tiles together (one __syncthreads per tile frees the buffer for the copy after next); each
+// still owns its own 128 rays.  The nearest hit so far of every ray lives in shared memory between tiles (the
+// position is o + t*dir, main.rs:210 / 304: recomputed, not stored); only rays with candidates in a tile touch it.
+constexpr uint32_t kRlTileBytes = 4u * kTileTris * 16u;
+
+struct RlTiledShared {                          // 38 KB per CTA
+    alignas(128) float4 tile[2][4 * kTileTris]; // TMA destinations
+    unsigned long long bar[2];                  // "tile landed" mbarriers
+    float4 ro[4][kRlThreads];
+    float4 rd[4][kRlThreads];
+    uint2 mk[4][kRlThreads];
+    float4 best[4][kRlThreads];                 // {(prim + 1) << 1 | backface, t, a0, a1}
+    float best_a2[4][kRlThreads];
+};
+
+RT_DI uint32_t rl_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+RT_DI void rl_mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rl_smem_addr(bar)), "r"(count) : "memory");
+}
+RT_DI void rl_tma_load_tile(float4* dst, const float4* src, unsigned long long* bar) {
+    const uint32_t b = rl_smem_addr(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(kRlTileBytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(rl_smem_addr(dst)), "l"(src), "r"(kRlTileBytes), "r"(b) : "memory");
+}
+RT_DI void rl_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t b = rl_smem_addr(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+RT_DI void rl_best_store(RlTiledShared& sh, int j, uint32_t tid, const Best& b) {
+    sh.best[j][tid] = make_float4(__uint_as_float(((uint32_t)(b.prim + 1) << 1) | (b.bf & 1u)), b.t, b.a0, b.a1);
+    sh.best_a2[j][tid] = b.a2;
+}
+RT_DI void rl_best_load(const RlTiledShared& sh, int j, uint32_t tid, const DRay& r, Best& b) {
+    const float4 v = sh.best[j][tid];
+    const uint32_t w = __float_as_uint(v.x);
+    b.prim = (int32_t)(w >> 1) - 1; b.bf = w & 1u; b.t = v.y; b.a0 = v.z; b.a1 = v.w; b.a2 = sh.best_a2[j][tid];
+    b.pos = b.prim >= 0 ? r.o + r.d * b.t : mk3(0.f, 0.f, 0.f);                   // main.rs:210 / 304
+}
+
+// CTA-collective (kRlThreads threads, ALL of them must call it, converged): casts rays [0, n_work) of `io` against
+// every tile of the scene.  Call once per kernel.
+template <class IO>
+RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_work, RlTiledShared& sh, CastStats& cs) {
+    const uint32_t lane = threadIdx.x & 31u, tid = threadIdx.x, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
+    if (n_work == 0u || n_tiles == 0u) return;
+    if (tid == 0u) { rl_mbar_init(&sh.bar[0], 1u); rl_mbar_init(&sh.bar[1], 1u); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t parity0 = 0u, parity1 = 0u;
+    const P2 A2 = p2_bc(sc.filter_A);
+    const float g = sc.filter_g;
+    const P2 one2 = p2_bc(__fmaf_rn(sc.filter_g, 0.0f, 1.0f));   // see cast_rays_in_lanes
+    const uint32_t n_blocks = (n_work + 127u) / 128u;
+    const uint32_t warps_per_cta = blockDim.x >> 5;
+    const uint32_t n_iters = (n_blocks + warps_per_cta - 1u) / warps_per_cta;
+    for (uint32_t it = blockIdx.x; it < n_iters; it += gridDim.x) {
+        // the first two tiles of this pass (both buffers are free: the pass before ended on a barrier)
+        if (tid == 0u) {
+            rl_tma_load_tile(sh.tile[0], sc.tri_filter_plain, &sh.bar[0]);
+            if (n_tiles > 1u) rl_tma_load_tile(sh.tile[1], sc.tri_filter_plain + 4u * kTileTris, &sh.bar[1]);
+        }
+        const uint32_t base = (it * warps_per_cta + warp) * 128u;   // >= n_work: this warp idles through the pass
+        P2 ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], cf[2];
+        uint32_t valid4 = 0u, trust4 = 0u;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            DRay r[2];
+            float c[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * k + h;
+                const uint32_t idx = base + lane + 32u * (uint32_t)j;
+                r[h].o = mk3(0.f, 0.f, 0.f); r[h].d = mk3(0.f, 0.f, 1.f); r[h].face = kFront; r[h].ex_prim = -1; r[h].ex_face = kFront;
+                uint32_t tag = kRlNoRay;
+                if (base < n_work && idx < n_work && !io.load(idx, r[h], tag)) tag = kRlNoRay;
+                c[h] = r[h].face == kFront ? -kCullK : (r[h].face == kBack ? kCullK : 0.0f);
+                float dd;
+                if (tag != kRlNoRay) { valid4 |= 1u << j; if (ray_trusted(sc, r[h], dd)) trust4 |= 1u << j; }
+                sh.ro[j][tid] = make_float4(r[h].o.x, r[h].o.y, r[h].o.z, __uint_as_float(rl_pack_ray_meta(r[h].face, r[h].ex_prim, r[h].ex_face)));
+                sh.rd[j][tid] = make_float4(r[h].d.x, r[h].d.y, r[h].d.z, __uint_as_float(tag));
+                Best b0;
+                best_init(b0);
+                rl_best_store(sh, j, tid, b0);
+            }
+            ox[k] = p2_mul(p2_pack(r[0].o.x, r[1].o.x), one2); oy[k] = p2_mul(p2_pack(r[0].o.y, r[1].o.y), one2);
+            oz[k] = p2_mul(p2_pack(r[0].o.z, r[1].o.z), one2);
+            dx[k] = p2_mul(p2_pack(r[0].d.x, r[1].d.x), one2); dy[k] = p2_mul(p2_pack(r[0].d.y, r[1].d.y), one2);
+            dz[k] = p2_mul(p2_pack(r[0].d.z, r[1].d.z), one2);
+            cf[k] = p2_mul(p2_pack(c[0], c[1]), one2);
+        }
+#pragma unroll 1
+        for (uint32_t tile = 0; tile < n_tiles; ++tile) {
+            const uint32_t buf = tile & 1u;
+            if (buf == 0u) { rl_mbar_wait(&sh.bar[0], parity0); parity0 ^= 1u; }
+            else           { rl_mbar_wait(&sh.bar[1], parity1); parity1 ^= 1u; }
+            const float4* __restrict__ recs = sh.tile[buf];
+            if (valid4) {                                           // (warp-uniform up to the tail of the last block)
+                uint32_t keep[4][2];
+                rl_filter_tile(recs, ox, oy, oz, dx, dy, dz, cf, A2, g, keep);
+                // phase 2 of this tile, for the rays that have candidates in it (untrusted rays: every triangle)
+                uint32_t todo4 = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (((valid4 >> j) & 1u) && ((keep[j][0] | keep[j][1]) != 0u || !((trust4 >> j) & 1u))) todo4 |= 1u << j;
+                if (todo4) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sh.mk[j][tid] = make_uint2(keep[j][0], keep[j][1]);
+#pragma unroll 1
+                    while (todo4) {
+                        const int j = __ffs((int)todo4) - 1;
+                        todo4 &= todo4 - 1u;
+                        const float4 a = sh.ro[j][tid], b = sh.rd[j][tid];
+                        const uint32_t meta = __float_as_uint(a.w);
+                        DRay r;
+                        r.o = mk3(a); r.d = mk3(b);
+                        r.face = meta & 3u; r.ex_face = (meta >> 2) & 3u; r.ex_prim = (int32_t)(meta >> 4) - 1;
+                        const bool trust = (trust4 >> j) & 1u;
+                        Best best;
+                        rl_best_load(sh, j, tid, r, best);
+                        confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, sh.mk[j][tid], trust), trust, r, best, cs, recs);
+                        rl_best_store(sh, j, tid, best);
+                    }
+                }
+            }
+            __syncthreads();                                        // every warp is done with this buffer
+            if (tid == 0u && tile + 2u < n_tiles)
+                rl_tma_load_tile(sh.tile[buf], sc.tri_filter_plain + (size_t)(tile + 2u) * 4u * kTileTris, &sh.bar[buf]);
+        }
+        // spheres, attributes, results
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            if (!((valid4 >> j) & 1u)) continue;
+            const float4 a = sh.ro[j][tid], b = sh.rd[j][tid];
+            const uint32_t tag = __float_as_uint(b.w), meta = __float_as_uint(a.w);
+            DRay r;
+            r.o = mk3(a); r.d = mk3(b);
+            r.face = meta & 3u; r.ex_face = (meta >> 2) & 3u; r.ex_prim = (int32_t)(meta >> 4) - 1;
+            float dd;
+            const bool trust = ray_trusted(sc, r, dd);
+            Best best;
+            rl_best_load(sh, j, tid, r, best);
             cast_spheres(sc, r, trust, dd, best);
             DHit h;
             h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;

@@ -678,6 +678,32 @@ __global__ void __launch_bounds__(kRlThreads, INTERSECT_RL_MIN_BLOCKS) intersect
     }
 }
 
+__global__ void __launch_bounds__(kRlThreads, 5) intersect_rl_tiled_kernel(const DScene sc, const b200rt_ray* __restrict__ rays, uint32_t n,
+                                                                          b200rt_hit* __restrict__ hits, DCounters* __restrict__ cnt) {
+    __shared__ RlTiledShared sh;
+    const uint32_t lane = threadIdx.x & 31u;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    const ApiRayIO io{rays, hits};
+    cast_rays_in_lanes_tiled(sc, io, n, sh, cs);
+    if (cnt) {
+        unsigned long long n_casts = cs.casts, n_conf = cs.confirms, n_fb = cs.fallbacks;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_casts += __shfl_xor_sync(0xffffffffu, n_casts, o);
+            n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+            n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
+        }
+        if (lane == 0u && n_casts) {
+            if (n_fb) atomicAdd(&cnt->fallbacks, n_fb);
+            atomicAdd(&cnt->casts, n_casts);
+            atomicAdd(&cnt->tri_pairs, n_casts * sc.n_tris);
+            atomicAdd(&cnt->sph_pairs, n_casts * sc.n_sph);
+            atomicAdd(&cnt->confirms, n_conf);
+        }
+    }
+}
+
 // photon.rs:18-21
 __global__ void resolve_kernel(const float4* __restrict__ accum, float* __restrict__ rgb, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -736,13 +762,18 @@ cudaError_t launch_intersect(const DScene& sc, const b200rt_ray* d_rays, size_t 
     const unsigned blocks = (unsigned)((n + 127) / 128);
     // one-tile scenes: rays in lanes (B200RT_INTERSECT=transposed keeps the warp-transposed kernel: measurement)
     const char* sel = getenv("B200RT_INTERSECT");
-    if (cast_mode != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded == (uint32_t)kTileTris && sc.tri_filter_plain &&
+    if (cast_mode != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded >= (uint32_t)kTileTris && sc.tri_filter_plain &&
         n < 0xffffffffull && !(sel && sel[0] == 't')) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * INTERSECT_RL_MIN_BLOCKS, (n + 511) / 512);
-        intersect_rl_kernel<<<grid, kRlThreads, 0, stream>>>(sc, d_rays, (uint32_t)n, d_hits, d_cnt);
+        if (sc.n_tris_padded == (uint32_t)kTileTris) {
+            const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * INTERSECT_RL_MIN_BLOCKS, (n + 511) / 512);
+            intersect_rl_kernel<<<grid, kRlThreads, 0, stream>>>(sc, d_rays, (uint32_t)n, d_hits, d_cnt);
+        } else {   // larger scenes: the tiles stream through shared memory (TMA)
+            const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * 5, (n + 511) / 512);
+            intersect_rl_tiled_kernel<<<grid, kRlThreads, 0, stream>>>(sc, d_rays, (uint32_t)n, d_hits, d_cnt);
+        }
         return cudaGetLastError();
     }
     if (cast_mode == B200RT_CAST_BRUTE_EXACT)

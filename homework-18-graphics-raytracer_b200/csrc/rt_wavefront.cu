@@ -266,6 +266,39 @@ __global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_
     }
 }
 
+// ---- cast, rays in lanes, scenes of more than one tile: the tiles stream through shared memory by TMA --------------------
+#ifndef WF_CAST_RL_TILED_MIN_BLOCKS
+#define WF_CAST_RL_TILED_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_TILED_MIN_BLOCKS) wf_cast_rl_tiled_kernel(const DScene sc, const WfBuffers wb,
+                                                                                                  const uint32_t buf,
+                                                                                                  DCounters* __restrict__ cnt) {
+    __shared__ RlTiledShared sh;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
+    const uint32_t n_work = wb.ctl->c[buf].work;
+    if (n_work == 0u) return;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    const WfRayIO io{wb, wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n};
+    cast_rays_in_lanes_tiled(sc, io, n_work, sh, cs);
+    if (cnt) {
+        unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+            n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
+        }
+        if (lane == 0u && n_conf) atomicAdd(&cnt->confirms, n_conf);
+        if (lane == 0u && n_fb) atomicAdd(&cnt->fallbacks, n_fb);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicAdd(&cnt->casts, (unsigned long long)n_work);
+            atomicAdd(&cnt->tri_pairs, (unsigned long long)n_work * sc.n_tris);
+            atomicAdd(&cnt->sph_pairs, (unsigned long long)n_work * sc.n_sph);
+        }
+    }
+}
+
 // ---- cast, split in two kernels (scenes of <= kSplitMaxTiles tiles) ------------------------------------------------
 // wf_filter_kernel   phase 1 alone: the packed-FFMA2 filter loop for every ray of the round, nothing else.  Few
 //                    registers (the lane's triangle pair + two rays in flight), so 6 warps per sub-partition hide the
@@ -922,10 +955,11 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     const int cast_blocks = sm_count * WF_CAST_MIN_BLOCKS;
     // small scenes: phase 1 and phase 2 of the cast as two kernels (B200RT_WF_FUSED_CAST=1 keeps them fused: tuning)
     const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
-    // B200RT_WF_CAST = rl (default for one-tile scenes) | fused (default otherwise) | split : tuning / measurement
+    // B200RT_WF_CAST = rl (default: rays in lanes, tiles by TMA for larger scenes) | fused (warp-transposed) | split : tuning / measurement
     const char* cast_env = getenv("B200RT_WF_CAST");
     const std::string cast_sel = cast_env ? cast_env : "";
     const bool rays_in_lanes = n_tiles == 1 && (cast_sel.empty() || cast_sel == "rl");
+    const bool rays_in_lanes_tiled = n_tiles > 1 && (cast_sel.empty() || cast_sel == "rl");
     const bool split = !rays_in_lanes && n_tiles >= 1 && n_tiles <= WF_SPLIT_MAX_TILES && cast_sel == "split";
     // fused levels (one light chunk): a hit's shadow rays and the next level's ray are cast in the same round, and one
     // kernel pass per level consumes both (B200RT_WF_FUSED_LEVELS=0: one pass per cast, as for scenes of > 4 lights)
@@ -960,6 +994,8 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
             }
             if (rays_in_lanes) {
                 wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
+            } else if (rays_in_lanes_tiled) {
+                wf_cast_rl_tiled_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
             } else if (split) {
                 wf_filter_kernel<<<sm_count * WF_FILTER_MIN_BLOCKS, 128, 0, stream>>>(sc, wb, buf);
                 if (timing) cudaEventRecord(timing->pool_mid[round - first_round_of_group], stream);
