@@ -355,6 +355,29 @@ int b200rt_upload_scene(b200rt_ctx* ctx, const b200rt_scene* s) {
         std::memcpy(o.color, l.color, 12);
     }
 
+    // Shadow rays of a directional light (main.rs:423-431: direction = -light.direction, back faces only) have the same
+    // direction wherever they start, so the face test of main.rs:184-188 is a property of the (light, triangle) pair:
+    // bf = n . (-direction) > 0 in the reference's own arithmetic; !bf triangles are culled for every such ray.  The
+    // cast kernels drop them from the candidate sets (this includes triangles exactly parallel to the light, which the
+    // conservative filter has to keep for every ray).  Only for scenes of one light chunk (slot s <-> light s).
+    const uint32_t n_tiles_sc = nt_pad / kTileTris;
+    std::vector<uint2> shadow_cull((size_t)std::max(nl <= 4u ? nl : 0u, 1u) * std::max(n_tiles_sc, 1u), make_uint2(0u, 0u));
+    if (nl <= 4u) {
+        for (uint32_t k = 0; k < nl; ++k) {
+            if (s->lights[k].kind != B200RT_LIGHT_DIRECTIONAL) continue;
+            const V3 rd = -v3(s->lights[k].direction);
+            for (uint32_t i = 0; i < nt; ++i) {
+                const float4 q0 = tri_exact[4 * (size_t)i];
+                const bool bf = dot(v3(q0.x, q0.y, q0.z), rd) > 0.0f;          // primitives.rs:45
+                if (!bf) {
+                    uint2& m = shadow_cull[(size_t)k * n_tiles_sc + i / kTileTris];
+                    const uint32_t bit = i % kTileTris;
+                    if (bit < 32u) m.x |= 1u << bit; else m.y |= 1u << (bit - 32u);
+                }
+            }
+        }
+    }
+
     // ---- one device blob, 256-byte aligned sections --------------------------------------------------
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;
@@ -364,6 +387,7 @@ int b200rt_upload_scene(b200rt_ctx* ctx, const b200rt_scene* s) {
     const size_t off_sobj = off;   off = align(off + sph_obj.size() * sizeof(uint32_t));
     const size_t off_mat = off;    off = align(off + mats.size() * sizeof(DMaterial));
     const size_t off_light = off;  off = align(off + lights.size() * sizeof(DLight));
+    const size_t off_cull = off;   off = align(off + shadow_cull.size() * sizeof(uint2));
     const size_t total = off;
     std::vector<unsigned char> blob(total, 0);
     std::memcpy(blob.data() + off_exact, tri_exact.data(), tri_exact.size() * sizeof(float4));
@@ -372,6 +396,7 @@ int b200rt_upload_scene(b200rt_ctx* ctx, const b200rt_scene* s) {
     std::memcpy(blob.data() + off_sobj, sph_obj.data(), sph_obj.size() * sizeof(uint32_t));
     std::memcpy(blob.data() + off_mat, mats.data(), mats.size() * sizeof(DMaterial));
     std::memcpy(blob.data() + off_light, lights.data(), lights.size() * sizeof(DLight));
+    std::memcpy(blob.data() + off_cull, shadow_cull.data(), shadow_cull.size() * sizeof(uint2));
 
     ctx->have_scene = false;
     int rc = ensure(ctx, &ctx->d_scene_blob, &ctx->scene_blob_bytes, total);
@@ -388,6 +413,7 @@ int b200rt_upload_scene(b200rt_ctx* ctx, const b200rt_scene* s) {
     d.sph_obj = reinterpret_cast<const uint32_t*>(base + off_sobj);
     d.materials = reinterpret_cast<const DMaterial*>(base + off_mat);
     d.lights = reinterpret_cast<const DLight*>(base + off_light);
+    d.shadow_cull = nl <= 4u && nl > 0u ? reinterpret_cast<const uint2*>(base + off_cull) : nullptr;
     d.n_tris = nt; d.n_sph = ns; d.n_lights = nl; d.n_materials = nm;
     d.n_tris_padded = nt_pad;
     // bounds for the filter slack

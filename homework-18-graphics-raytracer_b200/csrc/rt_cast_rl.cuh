@@ -17,6 +17,7 @@
 //     bool     load(uint32_t idx, DRay& r, uint32_t& tag)   ray of work index idx (idx < n_work); tag travels to store()
 //     void     prefetch(uint32_t idx)                        hint: idx will be loaded by this lane in its next block
 //     bool     want_attrs(uint32_t tag)                      false: only "is there a hit, and how far" is needed
+//     uint2    culled(const DScene&, uint32_t tag, uint32_t tile)   triangles of the tile this ray is known to cull
 //     void     store(uint32_t tag, const DHit& h)
 #pragma once
 #include "rt_cast.cuh"
@@ -148,7 +149,8 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, IO io, const uint32_t n_work, Rl
             const bool trust = ray_trusted(sc, r, dd);
             Best best;
             best_init(best);
-            confirm_tile(sc, 0u, tile_candidates(sc, 0u, sh.mk[j][tid], trust), trust, r, best, cs, sh.tile);
+            const uint2 km = sh.mk[j][tid], cm = io.culled(sc, tag, 0u);
+            confirm_tile(sc, 0u, tile_candidates(sc, 0u, make_uint2(km.x & ~cm.x, km.y & ~cm.y), trust), trust, r, best, cs, sh.tile);
             cast_spheres(sc, r, trust, dd, best);
             DHit h;
             h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
@@ -289,7 +291,9 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
                         const bool trust = (trust4 >> j) & 1u;
                         Best best;
                         rl_best_load(sh, j, tid, r, best);
-                        confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, sh.mk[j][tid], trust), trust, r, best, cs, recs);
+                        const uint2 km = sh.mk[j][tid], cm = io.culled(sc, __float_as_uint(b.w), tile);
+                        confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, make_uint2(km.x & ~cm.x, km.y & ~cm.y), trust),
+                                     trust, r, best, cs, recs);
                         rl_best_store(sh, j, tid, best);
                     }
                 }

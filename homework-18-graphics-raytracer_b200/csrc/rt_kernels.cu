@@ -637,6 +637,7 @@ struct ApiRayIO {
     }
     RT_DI void prefetch(uint32_t) const {}
     RT_DI bool want_attrs(uint32_t) const { return true; }
+    RT_DI uint2 culled(const DScene&, uint32_t, uint32_t) const { return make_uint2(0u, 0u); }
     RT_DI void store(uint32_t tag, const DHit& h) const {
         b200rt_hit o;
         o.prim_id = h.prim;

@@ -55,6 +55,9 @@ struct DScene {
     const uint32_t* sph_obj;
     const DMaterial* materials;
     const DLight* lights;
+    // [light][tile] 64-bit masks (scenes of <= 4 lights, else null): triangles that the shadow ray of a DIRECTIONAL light
+    // culls whatever its origin — the ray's direction is the light's, so main.rs:185-188 is decided per triangle.
+    const uint2* shadow_cull;
     uint32_t n_tris, n_sph, n_lights, n_materials;
     uint32_t n_tris_padded;  // tri_filter is padded to a multiple of kTileTris (padding is masked off)
     float origin_bound;      // filter slack was derived for ray origins with |o| <= origin_bound

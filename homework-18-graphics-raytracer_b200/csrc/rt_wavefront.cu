@@ -226,6 +226,12 @@ struct WfRayIO {
         }
     }
     RT_DI bool want_attrs(uint32_t tag) const { return (tag & 7u) == 0u; }   // shadow rays: main.rs:435-447
+    // shadow slot s of a one-chunk scene is light s: a directional light's shadow ray culls the same triangles everywhere
+    RT_DI uint2 culled(const DScene& sc, uint32_t tag, uint32_t tile) const {
+        const uint32_t slot = tag & 7u;
+        if (slot == 0u || sc.shadow_cull == nullptr) return make_uint2(0u, 0u);
+        return sc.shadow_cull[(size_t)(slot - 1u) * (sc.n_tris_padded / kTileTris) + tile];
+    }
     RT_DI void store(uint32_t tag, const DHit& h) const {
         const uint32_t pid = tag >> 3, slot = tag & 7u;
         if (slot == 0u) {
