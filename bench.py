@@ -32,7 +32,9 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (description, width, height, depth, epochs, tracer)
     "c4": ("C4 fixture scene 3840x2160 DoF+scatter 256 epochs depth 5 (epoch-sharded)", 3840, 2160, 5, 256, "distributed"),
+    "c1": ("C1 fixture scene 1280x960 Whitted depth 5, the reference's own frame (row-sharded)", 1280, 960, 5, 1, "whitted"),
     "c2": ("C2 fixture scene 1920x1080 Whitted depth 8 (row-sharded)", 1920, 1080, 8, 1, "whitted"),
+    "c3": ("C3 fixture scene 3840x2160 Whitted depth 5 (row-sharded)", 3840, 2160, 5, 1, "whitted"),
 }
 FLOP_TRI, FLOP_SPH = 36.0, 28.0   # algorithmic flop per ray x triangle / ray x sphere pair
 

@@ -15,7 +15,8 @@
 //
 // IO (a small struct, by value) connects the loop to its rays and results:
 //     bool     load(uint32_t idx, DRay& r, uint32_t& tag)   ray of work index idx (idx < n_work); tag travels to store()
-//     void     prefetch(uint32_t idx)                        hint: idx will be loaded by this lane in its next block
+//     uint32_t peek(uint32_t idx)                            the handle (!= kRlNoRay) prefetch() wants for work index idx
+//     void     prefetch(uint32_t handle)                     hint: the ray behind the handle is loaded in the lane's next block
 //     bool     want_attrs(uint32_t tag)                      false: only "is there a hit, and how far" is needed
 //     uint2    culled(const DScene&, uint32_t tag, uint32_t tile)   triangles of the tile this ray is known to cull
 //     void     store(uint32_t tag, const DHit& h)
@@ -123,17 +124,25 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, IO io, const uint32_t n_work, Rl
             dz[k] = p2_mul(p2_pack(r[0].d.z, r[1].d.z), one2);
             cf[k] = p2_mul(p2_pack(c[0], c[1]), one2);
         }
+        // the handles of this lane's NEXT four rays are fetched now, their rows are pulled into L2 after the filter loop
+        // (while phase 2 runs): the chain handle -> rows is two DRAM round trips otherwise
+        uint32_t next[4];
+        if (PREFETCH) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t idx = base + stride + lane + 32u * (uint32_t)j;
+                next[j] = (blk + warps_total < n_blocks && idx < n_work) ? io.peek(idx) : kRlNoRay;
+            }
+        }
         // phase 1: the candidate masks of this lane's four rays
         uint32_t keep[4][2];
         rl_filter_tile(sh.tile, ox, oy, oz, dx, dy, dz, cf, A2, g, keep);
 #pragma unroll
         for (int j = 0; j < 4; ++j) sh.mk[j][tid] = make_uint2(keep[j][0], keep[j][1]);
-        if (PREFETCH && blk + warps_total < n_blocks) {
+        if (PREFETCH) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t idx = base + stride + lane + 32u * (uint32_t)j;
-                if (idx < n_work) io.prefetch(idx);
-            }
+            for (int j = 0; j < 4; ++j)
+                if (next[j] != kRlNoRay) io.prefetch(next[j]);
         }
         // phase 2, ray by ray (every thread reads only its own slots: no barrier)
 #pragma unroll 1

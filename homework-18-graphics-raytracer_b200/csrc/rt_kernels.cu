@@ -635,6 +635,7 @@ struct ApiRayIO {
         tag = idx;
         return true;
     }
+    RT_DI uint32_t peek(uint32_t) const { return 0u; }
     RT_DI void prefetch(uint32_t) const {}
     RT_DI bool want_attrs(uint32_t) const { return true; }
     RT_DI uint2 culled(const DScene&, uint32_t, uint32_t) const { return make_uint2(0u, 0u); }

@@ -215,8 +215,8 @@ struct WfRayIO {
         tag = item;
         return true;
     }
-    RT_DI void prefetch(uint32_t idx) const {
-        const uint32_t item = work[idx];
+    RT_DI uint32_t peek(uint32_t idx) const { return work[idx]; }
+    RT_DI void prefetch(uint32_t item) const {
         const size_t pid = item >> 3;
         const uint32_t slot = item & 7u;
         if (slot == 0u) prefetch_l2(wb.req + pid * WF_REQ_ROWS + REQ_O);
