@@ -61,6 +61,22 @@ RT_DI f3 get_specular(const MatEval& m, f3 n, f3 view, f3 l) {
     const float amount = nl_powf(fmaxf(dot(reflected_ray, view), 0.0f), specular) * energy_conserving;
     return m.specular * amount;
 }
+// The two material constants of get_specular (materials.rs:60-62), for callers that evaluate several lights: the same
+// expressions, hence the same bits, without an IEEE division per light.
+struct SpecConst { float exponent, energy; };
+RT_DI SpecConst spec_const(const MatEval& m) {
+    SpecConst c;
+    c.exponent = 1.0f / (m.smoothness + kF32Epsilon);
+    c.energy = (c.exponent + 8.0f) / (8.0f * kPi);
+    return c;
+}
+RT_DI f3 get_specular(const MatEval& m, const SpecConst& c, f3 n, f3 view, f3 l) {
+    const float cosine = dot(l, n);
+    if (cosine <= 0.0f) return mk3(0.0f, 0.0f, 0.0f);
+    const f3 reflected_ray = 2.0f * cosine * n - l;
+    const float amount = nl_powf(fmaxf(dot(reflected_ray, view), 0.0f), c.exponent) * c.energy;
+    return m.specular * amount;
+}
 
 struct DirLight {  // lights.rs:6-11
     bool has_origin;

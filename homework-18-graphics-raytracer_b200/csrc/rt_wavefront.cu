@@ -51,7 +51,7 @@ enum : int {
     ROW_PEND,         // pending factor (BRDF probe value or decay^distance); w = get_refract travel distance
     ROW_HI_POS,       // get_refract: previous inside hit position, retry count | get_shade: sum of earlier light chunks
     ROW_SUM,          // this slot's PhotonAccumulator {sum.rgb, weight_sum} (photon.rs:9-12)
-    ROW_SPARE,
+    ROW_SPARE,        // adjust_normal(hit.at.normal) of the current hit, between get_shade's entry and its sum
     kStateRows
 };
 static_assert(kStateRows == WF_STATE_ROWS, "state rows");
@@ -606,7 +606,8 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         } else {   // WF_SEG_SHADE: the shadow rays of the current light chunk are back (main.rs:435-461)
             if (valid) {
                 const MatEval mat = material_approx(sc.materials, h.object, h.uv);
-                const f3 nadj = adjust_normal(mat, h.normal);
+                const f3 nadj = mk3(pm.ld(ROW_SPARE));     // adjust_normal(mat, h.normal), kept by get_shade's entry
+                const SpecConst spc = spec_const(mat);
                 const uint32_t li0 = (flags >> F_LI0_SHIFT) & 0xfffu, need = (flags >> F_NEED_SHIFT) & 15u;
                 const uint32_t purpose = (flags >> F_PURPOSE_SHIFT) & 3u;
                 // fused levels: the path ray that travelled with these shadow rays
@@ -645,10 +646,10 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                     if (!occluded) {
                         const f3 ldir = -L.dir;
                         const f3 diffuse = get_diffuse(mat, nadj, ldir) * L.color;         // main.rs:458
-                        const f3 specular = get_specular(mat, nadj, view, ldir) * L.color; // main.rs:459
+                        const f3 specular = get_specular(mat, spc, nadj, view, ldir) * L.color; // main.rs:459
                         shade = shade + diffuse * (1.0f - mat.shiness) + specular * mat.shiness;  // main.rs:461
                         if (FUSED && want_final) {
-                            const f3 specular2 = get_specular(mat, nadj, -h_dir, ldir) * L.color;
+                            const f3 specular2 = get_specular(mat, spc, nadj, -h_dir, ldir) * L.color;
                             shade2 = shade2 + diffuse * (1.0f - mat.shiness) + specular2 * mat.shiness;
                         }
                     }
@@ -742,6 +743,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
             if (do_shade_begin) {
                 const MatEval mat = material_approx(sc.materials, h.object, h.uv);
                 const f3 nadj = adjust_normal(mat, h.normal);
+                pm.sv(ROW_SPARE, make_float4(nadj.x, nadj.y, nadj.z, 0.0f));   // the consuming pass does not rotate it again
                 // (fused levels run scenes of one light chunk: get_shade always starts at light 0)
                 uint32_t li0 = (seg == WF_SEG_SHADE && !FUSED) ? ((flags >> F_LI0_SHIFT) & 0xfffu) : 0u;
                 if (seg != WF_SEG_SHADE || FUSED) flags &= ~F_PARTIAL;
