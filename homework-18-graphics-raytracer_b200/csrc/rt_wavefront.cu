@@ -422,6 +422,9 @@ template <> struct LogicCfg<WF_SEG_REFR, false> { static constexpr int kMinBlock
 // shade + arrival + next level in one pass
 template <> struct LogicCfg<WF_SEG_SHADE, true> { static constexpr int kMinBlocks = WF_FUSED_SHADE_MIN_BLOCKS, kThreads = WF_FUSED_SHADE_THREADS; };
 
+#ifndef WF_LOGIC_PREFETCH
+#define WF_LOGIC_PREFETCH 1
+#endif
 template <int SEG, bool FUSED>
 __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, FUSED>::kMinBlocks) wf_logic_kernel(const DScene sc, const DCamera cam, const DParams p,
                                                           const WfBuffers wb, const uint32_t buf,
@@ -436,11 +439,26 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
     const uint32_t n_epochs = p.epoch_count;
     unsigned long long n_samples = 0ull;
 
+    // the path of this lane in the warp's NEXT chunk is fetched one iteration ahead, and its rows are pulled into L2
+    // before the current chunk's stores and queue atomics: the chain queue -> path -> rows is otherwise two DRAM round
+    // trips at the top of every iteration of a kernel that runs 4-6 warps per sub-partition
+    const uint32_t* __restrict__ q_this = wb.q + ((size_t)buf * WF_SEG_COUNT + seg) * wb.n;
+    uint32_t pid_ahead = 0u;
+    if (seg != WF_SEG_INIT && WF_LOGIC_PREFETCH) {
+        const uint32_t k0 = gw * 32u + lane;
+        if (gw < total_chunks && k0 < n_this) pid_ahead = q_this[k0];
+    }
     for (uint32_t chunk = gw; chunk < total_chunks; chunk += n_warps) {
         const uint32_t k = chunk * 32u + lane;
         const bool valid = k < n_this;
-        const uint32_t pid = !valid ? 0u : (seg == WF_SEG_INIT ? k : wb.q[((size_t)buf * WF_SEG_COUNT + seg) * wb.n + k]);
+        const uint32_t pid = !valid ? 0u : (seg == WF_SEG_INIT ? k : (WF_LOGIC_PREFETCH ? pid_ahead : q_this[k]));
         const PathMem pm{wb.st, wb.req, pid};
+        bool valid_ahead = false;
+        if (seg != WF_SEG_INIT && WF_LOGIC_PREFETCH) {
+            const uint32_t k_ahead = (chunk + n_warps) * 32u + lane;
+            valid_ahead = chunk + n_warps < total_chunks && k_ahead < n_this;
+            if (valid_ahead) pid_ahead = q_this[k_ahead];
+        }
 
         // ---- per-path registers (the names of trace_kernel) --------------------------------------------------
         f3 acc = mk3(0.f, 0.f, 0.f), T = mk3(1.f, 1.f, 1.f), a_shade = mk3(0.f, 0.f, 0.f);
@@ -467,18 +485,6 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         const uint32_t px = pix % p.width, py = p.row_begin + pix / p.width;
 
         // ---- load: only the rows this segment reads -----------------------------------------------------------------
-        // rows that are read further down, behind decisions taken on the first ones (the shadow results and directions
-        // inside the light loop, the path ray and its hit): pulled into L2 now, so that the later loads do not each
-        // expose a DRAM round trip to the 4 warps per sub-partition this kernel runs with
-        if (valid && seg == WF_SEG_SHADE) {
-            prefetch_l2(wb.sres + (size_t)pid * 4u);
-            prefetch_l2(wb.req + (size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D);
-            prefetch_l2(wb.req + (size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + 2);
-            if (FUSED) {
-                prefetch_l2(wb.req + (size_t)pid * WF_REQ_ROWS + REQ_O);
-                prefetch_l2(wb.res + (size_t)pid * 2u);
-            }
-        }
         if (valid && seg != WF_SEG_INIT) {
             const float4 r0 = pm.ld(ROW_CTRL);
             flags = f2u(r0.x); depth = __float_as_int(r0.y); rng.draws = f2u(r0.z); sample_idx = f2u(r0.w);
@@ -813,6 +819,18 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
             }
         }
 
+        if (seg != WF_SEG_INIT && WF_LOGIC_PREFETCH && valid_ahead) {
+            const float4* st_a = wb.st + (size_t)pid_ahead * kStateRows;
+            const float4* rq_a = wb.req + (size_t)pid_ahead * WF_REQ_ROWS;
+            prefetch_l2(st_a + ROW_CTRL);                                             // + ROW_RNG
+            if (seg != WF_SEG_PRIMARY) { prefetch_l2(st_a + ROW_HPOS); prefetch_l2(st_a + ROW_HDIR); prefetch_l2(st_a + ROW_PEND); }
+            if (seg == WF_SEG_SHADE) {
+                prefetch_l2(st_a + ROW_ACC); prefetch_l2(st_a + ROW_SUM);             // + ROW_T, + ROW_SPARE
+                prefetch_l2(wb.sres + (size_t)pid_ahead * 4u);
+                prefetch_l2(rq_a + REQ_SHADOW_D); prefetch_l2(rq_a + REQ_SHADOW_D + 2);
+            }
+            if (seg != WF_SEG_SHADE || FUSED) { prefetch_l2(rq_a + REQ_O); prefetch_l2(wb.res + (size_t)pid_ahead * 2u); }
+        }
         // ---- store what changed and append the path to the next round's queues -------------------------------------------
         if (valid && out != OUT_RETIRE) {
             pm.sv(ROW_CTRL, make_float4(u2f(flags), __int_as_float(depth), u2f(rng.draws), u2f(sample_idx)));
