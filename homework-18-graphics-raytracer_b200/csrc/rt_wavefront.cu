@@ -55,6 +55,8 @@ enum : int {
     kStateRows
 };
 static_assert(kStateRows == WF_STATE_ROWS, "state rows");
+static_assert(ROW_CTRL % 2 == 0 && ROW_RNG == ROW_CTRL + 1 && ROW_ACC % 2 == 0 && ROW_T == ROW_ACC + 1 && ROW_HPOS % 2 == 0 &&
+              ROW_HNORMAL == ROW_HPOS + 1 && ROW_HDIR % 2 == 0 && ROW_HDIR0 == ROW_HDIR + 1, "rows that travel together share a sector");
 enum : int { REQ_O = 0, REQ_D = 1, REQ_SHADOW_D = 2 };
 
 // flags word of ROW_CTRL
@@ -82,16 +84,41 @@ RT_DI uint32_t pack_ray_meta(uint32_t face, int32_t ex_prim, uint32_t ex_face) {
     return face | (ex_face << 2) | ((uint32_t)(ex_prim + 1) << 4);
 }
 
+// Two neighbouring float4 rows that share a 32-byte sector, as ONE 256-bit access (LDG.E.256 / STG.E.256 on sm_100):
+// half the load / store instructions and L1 requests of the path-row gathers.  p must be 32-byte aligned.
+#ifndef WF_ROWS_256
+#define WF_ROWS_256 1
+#endif
+RT_DI void ld_rows2(const float4* p, float4& a, float4& b) {
+#if WF_ROWS_256
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+RT_DI void st_rows2(float4* p, float4 a, float4 b) {
+#if WF_ROWS_256
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+
 struct PathMem {
     float4* st; float4* req; uint32_t pid;
     RT_DI float4 ld(int row) const { return st[(size_t)pid * kStateRows + row]; }
     RT_DI void sv(int row, float4 v) const { st[(size_t)pid * kStateRows + row] = v; }
+    RT_DI void ld2(int row, float4& a, float4& b) const { ld_rows2(st + (size_t)pid * kStateRows + row, a, b); }   // row even
+    RT_DI void sv2(int row, float4 a, float4 b) const { st_rows2(st + (size_t)pid * kStateRows + row, a, b); }
     RT_DI void put_ray(const DRay& r) const {
-        req[(size_t)pid * WF_REQ_ROWS + REQ_O] = make_float4(r.o.x, r.o.y, r.o.z, u2f(pack_ray_meta(r.face, r.ex_prim, r.ex_face)));
-        req[(size_t)pid * WF_REQ_ROWS + REQ_D] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+        st_rows2(req + (size_t)pid * WF_REQ_ROWS + REQ_O,
+                 make_float4(r.o.x, r.o.y, r.o.z, u2f(pack_ray_meta(r.face, r.ex_prim, r.ex_face))), make_float4(r.d.x, r.d.y, r.d.z, 0.0f));
     }
     RT_DI void get_ray(DRay& r) const {
-        const float4 a = req[(size_t)pid * WF_REQ_ROWS + REQ_O], b = req[(size_t)pid * WF_REQ_ROWS + REQ_D];
+        float4 a, b;
+        ld_rows2(req + (size_t)pid * WF_REQ_ROWS + REQ_O, a, b);
         const uint32_t m = f2u(a.w);
         r.o = mk3(a); r.d = mk3(b); r.face = m & 3u; r.ex_face = (m >> 2) & 3u; r.ex_prim = (int32_t)(m >> 4) - 1;
     }
@@ -236,8 +263,8 @@ struct WfRayIO {
         const uint32_t pid = tag >> 3, slot = tag & 7u;
         if (slot == 0u) {
             const uint32_t m2 = h.prim >= 0 ? (h.face | (h.object << 8)) : 0u;
-            wb.res[(size_t)pid * 2u + 0u] = make_float4(__int_as_float(h.prim), u2f(m2), h.t, h.uv.x);
-            wb.res[(size_t)pid * 2u + 1u] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.uv.y);
+            st_rows2(wb.res + (size_t)pid * 2u, make_float4(__int_as_float(h.prim), u2f(m2), h.t, h.uv.x),
+                     make_float4(h.normal.x, h.normal.y, h.normal.z, h.uv.y));
         } else {
             wb.sres[(size_t)pid * 4u + (slot - 1u)] = make_float2(__int_as_float(h.prim), h.t);
         }
@@ -486,11 +513,16 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
 
         // ---- load: only the rows this segment reads -----------------------------------------------------------------
         if (valid && seg != WF_SEG_INIT) {
-            const float4 r0 = pm.ld(ROW_CTRL);
+            constexpr bool kNeedRng = seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE || (FUSED && seg == WF_SEG_BOUNCE);
+            float4 r0, r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kNeedRng) pm.ld2(ROW_CTRL, r0, r1); else r0 = pm.ld(ROW_CTRL);
             flags = f2u(r0.x); depth = __float_as_int(r0.y); rng.draws = f2u(r0.z); sample_idx = f2u(r0.w);
             rng.x = px; rng.y = py; rng.epoch = p.epoch_begin + sample_idx;
+            if (kNeedRng) { rng.b[0] = f2u(r1.x); rng.b[1] = f2u(r1.y); rng.b[2] = f2u(r1.z); rng.b[3] = f2u(r1.w); }
             if (seg != WF_SEG_PRIMARY) {
-                const float4 r5 = pm.ld(ROW_HPOS), r6 = pm.ld(ROW_HNORMAL), r7 = pm.ld(ROW_HDIR), r8 = pm.ld(ROW_HDIR0);
+                float4 r5, r6, r7, r8;
+                pm.ld2(ROW_HPOS, r5, r6);
+                pm.ld2(ROW_HDIR, r7, r8);
                 h.pos = mk3(r5); h.prim = __float_as_int(r5.w);
                 h.normal = mk3(r6);
                 const uint32_t meta = f2u(r6.w);
@@ -499,15 +531,13 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 h_dir_orig = mk3(r8); h.uv.y = r8.w;
             }
             if (seg == WF_SEG_SHADE) {
-                acc = mk3(pm.ld(ROW_ACC)); T = mk3(pm.ld(ROW_T));
+                float4 ra, rt;
+                pm.ld2(ROW_ACC, ra, rt);
+                acc = mk3(ra); T = mk3(rt);
             }
             if (seg == WF_SEG_SHADE || seg == WF_SEG_BOUNCE || seg == WF_SEG_REFR) {
                 const float4 r4 = pm.ld(ROW_PEND);
                 pend = mk3(r4); rf_travel = r4.w;
-            }
-            if (seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE || (FUSED && seg == WF_SEG_BOUNCE)) {
-                const float4 r = pm.ld(ROW_RNG);
-                rng.b[0] = f2u(r.x); rng.b[1] = f2u(r.y); rng.b[2] = f2u(r.z); rng.b[3] = f2u(r.w);
             }
         }
 
@@ -570,7 +600,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         };
         auto load_path_hit = [&](float4& a, float4& b, DHit& hc) {
             pm.get_ray(ray);
-            a = wb.res[(size_t)pid * 2u]; b = wb.res[(size_t)pid * 2u + 1u];
+            ld_rows2(wb.res + (size_t)pid * 2u, a, b);
             hc.prim = __float_as_int(a.x);
             const uint32_t meta = f2u(a.y);
             hc.face = meta & 1u; hc.object = meta >> 8; hc.t = a.z;
@@ -607,7 +637,9 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         } else if (seg == WF_SEG_REFR) {                                               // main.rs:371-402
             if (valid) {
                 pm.get_ray(ray);
-                refract_step(wb.res[(size_t)pid * 2u], wb.res[(size_t)pid * 2u + 1u]);
+                float4 ra, rb;
+                ld_rows2(wb.res + (size_t)pid * 2u, ra, rb);
+                refract_step(ra, rb);
             }
         } else {   // WF_SEG_SHADE: the shadow rays of the current light chunk are back (main.rs:435-461)
             if (valid) {
@@ -632,8 +664,8 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 const f3 view = purpose == SH_FINAL ? -h_dir : -h_dir_orig;
                 if (flags & F_PARTIAL) shade = mk3(pm.ld(ROW_HI_POS));
                 // the four shadow results of the path: one 32-byte sector, read before the loop
-                const float4 sr01 = reinterpret_cast<const float4*>(wb.sres)[(size_t)pid * 2u];
-                const float4 sr23 = reinterpret_cast<const float4*>(wb.sres)[(size_t)pid * 2u + 1u];
+                float4 sr01, sr23;
+                ld_rows2(reinterpret_cast<const float4*>(wb.sres) + (size_t)pid * 2u, sr01, sr23);
 #pragma unroll 1
                 for (uint32_t s = 0; s < 4u; ++s) {
                     if (!((need >> s) & 1u)) continue;
@@ -833,18 +865,16 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         }
         // ---- store what changed and append the path to the next round's queues -------------------------------------------
         if (valid && out != OUT_RETIRE) {
-            pm.sv(ROW_CTRL, make_float4(u2f(flags), __int_as_float(depth), u2f(rng.draws), u2f(sample_idx)));
-            if (w_acc) { pm.sv(ROW_ACC, make_float4(acc.x, acc.y, acc.z, 0.f)); pm.sv(ROW_T, make_float4(T.x, T.y, T.z, 0.f)); }
+            const float4 ctrl = make_float4(u2f(flags), __int_as_float(depth), u2f(rng.draws), u2f(sample_idx));
+            if (w_rng) pm.sv2(ROW_CTRL, ctrl, make_float4(u2f(rng.b[0]), u2f(rng.b[1]), u2f(rng.b[2]), u2f(rng.b[3])));
+            else pm.sv(ROW_CTRL, ctrl);
+            if (w_acc) pm.sv2(ROW_ACC, make_float4(acc.x, acc.y, acc.z, 0.f), make_float4(T.x, T.y, T.z, 0.f));
             if (w_pend) pm.sv(ROW_PEND, make_float4(pend.x, pend.y, pend.z, rf_travel));
-            if (w_hit) {
-                pm.sv(ROW_HPOS, make_float4(h.pos.x, h.pos.y, h.pos.z, __int_as_float(h.prim)));
-                pm.sv(ROW_HNORMAL, make_float4(h.normal.x, h.normal.y, h.normal.z, u2f(h.face | (h_rayface << 1) | (h.object << 8))));
-            }
-            if (w_dirs) {
-                pm.sv(ROW_HDIR, make_float4(h_dir.x, h_dir.y, h_dir.z, h.uv.x));
-                pm.sv(ROW_HDIR0, make_float4(h_dir_orig.x, h_dir_orig.y, h_dir_orig.z, h.uv.y));
-            }
-            if (w_rng) pm.sv(ROW_RNG, make_float4(u2f(rng.b[0]), u2f(rng.b[1]), u2f(rng.b[2]), u2f(rng.b[3])));
+            if (w_hit)
+                pm.sv2(ROW_HPOS, make_float4(h.pos.x, h.pos.y, h.pos.z, __int_as_float(h.prim)),
+                       make_float4(h.normal.x, h.normal.y, h.normal.z, u2f(h.face | (h_rayface << 1) | (h.object << 8))));
+            if (w_dirs)
+                pm.sv2(ROW_HDIR, make_float4(h_dir.x, h_dir.y, h_dir.z, h.uv.x), make_float4(h_dir_orig.x, h_dir_orig.y, h_dir_orig.z, h.uv.y));
             if (out == OUT_PRIMARY || out == OUT_BOUNCE || out == OUT_REFR || pre_ray) pm.put_ray(ray);
         }
         // ---- route: every reservation of this chunk (5 queues, the cast work list, the retired counter) is one
