@@ -49,14 +49,15 @@ enum : int {
     ROW_HDIR,         // hit.ray.direction (after scatter_hit), uv.x
     ROW_HDIR0,        // hit.ray.direction before scatter_hit (view direction of the BRDF probes), uv.y
     ROW_PEND,         // pending factor (BRDF probe value or decay^distance); w = get_refract travel distance
+    ROW_NADJ,         // adjust_normal(hit.at.normal) of the current hit, between get_shade's entry and its sum
     ROW_HI_POS,       // get_refract: previous inside hit position, retry count | get_shade: sum of earlier light chunks
     ROW_SUM,          // this slot's PhotonAccumulator {sum.rgb, weight_sum} (photon.rs:9-12)
-    ROW_SPARE,        // adjust_normal(hit.at.normal) of the current hit, between get_shade's entry and its sum
     kStateRows
 };
 static_assert(kStateRows == WF_STATE_ROWS, "state rows");
 static_assert(ROW_CTRL % 2 == 0 && ROW_RNG == ROW_CTRL + 1 && ROW_ACC % 2 == 0 && ROW_T == ROW_ACC + 1 && ROW_HPOS % 2 == 0 &&
-              ROW_HNORMAL == ROW_HPOS + 1 && ROW_HDIR % 2 == 0 && ROW_HDIR0 == ROW_HDIR + 1, "rows that travel together share a sector");
+              ROW_HNORMAL == ROW_HPOS + 1 && ROW_HDIR % 2 == 0 && ROW_HDIR0 == ROW_HDIR + 1 && ROW_PEND % 2 == 0 &&
+              ROW_NADJ == ROW_PEND + 1 && ROW_HI_POS % 2 == 0 && ROW_SUM == ROW_HI_POS + 1, "rows that travel together share a sector");
 enum : int { REQ_O = 0, REQ_D = 1, REQ_SHADOW_D = 2 };
 
 // flags word of ROW_CTRL
@@ -500,6 +501,8 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         uint32_t h_rayface = kFront;
         f3 shade = mk3(0.f, 0.f, 0.f);
         bool do_level = false, do_shade_begin = false, do_finish = false;
+        f3 nadj_in = mk3(0.f, 0.f, 1.f), nadj_out = nadj_in;   // adjusted normal: read by get_shade's sum, written by its entry
+        bool w_nadj = false;
         bool pre_level = false;     // fused levels: do_level runs for the level AFTER the pending get_shade (depth - 1)
         bool pre_ray = false;       // ... and requested a path ray that travels with the shadow rays
         bool w_hit = false, w_dirs = false, w_acc = false, w_pend = false, w_rng = false;   // rows to write back
@@ -536,7 +539,9 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 acc = mk3(ra); T = mk3(rt);
             }
             if (seg == WF_SEG_SHADE || seg == WF_SEG_BOUNCE || seg == WF_SEG_REFR) {
-                const float4 r4 = pm.ld(ROW_PEND);
+                float4 r4;
+                if (seg == WF_SEG_SHADE) { float4 r9; pm.ld2(ROW_PEND, r4, r9); nadj_in = mk3(r9); }
+                else r4 = pm.ld(ROW_PEND);
                 pend = mk3(r4); rf_travel = r4.w;
             }
         }
@@ -644,7 +649,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         } else {   // WF_SEG_SHADE: the shadow rays of the current light chunk are back (main.rs:435-461)
             if (valid) {
                 const MatEval mat = material_approx(sc.materials, h.object, h.uv);
-                const f3 nadj = mk3(pm.ld(ROW_SPARE));     // adjust_normal(mat, h.normal), kept by get_shade's entry
+                const f3 nadj = nadj_in;                   // adjust_normal(mat, h.normal), kept by get_shade's entry
                 const SpecConst spc = spec_const(mat);
                 const uint32_t li0 = (flags >> F_LI0_SHIFT) & 0xfffu, need = (flags >> F_NEED_SHIFT) & 15u;
                 const uint32_t purpose = (flags >> F_PURPOSE_SHIFT) & 3u;
@@ -781,7 +786,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
             if (do_shade_begin) {
                 const MatEval mat = material_approx(sc.materials, h.object, h.uv);
                 const f3 nadj = adjust_normal(mat, h.normal);
-                pm.sv(ROW_SPARE, make_float4(nadj.x, nadj.y, nadj.z, 0.0f));   // the consuming pass does not rotate it again
+                nadj_out = nadj; w_nadj = true;                                // the consuming pass does not rotate it again
                 // (fused levels run scenes of one light chunk: get_shade always starts at light 0)
                 uint32_t li0 = (seg == WF_SEG_SHADE && !FUSED) ? ((flags >> F_LI0_SHIFT) & 0xfffu) : 0u;
                 if (seg != WF_SEG_SHADE || FUSED) flags &= ~F_PARTIAL;
@@ -822,13 +827,12 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                     sample_idx += wb.epar;
                 } else {
                     sample_idx = e_lane;
-                    pm.sv(ROW_SUM, sum);
-                    pm.sv(ROW_SPARE, sum);        // completes the 32-byte sector: no read-modify-write in DRAM
+                    pm.sv2(ROW_HI_POS, sum, sum);   // the whole 32-byte sector: no read-modify-write in DRAM
                 }
                 if (sample_idx >= n_epochs) out = OUT_RETIRE;
                 else {
                     acc = mk3(0.f, 0.f, 0.f); T = mk3(1.f, 1.f, 1.f); depth = p.depth; flags = 0u;
-                    w_acc = false; w_hit = false; w_dirs = false; w_pend = false;
+                    w_acc = false; w_hit = false; w_dirs = false; w_pend = false; w_nadj = false;
                     // Camera::shoot_focus, main.rs:101-127 (Box-Muller on two stream uniforms)
                     float clip_x, clip_y;
                     clip_y = ((float)p.height / 2.0f - (float)py) / (float)p.height;   // main.rs:1094
@@ -857,7 +861,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
             prefetch_l2(st_a + ROW_CTRL);                                             // + ROW_RNG
             if (seg != WF_SEG_PRIMARY) { prefetch_l2(st_a + ROW_HPOS); prefetch_l2(st_a + ROW_HDIR); prefetch_l2(st_a + ROW_PEND); }
             if (seg == WF_SEG_SHADE) {
-                prefetch_l2(st_a + ROW_ACC); prefetch_l2(st_a + ROW_SUM);             // + ROW_T, + ROW_SPARE
+                prefetch_l2(st_a + ROW_ACC);                                          // + ROW_T
                 prefetch_l2(wb.sres + (size_t)pid_ahead * 4u);
                 prefetch_l2(rq_a + REQ_SHADOW_D); prefetch_l2(rq_a + REQ_SHADOW_D + 2);
             }
@@ -869,7 +873,9 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
             if (w_rng) pm.sv2(ROW_CTRL, ctrl, make_float4(u2f(rng.b[0]), u2f(rng.b[1]), u2f(rng.b[2]), u2f(rng.b[3])));
             else pm.sv(ROW_CTRL, ctrl);
             if (w_acc) pm.sv2(ROW_ACC, make_float4(acc.x, acc.y, acc.z, 0.f), make_float4(T.x, T.y, T.z, 0.f));
-            if (w_pend) pm.sv(ROW_PEND, make_float4(pend.x, pend.y, pend.z, rf_travel));
+            if (w_pend && w_nadj) pm.sv2(ROW_PEND, make_float4(pend.x, pend.y, pend.z, rf_travel), make_float4(nadj_out.x, nadj_out.y, nadj_out.z, 0.0f));
+            else if (w_pend) pm.sv(ROW_PEND, make_float4(pend.x, pend.y, pend.z, rf_travel));
+            else if (w_nadj) pm.sv(ROW_NADJ, make_float4(nadj_out.x, nadj_out.y, nadj_out.z, 0.0f));
             if (w_hit)
                 pm.sv2(ROW_HPOS, make_float4(h.pos.x, h.pos.y, h.pos.z, __int_as_float(h.prim)),
                        make_float4(h.normal.x, h.normal.y, h.normal.z, u2f(h.face | (h_rayface << 1) | (h.object << 8))));
