@@ -383,6 +383,26 @@ RT_DI bool ray_trusted(const DScene& sc, const DRay& ray, float& dd) {
     return (oo <= sc.origin_bound * sc.origin_bound) && (fabsf(dd - 1.0f) <= 1e-3f);  // false for NaN/Inf
 }
 
+// A ray with a NaN component (the reference produces them: a zero vector normalised, 0/0 in a refraction) makes every
+// plane distance NaN, and main.rs:205 / 224 / 229-233 reject nothing on NaN: each triangle that the face and exclusion
+// tests (main.rs:185-200) let through replaces the nearest-so-far, whatever came before.  The ordered walk over all
+// triangles therefore ends with the LAST such triangle — found here from the end, instead of 100 000 exact tests by
+// one lane.  (Infinite components do not qualify: their distances can be +-inf, which compare.)
+RT_DI bool ray_has_nan(const DRay& r) {
+    const float oo = r.o.x * r.o.x + r.o.y * r.o.y + r.o.z * r.o.z, dd = r.d.x * r.d.x + r.d.y * r.d.y + r.d.z * r.d.z;
+    return oo != oo || dd != dd;
+}
+RT_DI void cast_nan_ray_triangles(const DScene& sc, const DRay& r, Best& best, CastStats& cs) {
+#pragma unroll 1
+    for (int32_t i = (int32_t)sc.n_tris - 1; i >= 0; --i) {
+        Best b;
+        best_init(b);
+        tri_exact_test(sc.tri_exact + 4 * (size_t)i, i, r, b);
+        cs.confirms += 1ull;
+        if (b.prim >= 0) { best = b; return; }
+    }
+}
+
 // this ray's candidates of one tile from its filter mask (padding lanes masked off; untrusted rays: every triangle)
 RT_DI unsigned long long tile_candidates(const DScene& sc, uint32_t tile, uint2 m, bool trust) {
     const uint32_t left = sc.n_tris - tile * kTileTris;              // >= 1
@@ -440,16 +460,18 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
     const bool trust = ray_trusted(sc, ray, dd);
     __syncwarp();
     const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
+    const bool nan_ray = active && !trust && ray_has_nan(ray);
     for (uint32_t tile = 0; tile < n_tiles; ++tile) {
         TriPair c;
         if (tile == 0) c = tile0; else load_tripair(sc.tri_filter, tile, lane, c);
         filter_tile(sc, s_rays, c, n_act, lane);
         __syncwarp();
-        if (active) confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, s_mask[rank], trust), trust, ray, best, cs,
+        if (active && !nan_ray) confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, s_mask[rank], trust), trust, ray, best, cs,
                                  sc.tri_exact + 4 * (size_t)(tile * kTileTris));
         __syncwarp();   // masks (and, after the last tile, the ray slots) are free again
     }
     if (active) {
+        if (nan_ray) cast_nan_ray_triangles(sc, ray, best, cs);
         cast_spheres(sc, ray, trust, dd, best);
         finalize_hit(sc, best, hit, want_attrs);
         cs.casts += 1ull;

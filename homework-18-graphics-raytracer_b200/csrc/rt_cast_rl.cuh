@@ -219,6 +219,54 @@ RT_DI void rl_best_load(const RlTiledShared& sh, int j, uint32_t tid, const DRay
     b.pos = b.prim >= 0 ? r.o + r.d * b.t : mk3(0.f, 0.f, 0.f);                   // main.rs:210 / 304
 }
 
+// One UNTRUSTED ray (origin at infinity after a t = +inf hit, |dir| != 1: the filter's bounds do not cover it) against
+// the tile, by the whole warp: every lane puts two triangles through the exact test on its own (main.rs:184-227 do not
+// look at the nearest-so-far), then the nearest-so-far rule (main.rs:229-233) is folded over the triangles that passed,
+// in index order, by all lanes alike.  32x the speed of one lane walking 64 exact tests, same result as the walk for
+// any distances (inf and NaN included).  Warp-collective: every lane calls it with the SAME ray and the owner's best.
+RT_DI void rl_coop_exact_tile(const DScene& sc, uint32_t tile, const DRay& r, uint32_t lane, bool& best_valid, float& best_t,
+                              Best& winner, bool& changed, CastStats& cs) {
+    const uint32_t base = tile * kTileTris;
+    Best ba, bb;
+    best_init(ba); best_init(bb);
+    const uint32_t ia = base + lane, ib = base + 32u + lane;
+    if (ia < sc.n_tris) tri_exact_test(sc.tri_exact + 4 * (size_t)ia, (int32_t)ia, r, ba);
+    if (ib < sc.n_tris) tri_exact_test(sc.tri_exact + 4 * (size_t)ib, (int32_t)ib, r, bb);
+    unsigned ma = __ballot_sync(kFullMask, ba.prim >= 0), mb = __ballot_sync(kFullMask, bb.prim >= 0);
+    int win = -1;                                   // 0..31: triangle a of that lane, 32..63: triangle b
+#pragma unroll 1
+    while (ma) {
+        const int l = __ffs((int)ma) - 1;
+        ma &= ma - 1u;
+        const float t = __shfl_sync(kFullMask, ba.t, l);
+        if (best_valid && best_t < t) continue;     // main.rs:229-233
+        best_valid = true; best_t = t; win = l;
+    }
+#pragma unroll 1
+    while (mb) {
+        const int l = __ffs((int)mb) - 1;
+        mb &= mb - 1u;
+        const float t = __shfl_sync(kFullMask, bb.t, l);
+        if (best_valid && best_t < t) continue;
+        best_valid = true; best_t = t; win = 32 + l;
+    }
+    if (lane == 0u) cs.confirms += (unsigned long long)min(kTileTris, (int)(sc.n_tris - base));
+    if (win >= 0) {
+        const int l = win & 31;
+        const Best mine = win < 32 ? ba : bb;
+        winner.prim = __shfl_sync(kFullMask, mine.prim, l);
+        winner.bf = __shfl_sync(kFullMask, mine.bf, l);
+        winner.t = __shfl_sync(kFullMask, mine.t, l);
+        winner.pos.x = __shfl_sync(kFullMask, mine.pos.x, l);
+        winner.pos.y = __shfl_sync(kFullMask, mine.pos.y, l);
+        winner.pos.z = __shfl_sync(kFullMask, mine.pos.z, l);
+        winner.a0 = __shfl_sync(kFullMask, mine.a0, l);
+        winner.a1 = __shfl_sync(kFullMask, mine.a1, l);
+        winner.a2 = __shfl_sync(kFullMask, mine.a2, l);
+        changed = true;
+    }
+}
+
 // CTA-collective (kRlThreads threads, ALL of them must call it, converged): casts rays [0, n_work) of `io` against
 // every tile of the scene.  Call once per kernel.
 template <class IO>
@@ -244,7 +292,7 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
         }
         const uint32_t base = (it * warps_per_cta + warp) * 128u;   // >= n_work: this warp idles through the pass
         P2 ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], cf[2];
-        uint32_t valid4 = 0u, trust4 = 0u;
+        uint32_t valid4 = 0u, trust4 = 0u, nan4 = 0u;   // nan4: rays with a NaN component (cast_nan_ray_triangles)
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             DRay r[2];
@@ -258,7 +306,11 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
                 if (base < n_work && idx < n_work && !io.load(idx, r[h], tag)) tag = kRlNoRay;
                 c[h] = r[h].face == kFront ? -kCullK : (r[h].face == kBack ? kCullK : 0.0f);
                 float dd;
-                if (tag != kRlNoRay) { valid4 |= 1u << j; if (ray_trusted(sc, r[h], dd)) trust4 |= 1u << j; }
+                if (tag != kRlNoRay) {
+                    valid4 |= 1u << j;
+                    if (ray_trusted(sc, r[h], dd)) trust4 |= 1u << j;
+                    else if (ray_has_nan(r[h])) nan4 |= 1u << j;
+                }
                 sh.ro[j][tid] = make_float4(r[h].o.x, r[h].o.y, r[h].o.z, __uint_as_float(rl_pack_ray_meta(r[h].face, r[h].ex_prim, r[h].ex_face)));
                 sh.rd[j][tid] = make_float4(r[h].d.x, r[h].d.y, r[h].d.z, __uint_as_float(tag));
                 Best b0;
@@ -271,20 +323,47 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
             dz[k] = p2_mul(p2_pack(r[0].d.z, r[1].d.z), one2);
             cf[k] = p2_mul(p2_pack(c[0], c[1]), one2);
         }
+        const bool warp_valid = __any_sync(kFullMask, valid4 != 0u);
 #pragma unroll 1
         for (uint32_t tile = 0; tile < n_tiles; ++tile) {
             const uint32_t buf = tile & 1u;
             if (buf == 0u) { rl_mbar_wait(&sh.bar[0], parity0); parity0 ^= 1u; }
             else           { rl_mbar_wait(&sh.bar[1], parity1); parity1 ^= 1u; }
             const float4* __restrict__ recs = sh.tile[buf];
-            if (valid4) {                                           // (warp-uniform up to the tail of the last block)
+            if (warp_valid) {                                       // warp-uniform: lanes without rays filter a dummy ray
                 uint32_t keep[4][2];
                 rl_filter_tile(recs, ox, oy, oz, dx, dy, dz, cf, A2, g, keep);
-                // phase 2 of this tile, for the rays that have candidates in it (untrusted rays: every triangle)
+                // untrusted rays without NaNs: the whole warp tests the tile for each of them (rl_coop_exact_tile)
+                const uint32_t coop4 = valid4 & ~trust4 & ~nan4;
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    unsigned owners = __ballot_sync(kFullMask, (coop4 >> j) & 1u);
+#pragma unroll 1
+                    while (owners) {
+                        const int l = __ffs((int)owners) - 1;
+                        owners &= owners - 1u;
+                        // the owner's ray and nearest-so-far, from its shared-memory slots
+                        const uint32_t ot = (tid & ~31u) + (uint32_t)l;
+                        const float4 a = sh.ro[j][ot], b = sh.rd[j][ot];
+                        const uint32_t meta = __float_as_uint(a.w);
+                        DRay r;
+                        r.o = mk3(a); r.d = mk3(b);
+                        r.face = meta & 3u; r.ex_face = (meta >> 2) & 3u; r.ex_prim = (int32_t)(meta >> 4) - 1;
+                        Best cur;
+                        rl_best_load(sh, j, ot, r, cur);
+                        bool bvalid = cur.prim >= 0, changed = false;
+                        float bt = cur.t;
+                        Best winner = cur;
+                        rl_coop_exact_tile(sc, tile, r, lane, bvalid, bt, winner, changed, cs);
+                        if (changed && lane == (uint32_t)l) rl_best_store(sh, j, tid, winner);
+                        __syncwarp();
+                    }
+                }
+                // phase 2 of this tile, for the trusted rays that have candidates in it
                 uint32_t todo4 = 0u;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (((valid4 >> j) & 1u) && ((keep[j][0] | keep[j][1]) != 0u || !((trust4 >> j) & 1u))) todo4 |= 1u << j;
+                    if (((valid4 & trust4) >> j) & 1u) { if ((keep[j][0] | keep[j][1]) != 0u) todo4 |= 1u << j; }
                 if (todo4) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) sh.mk[j][tid] = make_uint2(keep[j][0], keep[j][1]);
@@ -324,6 +403,13 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
             const bool trust = ray_trusted(sc, r, dd);
             Best best;
             rl_best_load(sh, j, tid, r, best);
+            if ((nan4 >> j) & 1u) cast_nan_ray_triangles(sc, r, best, cs);
+#ifdef RL_DIAG_UNTRUSTED   // diagnostics build: untrusted rays (every pair through the exact test) in bits 40.. of the fallback counter
+            if (!trust) {
+                const float oo = r.o.x * r.o.x + r.o.y * r.o.y + r.o.z * r.o.z;
+                cs.fallbacks += ray_has_nan(r) ? 0ull : (!(oo <= sc.origin_bound * sc.origin_bound) ? (1ull << 40) : (1ull << 52));
+            }
+#endif
             cast_spheres(sc, r, trust, dd, best);
             DHit h;
             h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;

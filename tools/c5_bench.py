@@ -29,3 +29,6 @@ print(f"  samples {s['samples']} casts {s['casts']} pair tests {s['tri_pair_test
 print(f"  {s['samples'] / s['kernel_ms'] / 1e3:.2f} Mrays/s (one GPU, one band)  {(s['tri_pair_tests'] + s['sph_pair_tests']) / s['kernel_ms'] / 1e6:.1f} Gpairs/s  "
       f"{flops / (s['kernel_ms'] * 1e-3) / 1e12:.2f} TFLOP/s algorithmic = {100 * flops / (s['kernel_ms'] * 1e-3) / peak:.1f} % of the FP32 roofline; "
       f"exact tests / cast {s['exact_confirms'] / max(s['casts'], 1):.2f}")
+if os.environ.get("B200RT_LIB", "").endswith("diag.so"):
+    fb = s['certify_fallbacks']
+    print(f"  untrusted finite rays: origin beyond the bound {(fb >> 40) & 0xfff}, |dir|^2 off {fb >> 52}, of {s['casts']} casts; certify fallbacks {fb & ((1 << 40) - 1)}")
