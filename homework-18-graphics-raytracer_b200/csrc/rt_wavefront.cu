@@ -449,7 +449,15 @@ __global__ void __launch_bounds__(128, WF_OWNER_MIN_BLOCKS) wf_owner_kernel(cons
 #ifndef WF_FUSED_SHADE_THREADS
 #define WF_FUSED_SHADE_THREADS 256
 #endif
+#ifndef WF_PRIMARY_MIN_BLOCKS
+#define WF_PRIMARY_MIN_BLOCKS 3
+#endif
+#ifndef WF_FUSED_BOUNCE_MIN_BLOCKS
+#define WF_FUSED_BOUNCE_MIN_BLOCKS 3
+#endif
 template <int SEG, bool FUSED = false> struct LogicCfg { static constexpr int kMinBlocks = 3, kThreads = 256; };
+template <> struct LogicCfg<WF_SEG_PRIMARY, false> { static constexpr int kMinBlocks = WF_PRIMARY_MIN_BLOCKS, kThreads = 256; };
+template <> struct LogicCfg<WF_SEG_BOUNCE, true> { static constexpr int kMinBlocks = WF_FUSED_BOUNCE_MIN_BLOCKS, kThreads = 256; };
 template <> struct LogicCfg<WF_SEG_INIT, false> { static constexpr int kMinBlocks = 4, kThreads = 256; };
 template <> struct LogicCfg<WF_SEG_REFR, false> { static constexpr int kMinBlocks = 4, kThreads = 256; };
 // shade + arrival + next level in one pass
