@@ -65,6 +65,44 @@ def test_ragged_triangle_counts(b200rt, oracle):
         ctx.close()
 
 
+def test_multi_tile_rays_outside_the_filter_assumptions(b200rt, oracle, mesh_ctx):
+    """NaN components (the walk ends with the last admissible triangle: cast_nan_ray_triangles), origins at infinity /
+    beyond the packed bound and non-unit directions (the warp tests the tile together and folds the nearest-so-far rule
+    in index order: rl_coop_exact_tile), mixed with ordinary rays in the same warps, on a 51-tile scene: ids, faces and
+    distances as the reference's ordered walk over every triangle, through both cast kernels."""
+    ctx, world, ntri = mesh_ctx
+    n = 4096
+    rays = random_rays(b200rt, n, 7)
+    rng = np.random.default_rng(8)
+    kind = rng.integers(0, 8, size=n)                        # 0..3 ordinary
+    o, d = rays["origin"].copy(), rays["direction"].copy()
+    sel = kind == 4; o[sel, rng.integers(0, 3, size=sel.sum())] = np.nan
+    sel = kind == 5; d[sel, rng.integers(0, 3, size=sel.sum())] = np.nan
+    sel = kind == 6                                           # origin at +-inf on one axis, or merely far away
+    ax = rng.integers(0, 3, size=sel.sum())
+    far = np.where(rng.random(sel.sum()) < 0.5, 3e4, -3e4)
+    o[sel, ax] = np.where(rng.random(sel.sum()) < 0.7, np.where(far > 0, np.inf, -np.inf), far)
+    sel = kind == 7; d[sel] *= rng.uniform(0.2, 5.0, size=(sel.sum(), 1)).astype(np.float32)   # |dir| != 1
+    rays["origin"], rays["direction"] = o, d
+    ob = oracle.intersect(world.scene(), rays)
+    for mode in ("rl", "transposed"):
+        import os
+        if mode == "transposed":
+            os.environ["B200RT_INTERSECT"] = "transposed"
+        try:
+            g = ctx.intersect(rays, b200rt.CAST_TWO_PHASE)
+        finally:
+            os.environ.pop("B200RT_INTERSECT", None)
+        assert np.array_equal(g["prim_id"], ob["prim_id"]), (mode, int((g["prim_id"] != ob["prim_id"]).sum()))
+        hit = ob["prim_id"] >= 0
+        assert np.array_equal(g["face_direction"][hit], ob["face_direction"][hit]), mode
+        gd, od = g["distance"][hit], ob["distance"][hit]
+        assert np.array_equal(np.isnan(gd), np.isnan(od)), mode
+        fin = ~np.isnan(od)
+        assert np.array_equal(gd[fin].view(np.uint32), od[fin].view(np.uint32)), mode
+    assert (kind >= 4).sum() > 1500 and (ob["prim_id"][kind >= 4] >= 0).sum() > 100    # the odd rays do "hit" things
+
+
 def test_degenerate_and_far_inputs_bypass_the_filter(b200rt, oracle):
     """Zero-area triangles (NaN normal in the reference), rays far outside the packed origin bound, non-unit and
     non-finite directions: the conservative filter must hand all of them to the exact test."""
