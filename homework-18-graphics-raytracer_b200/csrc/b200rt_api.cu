@@ -268,7 +268,6 @@ int b200rt_destroy(b200rt_ctx* ctx) {
     if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
     if (ctx->ev_poll) cudaEventDestroy(ctx->ev_poll);
     for (cudaEvent_t ev : ctx->wf_timing.pool) cudaEventDestroy(ev);
-    for (cudaEvent_t ev : ctx->wf_timing.pool_mid) cudaEventDestroy(ev);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);

@@ -138,6 +138,43 @@ struct PathMem {
     }
 };
 
+// The cast work of one round: ONE LIST PER RAY SLOT (0 = the path rays, s = the shadow rays of light slot s - 1), so
+// that a warp of the cast kernels carries rays of one kind (shadow rays of one light are coherent and cull the same
+// triangles; only path rays need hit attributes) and the shading kernels append with coalesced stores.  The cast
+// kernels walk a virtual index space in which every list is padded to whole 128-ray blocks.
+struct WfWork {
+    const uint32_t* __restrict__ lists;   // [WF_WORK_PER_PATH][n]
+    uint32_t n;
+    uint32_t count[WF_WORK_PER_PATH];
+    uint32_t first_block[WF_WORK_PER_PATH + 1];
+    RT_DI uint32_t n_virtual() const { return first_block[WF_WORK_PER_PATH] * 128u; }
+    RT_DI uint32_t n_real() const { return count[0] + count[1] + count[2] + count[3] + count[4]; }
+    // (path << 3 | slot) of virtual index v, or 0xffffffff for the padding of a list
+    RT_DI uint32_t item(uint32_t v) const {
+        const uint32_t block = v >> 7;
+        const uint32_t k = (block >= first_block[1] ? 1u : 0u) + (block >= first_block[2] ? 1u : 0u) +
+                           (block >= first_block[3] ? 1u : 0u) + (block >= first_block[4] ? 1u : 0u);
+        const uint32_t fb = k == 0u ? first_block[0] : k == 1u ? first_block[1] : k == 2u ? first_block[2] : k == 3u ? first_block[3] : first_block[4];
+        const uint32_t cn = k == 0u ? count[0] : k == 1u ? count[1] : k == 2u ? count[2] : k == 3u ? count[3] : count[4];
+        const uint32_t i = v - fb * 128u;
+        return i < cn ? (lists[(size_t)k * n + i] << 3) | k : 0xffffffffu;
+    }
+};
+RT_DI WfWork wf_work(const WfBuffers& wb, uint32_t buf) {
+    WfWork w;
+    w.lists = wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n;
+    w.n = wb.n;
+    uint32_t fb = 0u;
+#pragma unroll
+    for (uint32_t k = 0; k < WF_WORK_PER_PATH; ++k) {
+        w.count[k] = wb.ctl->c[buf].work[k];
+        w.first_block[k] = fb;
+        fb += (w.count[k] + 127u) >> 7;
+    }
+    w.first_block[WF_WORK_PER_PATH] = fb;
+    return w;
+}
+
 }  // namespace
 
 // ---- cast --------------------------------------------------------------------------------------------------
@@ -154,8 +191,9 @@ __global__ void __launch_bounds__(128, WF_CAST_MIN_BLOCKS) wf_cast_kernel(const 
     float4* s_rays = s_rays_all[warp];
     // the counters the logic kernel of this round appends to
     if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
-    const uint32_t n_work = wb.ctl->c[buf].work;
-    if (n_work == 0u) return;
+    const WfWork wk = wf_work(wb, buf);
+    const uint32_t n_real = wk.n_real(), n_work = wk.n_virtual();
+    if (n_real == 0u) return;
     TriPair tile0;
     if (sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
     else {
@@ -163,7 +201,6 @@ __global__ void __launch_bounds__(128, WF_CAST_MIN_BLOCKS) wf_cast_kernel(const 
         tile0.nx = tile0.ny = tile0.nz = tile0.d = tile0.m0x = tile0.m0y = tile0.m0z = tile0.w0 = tile0.m1x = tile0.m1y = tile0.m1z =
             tile0.w1 = tile0.m2x = tile0.m2y = tile0.m2z = tile0.w2 = z;
     }
-    const uint32_t* __restrict__ work = wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n;
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
     const uint32_t stride = gridDim.x * 4u * 32u;
@@ -171,9 +208,9 @@ __global__ void __launch_bounds__(128, WF_CAST_MIN_BLOCKS) wf_cast_kernel(const 
     // (a dependent chain work[] -> path -> ray rows of ~2 us that 4 warps per sub-partition cannot hide)
     auto fetch = [&](uint32_t idx, uint32_t& item, DRay& r) {
         r.o = mk3(0.f, 0.f, 0.f); r.d = mk3(0.f, 0.f, 1.f); r.face = kFront; r.ex_prim = -1; r.ex_face = kFront;
-        item = 0u;
-        if (idx < n_work) {
-            item = work[idx];
+        item = 0xffffffffu;                                  // padding of a work list: no ray
+        if (idx < n_work) item = wk.item(idx);
+        if (item != 0xffffffffu) {
             const PathMem pm{wb.st, wb.req, item >> 3};
             if ((item & 7u) == 0u) pm.get_ray(r);
             else pm.get_shadow_ray((item & 7u) - 1u, r);
@@ -184,7 +221,6 @@ __global__ void __launch_bounds__(128, WF_CAST_MIN_BLOCKS) wf_cast_kernel(const 
     DRay r_next;
     fetch(base + lane, item_next, r_next);
     for (; base < n_work; base += stride) {
-        const bool active = base + lane < n_work;
 #if WF_CAST_PREFETCH
         const uint32_t item = item_next;
         const DRay r = r_next;
@@ -194,6 +230,7 @@ __global__ void __launch_bounds__(128, WF_CAST_MIN_BLOCKS) wf_cast_kernel(const 
         DRay r;
         fetch(base + lane, item, r);
 #endif
+        const bool active = item != 0xffffffffu;
         const uint32_t pid = item >> 3, slot = item & 7u;
         DHit h;
         h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
@@ -218,9 +255,9 @@ __global__ void __launch_bounds__(128, WF_CAST_MIN_BLOCKS) wf_cast_kernel(const 
         if (lane == 0u && n_conf) atomicAdd(&cnt->confirms, n_conf);
         if (lane == 0u && n_fb) atomicAdd(&cnt->fallbacks, n_fb);
         if (blockIdx.x == 0 && threadIdx.x == 0) {
-            atomicAdd(&cnt->casts, (unsigned long long)n_work);
-            atomicAdd(&cnt->tri_pairs, (unsigned long long)n_work * sc.n_tris);
-            atomicAdd(&cnt->sph_pairs, (unsigned long long)n_work * sc.n_sph);
+            atomicAdd(&cnt->casts, (unsigned long long)n_real);
+            atomicAdd(&cnt->tri_pairs, (unsigned long long)n_real * sc.n_tris);
+            atomicAdd(&cnt->sph_pairs, (unsigned long long)n_real * sc.n_sph);
         }
     }
 }
@@ -239,16 +276,17 @@ RT_DI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" 
 namespace {
 struct WfRayIO {
     WfBuffers wb;
-    const uint32_t* __restrict__ work;
+    WfWork work;
     RT_DI bool load(uint32_t idx, DRay& r, uint32_t& tag) const {
-        const uint32_t item = work[idx];
+        const uint32_t item = work.item(idx);
+        if (item == 0xffffffffu) return false;
         const PathMem pm{wb.st, wb.req, item >> 3};
         if ((item & 7u) == 0u) pm.get_ray(r);
         else pm.get_shadow_ray((item & 7u) - 1u, r);
         tag = item;
         return true;
     }
-    RT_DI uint32_t peek(uint32_t idx) const { return work[idx]; }
+    RT_DI uint32_t peek(uint32_t idx) const { return work.item(idx); }
     RT_DI void prefetch(uint32_t item) const {
         const size_t pid = item >> 3;
         const uint32_t slot = item & 7u;
@@ -282,12 +320,13 @@ __global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_
     __shared__ RlShared sh;
     const uint32_t lane = threadIdx.x & 31u;
     if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
-    const uint32_t n_work = wb.ctl->c[buf].work;
+    const WfWork wk = wf_work(wb, buf);
+    const uint32_t n_work = wk.n_real();
     if (n_work == 0u) return;
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
-    const WfRayIO io{wb, wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n};
-    cast_rays_in_lanes<WF_CAST_RL_PREFETCH != 0>(sc, io, n_work, sh, cs);
+    const WfRayIO io{wb, wk};
+    cast_rays_in_lanes<WF_CAST_RL_PREFETCH != 0>(sc, io, wk.n_virtual(), sh, cs);
     if (cnt) {
         unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
 #pragma unroll
@@ -315,113 +354,13 @@ __global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_TILED_MIN_BLOCKS) wf_ca
     __shared__ RlTiledShared sh;
     const uint32_t lane = threadIdx.x & 31u;
     if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
-    const uint32_t n_work = wb.ctl->c[buf].work;
+    const WfWork wk = wf_work(wb, buf);
+    const uint32_t n_work = wk.n_real();
     if (n_work == 0u) return;
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
-    const WfRayIO io{wb, wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n};
-    cast_rays_in_lanes_tiled(sc, io, n_work, sh, cs);
-    if (cnt) {
-        unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
-            n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
-        }
-        if (lane == 0u && n_conf) atomicAdd(&cnt->confirms, n_conf);
-        if (lane == 0u && n_fb) atomicAdd(&cnt->fallbacks, n_fb);
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            atomicAdd(&cnt->casts, (unsigned long long)n_work);
-            atomicAdd(&cnt->tri_pairs, (unsigned long long)n_work * sc.n_tris);
-            atomicAdd(&cnt->sph_pairs, (unsigned long long)n_work * sc.n_sph);
-        }
-    }
-}
-
-// ---- cast, split in two kernels (scenes of <= kSplitMaxTiles tiles) ------------------------------------------------
-// wf_filter_kernel   phase 1 alone: the packed-FFMA2 filter loop for every ray of the round, nothing else.  Few
-//                    registers (the lane's triangle pair + two rays in flight), so 6 warps per sub-partition hide the
-//                    FFMA2 / MUFU dependency latencies that the fused kernel (4 warps, 128 registers) cannot: this is
-//                    the FP32-roofline kernel.  Output: the 64-bit candidate mask of every (ray, tile), 8 B per ray.
-// wf_owner_kernel    phase 2 for every ray: certified select + exact test, spheres, hit attributes.  Plain per-lane code.
-#ifndef WF_FILTER_MIN_BLOCKS
-#define WF_FILTER_MIN_BLOCKS 6
-#endif
-#ifndef WF_OWNER_MIN_BLOCKS
-#define WF_OWNER_MIN_BLOCKS 5
-#endif
-__global__ void __launch_bounds__(128, WF_FILTER_MIN_BLOCKS) wf_filter_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf) {
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    __shared__ float4 s_rays_all[4][kCastSlotFloat4];
-    float4* s_rays = s_rays_all[warp];
-    // the counters the logic kernels of this round append to
-    if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
-    const uint32_t n_work = wb.ctl->c[buf].work;
-    if (n_work == 0u) return;
-    TriPair tile0;
-    load_tripair(sc.tri_filter, 0, lane, tile0);
-    const uint32_t* __restrict__ work = wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n;
-    const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
-    const uint2* s_mask = cast_slot_masks(s_rays);
-    const uint32_t stride = gridDim.x * 4u * 32u;
-    for (uint32_t base = (blockIdx.x * 4u + warp) * 32u; base < n_work; base += stride) {
-        const uint32_t idx = base + lane;
-        const bool active = idx < n_work;
-        if (active) {
-            const uint32_t item = work[idx];
-            const PathMem pm{wb.st, wb.req, item >> 3};
-            DRay r;
-            if ((item & 7u) == 0u) pm.get_ray(r);
-            else pm.get_shadow_ray((item & 7u) - 1u, r);
-            stage_ray(s_rays, lane, r);
-        }
-        __syncwarp();
-        const uint32_t n_act = min(32u, n_work - base);
-        for (uint32_t tile = 0; tile < n_tiles; ++tile) {
-            TriPair c;
-            if (tile == 0) c = tile0; else load_tripair(sc.tri_filter, tile, lane, c);
-            filter_tile(sc, s_rays, c, n_act, lane);
-            __syncwarp();
-            if (active) wb.masks[(size_t)idx * n_tiles + tile] = s_mask[lane];
-            __syncwarp();
-        }
-    }
-}
-
-__global__ void __launch_bounds__(128, WF_OWNER_MIN_BLOCKS) wf_owner_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf,
-                                                                          DCounters* __restrict__ cnt) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_work = wb.ctl->c[buf].work;
-    const uint32_t* __restrict__ work = wb.work + (size_t)buf * WF_WORK_PER_PATH * wb.n;
-    const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
-    CastStats cs;
-    cs.casts = cs.confirms = cs.fallbacks = 0ull;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_work; idx += gridDim.x * blockDim.x) {
-        const uint32_t item = work[idx];
-        const uint32_t pid = item >> 3, slot = item & 7u;
-        const PathMem pm{wb.st, wb.req, pid};
-        DRay r;
-        if (slot == 0u) pm.get_ray(r);
-        else pm.get_shadow_ray(slot - 1u, r);
-        float dd;
-        const bool trust = ray_trusted(sc, r, dd);
-        Best best;
-        best_init(best);
-        for (uint32_t tile = 0; tile < n_tiles; ++tile)
-            confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, wb.masks[(size_t)idx * n_tiles + tile], trust), trust, r, best, cs,
-                         sc.tri_exact + 4 * (size_t)(tile * kTileTris));
-        cast_spheres(sc, r, trust, dd, best);
-        DHit h;
-        h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
-        finalize_hit(sc, best, h, slot == 0u);
-        if (slot == 0u) {
-            const uint32_t meta = h.prim >= 0 ? (h.face | (h.object << 8)) : 0u;
-            wb.res[(size_t)pid * 2u + 0u] = make_float4(__int_as_float(h.prim), u2f(meta), h.t, h.uv.x);
-            wb.res[(size_t)pid * 2u + 1u] = make_float4(h.normal.x, h.normal.y, h.normal.z, h.uv.y);
-        } else {
-            wb.sres[(size_t)pid * 4u + (slot - 1u)] = make_float2(__int_as_float(h.prim), h.t);
-        }
-    }
+    const WfRayIO io{wb, wk};
+    cast_rays_in_lanes_tiled(sc, io, wk.n_virtual(), sh, cs);
     if (cnt) {
         unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
 #pragma unroll
@@ -899,31 +838,31 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 pm.sv2(ROW_HDIR, make_float4(h_dir.x, h_dir.y, h_dir.z, h.uv.x), make_float4(h_dir_orig.x, h_dir_orig.y, h_dir_orig.z, h.uv.y));
             if (out == OUT_PRIMARY || out == OUT_BOUNCE || out == OUT_REFR || pre_ray) pm.template put_ray<kW>(ray);
         }
-        // ---- route: every reservation of this chunk (5 queues, the cast work list, the retired counter) is one
-        // atomic issued by a different lane, so the warp pays one round trip to L2 instead of seven
+        // ---- route: every reservation of this chunk (5 queues, the 5 cast work lists, the retired counter) is one
+        // atomic issued by a different lane, so the warp pays one round trip to L2 instead of eleven
         {
             const bool path_ray = out == OUT_PRIMARY || out == OUT_BOUNCE || out == OUT_REFR;
-            const uint32_t n_items = !valid ? 0u : (path_ray ? 1u : (out == OUT_SHADE ? n_shadow + (pre_ray ? 1u : 0u) : 0u));
-            uint32_t incl = n_items;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(kFullMask, incl, o);
-                if ((int)lane >= o) incl += v;
-            }
-            const uint32_t total = __shfl_sync(kFullMask, incl, 31);
+            const uint32_t need_out = (valid && out == OUT_SHADE) ? ((flags >> F_NEED_SHIFT) & 15u) : 0u;
             const int my_seg = out == OUT_PRIMARY ? WF_SEG_PRIMARY : out == OUT_BOUNCE ? WF_SEG_BOUNCE : out == OUT_REFR ? WF_SEG_REFR
                              : out == OUT_SHADE ? WF_SEG_SHADE : out == OUT_SHB ? WF_SEG_SHB : 0;   // 0 = none (INIT is never a target)
             unsigned m_seg[WF_SEG_COUNT];
 #pragma unroll
             for (int sgi = 1; sgi < WF_SEG_COUNT; ++sgi) m_seg[sgi] = __ballot_sync(kFullMask, valid && my_seg == sgi);
             const unsigned m_ret = __ballot_sync(kFullMask, valid && out == OUT_RETIRE);
+            // cast work: slot 0 = the path ray (also the one that travels with shadow rays), slots 1..4 = shadow rays
+            unsigned m_work[WF_WORK_PER_PATH];
+            m_work[0] = __ballot_sync(kFullMask, valid && (path_ray || (out == OUT_SHADE && pre_ray)));
+#pragma unroll
+            for (uint32_t sl = 0; sl < 4u; ++sl) m_work[sl + 1u] = __ballot_sync(kFullMask, ((need_out >> sl) & 1u) != 0u);
             uint32_t my_n = 0u;
             uint32_t* my_addr = nullptr;
 #pragma unroll
             for (int sgi = 1; sgi < WF_SEG_COUNT; ++sgi)
                 if ((int)lane == sgi) { my_n = (uint32_t)__popc(m_seg[sgi]); my_addr = &wb.ctl->c[nbuf].seg[sgi]; }
-            if (lane == 0u) { my_n = total; my_addr = &wb.ctl->c[nbuf].work; }
             if (lane == (uint32_t)WF_SEG_COUNT) { my_n = (uint32_t)__popc(m_ret); my_addr = &wb.ctl->retired; }
+#pragma unroll
+            for (uint32_t k = 0; k < WF_WORK_PER_PATH; ++k)
+                if (lane == 8u + k) { my_n = (uint32_t)__popc(m_work[k]); my_addr = &wb.ctl->c[nbuf].work[k]; }
             uint32_t my_base = 0u;
             if (my_n) my_base = atomicAdd(my_addr, my_n);
             uint32_t seg_base = 0u;
@@ -933,20 +872,14 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 const uint32_t bse = __shfl_sync(kFullMask, my_base, sgi);
                 if (my_seg == sgi) { seg_base = bse; seg_mask = m_seg[sgi]; }
             }
-            const uint32_t work_base = __shfl_sync(kFullMask, my_base, 0) + (incl - n_items);
+            const uint32_t lt = (1u << lane) - 1u;
             if (valid && my_seg != 0)
-                wb.q[((size_t)nbuf * WF_SEG_COUNT + my_seg) * wb.n + seg_base + (uint32_t)__popc(seg_mask & ((1u << lane) - 1u))] = pid;
+                wb.q[((size_t)nbuf * WF_SEG_COUNT + my_seg) * wb.n + seg_base + (uint32_t)__popc(seg_mask & lt)] = pid;
             uint32_t* w = wb.work + (size_t)nbuf * WF_WORK_PER_PATH * wb.n;
-            if (n_items) {
-                if (path_ray) w[work_base] = pid << 3;
-                else {
-                    const uint32_t need = (flags >> F_NEED_SHIFT) & 15u;
-                    uint32_t at = work_base;
-                    if (pre_ray) w[at++] = pid << 3;
 #pragma unroll
-                    for (uint32_t sl = 0; sl < 4u; ++sl)
-                        if ((need >> sl) & 1u) w[at++] = (pid << 3) | (sl + 1u);
-                }
+            for (uint32_t k = 0; k < WF_WORK_PER_PATH; ++k) {
+                const uint32_t bse = __shfl_sync(kFullMask, my_base, 8 + (int)k);
+                if ((m_work[k] >> lane) & 1u) w[(size_t)k * wb.n + bse + (uint32_t)__popc(m_work[k] & lt)] = pid;
             }
         }
     }
@@ -973,14 +906,8 @@ __global__ void wf_combine_kernel(const WfBuffers wb, const DParams p, float4* _
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
-// the candidate masks between wf_filter_kernel and wf_owner_kernel exist only in the (tuning) split-cast mode
-static bool wf_split_selected() {
-    const char* e = getenv("B200RT_WF_CAST");
-    return e && std::string(e) == "split";
-}
 size_t wf_workspace_bytes_per_path() {
-    return (size_t)kStateRows * 16 + WF_REQ_ROWS * 16 + 32 + 32 + 2 * WF_SEG_COUNT * 4 + 2 * WF_WORK_PER_PATH * 4 +
-           (wf_split_selected() ? WF_WORK_PER_PATH * WF_SPLIT_MAX_TILES * 8 : 0);
+    return (size_t)kStateRows * 16 + WF_REQ_ROWS * 16 + 32 + 32 + 2 * WF_SEG_COUNT * 4 + 2 * WF_WORK_PER_PATH * 4;
 }
 size_t wf_workspace_bytes(uint32_t n_paths) {
     return sizeof(WfControl) + 256 + (size_t)n_paths * wf_workspace_bytes_per_path() + 16 * 64;
@@ -1017,7 +944,6 @@ static WfBuffers wf_carve(void* workspace, uint32_t n_paths, uint32_t n_pixels, 
     wb.sres = reinterpret_cast<float2*>(b + off);              off = align(off + n * 32);
     wb.q = reinterpret_cast<uint32_t*>(b + off);               off = align(off + n * 2 * WF_SEG_COUNT * 4);
     wb.work = reinterpret_cast<uint32_t*>(b + off);            off = align(off + n * 2 * WF_WORK_PER_PATH * 4);
-    wb.masks = reinterpret_cast<uint2*>(b + off);              off = align(off + (wf_split_selected() ? n * WF_WORK_PER_PATH * WF_SPLIT_MAX_TILES * 8 : 0));
     wb.n = n_paths; wb.n_pixels = n_pixels; wb.epar = epar;
     return wb;
 }
@@ -1033,12 +959,11 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     const int cast_blocks = sm_count * WF_CAST_MIN_BLOCKS;
     // small scenes: phase 1 and phase 2 of the cast as two kernels (B200RT_WF_FUSED_CAST=1 keeps them fused: tuning)
     const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
-    // B200RT_WF_CAST = rl (default: rays in lanes, tiles by TMA for larger scenes) | fused (warp-transposed) | split : tuning / measurement
+    // B200RT_WF_CAST = rl (default: rays in lanes, tiles by TMA for larger scenes) | fused (warp-transposed): measurement
     const char* cast_env = getenv("B200RT_WF_CAST");
     const std::string cast_sel = cast_env ? cast_env : "";
     const bool rays_in_lanes = n_tiles == 1 && (cast_sel.empty() || cast_sel == "rl");
     const bool rays_in_lanes_tiled = n_tiles > 1 && (cast_sel.empty() || cast_sel == "rl");
-    const bool split = !rays_in_lanes && n_tiles >= 1 && n_tiles <= WF_SPLIT_MAX_TILES && cast_sel == "split";
     // fused levels (one light chunk): a hit's shadow rays and the next level's ray are cast in the same round, and one
     // kernel pass per level consumes both (B200RT_WF_FUSED_LEVELS=0: one pass per cast, as for scenes of > 4 lights)
     const char* fused_env = getenv("B200RT_WF_FUSED_LEVELS");
@@ -1060,12 +985,6 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                     if (e != cudaSuccess) return e;
                     timing->pool.push_back(ev);
                 }
-                while (timing->pool_mid.size() < (size_t)(round - first_round_of_group + 1)) {
-                    cudaEvent_t ev;
-                    e = cudaEventCreate(&ev);
-                    if (e != cudaSuccess) return e;
-                    timing->pool_mid.push_back(ev);
-                }
                 ev_a = timing->pool[2 * (round - first_round_of_group)];
                 ev_b = timing->pool[2 * (round - first_round_of_group) + 1];
                 cudaEventRecord(ev_a, stream);
@@ -1074,10 +993,6 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                 wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
             } else if (rays_in_lanes_tiled) {
                 wf_cast_rl_tiled_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
-            } else if (split) {
-                wf_filter_kernel<<<sm_count * WF_FILTER_MIN_BLOCKS, 128, 0, stream>>>(sc, wb, buf);
-                if (timing) cudaEventRecord(timing->pool_mid[round - first_round_of_group], stream);
-                wf_owner_kernel<<<sm_count * WF_OWNER_MIN_BLOCKS, 128, 0, stream>>>(sc, wb, buf, d_cnt);
             } else {
                 wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
             }
@@ -1106,10 +1021,6 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                 cudaEventElapsedTime(&ms, timing->pool[2 * g], timing->pool[2 * g + 1]);
                 timing->cast_ms += ms;
                 timing->cast_launches += 1;
-                if (split) {
-                    cudaEventElapsedTime(&ms, timing->pool[2 * g], timing->pool_mid[g]);
-                    timing->filter_ms += ms;
-                }
                 if (g + 1 < round - first_round_of_group) {       // cast end -> next cast start = the logic kernels of the round
                     cudaEventElapsedTime(&ms, timing->pool[2 * g + 1], timing->pool[2 * g + 2]);
                     timing->logic_ms += ms;
@@ -1122,7 +1033,7 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     }
     wf_combine_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(wb, p, reinterpret_cast<float4*>(d_accum));
     if (rounds_out) *rounds_out = round;
-    if (launches_out) *launches_out += 2u + round * ((p.depth <= 0 ? 6u : 5u) + (split ? 1u : 0u));
+    if (launches_out) *launches_out += 2u + round * ((p.depth <= 0 ? 6u : 5u));
     return cudaGetLastError();
 }
 

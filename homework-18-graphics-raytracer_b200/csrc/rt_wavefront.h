@@ -22,8 +22,8 @@ enum : int {
 
 struct WfCounters {          // per round parity
     uint32_t seg[8];         // queue length per segment
-    uint32_t work;           // cast work items
-    uint32_t pad[7];
+    uint32_t work[5];        // cast work items per ray slot (0 = path ray, 1..4 = shadow ray of light slot s - 1)
+    uint32_t pad[3];
 };
 struct WfControl {
     WfCounters c[2];
@@ -32,7 +32,6 @@ struct WfControl {
 };
 
 constexpr int WF_STATE_ROWS = 12;   // float4 rows of path state (192 B = 6 sectors)
-constexpr int WF_SPLIT_MAX_TILES = 2;  // scenes of up to 128 triangles run the cast as filter kernel + owner kernel
 constexpr uint32_t WF_WORK_PER_PATH = 5u;   // cast items a path can request in one round: its path ray + 4 shadow rays
 constexpr int WF_REQ_ROWS = 6;      // path ray (2) + 4 shadow directions (96 B = 3 sectors)
 #ifndef WF_LOGIC_MIN_BLOCKS
@@ -46,15 +45,14 @@ struct WfBuffers {
     float4* res;             // [n][2]
     float2* sres;            // [n][4]
     uint32_t* q;             // [2][WF_SEG_COUNT][n]
-    uint32_t* work;          // [2][WF_WORK_PER_PATH n]
-    uint2* masks;            // [WF_WORK_PER_PATH n][n_tiles] candidate masks between wf_filter_kernel and wf_owner_kernel
+    uint32_t* work;          // [2][WF_WORK_PER_PATH][n]: one list of path ids per ray slot
     uint32_t n, n_pixels, epar;
 };
 
 // Per-kernel device times of a wavefront render (filled when the caller asks for them): CUDA events on the
 // launching stream around every wf_cast_kernel launch.
 struct WfKernelTiming {
-    std::vector<cudaEvent_t> pool, pool_mid;
+    std::vector<cudaEvent_t> pool;
     double cast_ms = 0.0, logic_ms = 0.0, filter_ms = 0.0;
     uint64_t cast_launches = 0;
 };
