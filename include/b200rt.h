@@ -183,11 +183,11 @@ typedef struct b200rt_stats {
     uint32_t wavefront_rounds;     /* cast + shading rounds of the last wavefront render        */
     uint64_t certify_fallbacks;    /* casts whose certified select fell back to the ordered walk */
     /* only with b200rt_set_kernel_timing(ctx, 1): device time of the last wavefront render split by kernel */
-    float cast_kernel_ms;          /* sum over the cast launches (World::cast): filter + owner, or the fused kernel */
+    float cast_kernel_ms;          /* sum over the cast launches (World::cast)                    */
     float logic_kernel_ms;         /* sum over the shading / scatter kernels between them         */
     uint32_t cast_kernel_launches;
     uint32_t kernel_launches;      /* kernels launched by the last render call (always counted) */
-    float filter_kernel_ms;        /* of cast_kernel_ms: the wf_filter_kernel launches (0 when the cast runs fused) */
+    float filter_kernel_ms;        /* always 0 (the split filter / owner cast of round 1 was removed; kept for layout) */
     uint32_t reserved;
 } b200rt_stats;
 

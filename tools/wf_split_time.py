@@ -15,5 +15,5 @@ s = ctx.stats()
 flops = s["tri_pair_tests"] * 36.0 + s["sph_pair_tests"] * 28.0
 peak = 148 * 128 * 2 * 1.965e9
 print(os.environ.get("B200RT_LIB", "default"), os.environ.get("B200RT_WF_CAST", "default"),
-      f"total {s['kernel_ms']:.1f} cast {s['cast_kernel_ms']:.1f} filter {s['filter_kernel_ms']:.1f} owner {s['cast_kernel_ms'] - s['filter_kernel_ms']:.1f} logic {s['logic_kernel_ms']:.1f}",
-      f"| filter roofline {flops / (s['filter_kernel_ms'] * 1e-3) / peak if s['filter_kernel_ms'] else 0:.3f} cast roofline {flops / (s['cast_kernel_ms'] * 1e-3) / peak:.3f}", flush=True)
+      f"total {s['kernel_ms']:.1f} cast {s['cast_kernel_ms']:.1f} logic {s['logic_kernel_ms']:.1f}",
+      f"| cast roofline {flops / (s['cast_kernel_ms'] * 1e-3) / peak:.3f}", flush=True)
