@@ -2,13 +2,15 @@
 // main.rs:1129-1167) as a WAVEFRONT pipeline: every pixel sample is a path whose state lives in HBM, and the
 // frame advances in rounds of two kernels
 //
-//     wf_cast_kernel    World::cast (main.rs:180-326) for every ray requested in the previous round — the
-//                       warp-transposed FFMA2 filter + certified exact select of rt_cast.cuh with all 32
-//                       lanes of every warp carrying a ray (the FP32-roofline kernel of the render);
+//     wf_cast_rl_kernel World::cast (main.rs:180-326) for every ray requested in the previous round — the
+//      (_tiled / wf_cast_kernel)  packed-FFMA2 filter with rays in lanes (rt_cast_rl.cuh; tiles by TMA for scenes of
+//                       more than 64 triangles; warp-transposed alternative: rt_cast.cuh) + the certified exact
+//                       select, all 32 lanes of every warp carrying rays of one kind (the FP32-roofline kernel);
 //     wf_logic_kernel   everything between two casts (camera, get_shade, scatter, reflect / refract,
 //                       accumulation), run on queues that are binned by WHAT the finished cast was for
 //                       (primary / bounce / shadow rays / refraction step), so each warp executes one
-//                       branch of the reference's recursion with full lanes.
+//                       branch of the reference's recursion with full lanes.  With fused levels a hit's shadow
+//                       rays and the next level's ray travel in the same round (one pass per level).
 //
 // The per-path transitions are the same ones, in the same arithmetic, as the phase machine of rt_kernels.cu
 // (trace_kernel<kModeDistributed>): with one epoch in flight per pixel both tracers produce bit-identical
@@ -23,7 +25,7 @@
 //   res [n][2]   result of the path ray {prim, meta, t, uv.x}{normal, uv.y}             32 B
 //   sres[n][4]   float2 {prim, t} per shadow ray                                        32 B
 //   q   [2][6][n] path ids per consumer segment (double buffered by round parity)       48 B
-//   work[2][5n]  cast work items (path << 3 | slot): the path ray + up to 4 shadow rays  40 B
+//   work[2][5][n] cast work: one list of path ids per ray slot (path ray, 4 shadow rays)  40 B
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include <string>
