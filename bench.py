@@ -1,15 +1,17 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200 render core.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c1|c2|c3|c5]
 
 Workload (BASELINE.json): C4 — the reference's scene literal (main.rs:810-1083) at 3840x2160, thin-lens
 DoF + scatter tracer (main.rs:1129-1167), 256 epochs, depth 5, focus 3.0, blur 0.04, seed 0.  One "step"
-is the whole 256-epoch frame.  With N GPUs the epochs are split contiguously over the ranks (strong
-scaling: total work fixed) and the float4 {sum.rgb,count} accumulation buffers are summed with one NCCL
-all-reduce inside the timed region.  `value` = primary samples ("rays" in the reference's own print,
-main.rs:1169) per second over all ranks, in Mrays/s, with inputs resident in HBM.  `e2e` is the same
-through the host-buffer C-ABI entry point (pinned host accumulators, H2D + D2H inside the timed region).
+is the whole 256-epoch frame.  Every rank is one member of a device group of the C ABI (b200rt_group_*,
+include/b200rt.h): the library splits the epochs contiguously over the ranks (strong scaling: total work
+fixed) and sums the float4 {sum.rgb,count} accumulation buffers with one ncclReduce to rank 0 inside the
+timed region.  `value` = pixel samples per second over all ranks, in Mrays/s, with the scene resident in
+HBM and the frame left on rank 0's GPU.  `e2e` is the same through the host-buffer entry points (scene,
+camera, parameters in; the reduced frame out to a pinned host buffer on rank 0).  c1/c2/c3 are the Whitted
+frames (rows sharded), c5 the 100 352-triangle mesh with 10 M one-sample photons (rows sharded).
 
 --impl reference times the reference's CPU algorithm (the oracle port: the Rust crate cannot be built in
 this image) on all host cores, on a bounded sample of the same workload.
@@ -35,8 +37,13 @@ WORKLOADS = {
     "c1": ("C1 fixture scene 1280x960 Whitted depth 5, the reference's own frame (row-sharded)", 1280, 960, 5, 1, "whitted"),
     "c2": ("C2 fixture scene 1920x1080 Whitted depth 8 (row-sharded)", 1920, 1080, 8, 1, "whitted"),
     "c3": ("C3 fixture scene 3840x2160 Whitted depth 5 (row-sharded)", 3840, 2160, 5, 1, "whitted"),
+    "c5": ("C5 fixture scene + 100 352-triangle OBJ height field, 4000x2500 = 10 M one-sample photons, depth 5 (row-sharded)", 4000, 2500, 5, 1, "distributed"),
 }
 FLOP_TRI, FLOP_SPH = 36.0, 28.0   # algorithmic flop per ray x triangle / ray x sphere pair
+# "rays" = pixel samples GENERATED per second (width x height x epochs / time).  The reference's own print (main.rs:1169)
+# counts the samples it ACCEPTED (non-normal ones are dropped, main.rs:1157-1160: ~20 % on this scene); that figure is
+# reported beside it as accepted_samples_per_s.  Both arms use the same convention.
+METRIC = "Mrays/s (pixel samples generated per second; accepted samples, the reference's own 'rays/s' of main.rs:1169, beside it)"
 
 
 def measured_peaks():
@@ -116,31 +123,34 @@ def shard(total: int, rank: int, world: int):
 
 # --------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """The reference's CPU algorithm (oracle port) on all host cores; rank 0 only."""
+    """The reference's CPU algorithm (oracle port) on all host cores; rank 0 only.  The scene comes from
+    tests/golden/fixture_scene.npz: this arm loads oracle/liboracle.so and nothing of the product."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob      # bench.py's reference arm is one of the places allowed to run the oracle
-    b = ob.b
     desc, W, H, depth, epochs, tracer = WORKLOADS[args.workload]
-    world = b.World.fixture()
-    cam = b.fixture_camera()
-    cores = ob.max_threads()
+    fx = ob.GoldenFixture()
+    scene, cam = fx.scene, fx.camera
+    if args.workload == "c5":
+        print(json.dumps({"impl": "reference", "unavailable": "c5 needs the 100 352-triangle OBJ mesh through the product's importer; its CPU sample is bench.py's cpu_baseline leg"}), flush=True)
+        return 0
+    # torchrun exports OMP_NUM_THREADS=1: the thread count is passed explicitly (every core this process may use)
+    cores = ob.host_threads()
     # bounded sample: a band of rows through the middle of the frame x a few epochs, sized from a probe
     rows, ep = 32, 1
-    params = b.default_params(width=W, height=H, depth=depth, seed=0, row_begin=H // 2 - rows // 2, row_count=rows)
 
     def one(rows_, ep_):
-        p = b.copy_params(params, row_begin=H // 2 - rows_ // 2, row_count=rows_)
+        p = fx.params(width=W, height=H, depth=depth, seed=0, row_begin=H // 2 - rows_ // 2, row_count=rows_)
         t0 = time.perf_counter()
         if tracer == "distributed":
-            ob.render_distributed(world.scene(), cam, p, 0, ep_)
+            _, cnt = ob.render_distributed(scene, cam, p, 0, ep_, n_threads=cores)
         else:
-            ob.render_whitted(world.scene(), cam, p)
-        return time.perf_counter() - t0
+            _, _, cnt = ob.render_whitted(scene, cam, p, n_threads=cores)
+        return time.perf_counter() - t0, cnt["samples"]
 
-    t_probe = one(rows, ep)
+    t_probe, _ = one(rows, ep)
     target_s = 8.0   # per step; (warmup + steps) * target stays within a few minutes
     scale = max(1.0, target_s / max(t_probe, 1e-3))
     if tracer == "distributed":
@@ -150,17 +160,19 @@ def run_reference(args):
         rows = int(min(H, max(32, round(rows * scale))))
     for _ in range(args.warmup):
         one(rows, ep)
-    ts = [one(rows, ep) for _ in range(args.steps)]
+    runs = [one(rows, ep) for _ in range(args.steps)]
     samples = rows * W * ep
-    t = sum(ts) / len(ts)
+    t = sum(r[0] for r in runs) / len(runs)
+    accepted = runs[-1][1]
     v = samples / t / 1e6
     sample = f"rows [{H // 2 - rows // 2},{H // 2 - rows // 2 + rows}) x {ep} epoch(s) of {desc}: {samples} samples/step"
     line = {
-        "impl": "reference", "metric": "Mrays/s (primary samples/s, the reference's own 'rays/s', main.rs:1169)",
+        "impl": "reference", "metric": METRIC,
         "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": desc, "width": W, "height": H, "depth": depth, "epochs": epochs,
                                         "sample": sample},
+        "accepted_samples_per_s": accepted / t / 1e6 if tracer == "distributed" else v,
         "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C++ restatement of the reference CPU algorithm (the Rust crate cannot be built here: no rustc/cargo)",
@@ -187,114 +199,122 @@ def run_b200(args):
                                 device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    root = rank == 0
 
     desc, W, H, depth, epochs, tracer = WORKLOADS[args.workload]
     if args.width: W = args.width
     if args.height: H = args.height
     if args.epochs: epochs = args.epochs
     reduced = bool(args.width or args.height or args.epochs)
+    by_rows = args.workload == "c5"     # one epoch: the frame is split by rows; C4 splits its 256 epochs
 
-    ctx = b.Context(local_rank)          # raises without a GPU: there is no CPU fallback
-    scene_world = b.World.fixture()
-    ctx.upload_scene(scene_world)
+    # ---- the scene ------------------------------------------------------------------------------------------------
+    if args.workload == "c5":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from scene_util import fixture_plus_mesh
+        tmp = tempfile.mkdtemp(prefix="b200rt_c5_")
+        scene_world, _ = fixture_plus_mesh(b, tmp, 225)      # fixture scene + the 100 352-triangle OBJ height field
+    else:
+        scene_world = b.World.fixture()
+    sc = scene_world.scene()
+    scene_bytes = (sc.n_triangles * ctypes.sizeof(b.Triangle) + sc.n_spheres * ctypes.sizeof(b.Sphere) +
+                   sc.n_materials * ctypes.sizeof(b.Material) + sc.n_lights * ctypes.sizeof(b.Light))
     cam = b.fixture_camera()
     tracer_id = b.TRACER_WAVEFRONT if args.tracer == "wavefront" else b.TRACER_MEGAKERNEL
     params = b.default_params(width=W, height=H, depth=depth, seed=0, tracer=tracer_id)
-    # every launch, copy, collective and timing event of the bench goes on this one stream
-    tstream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
+
+    # ---- the device group: one rank per process, NCCL inside the library (include/b200rt.h, "device groups") -------------
+    # The id of the NCCL communicator is made on rank 0 and handed to the other ranks (here: a torch broadcast).
+    uid = None
+    if world_size > 1:
+        t = torch.zeros(b.GROUP_ID_BYTES, dtype=torch.uint8, device=dev)
+        if root:
+            t.copy_(torch.frombuffer(bytearray(b.Group.unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        uid = bytes(t.cpu().numpy().tobytes())
+    group = b.Group.rank(local_rank, rank, world_size, uid)     # raises without a GPU: there is no CPU fallback
+    group.upload_scene(scene_world)
+    ctx = group.member(0)
 
     if tracer == "distributed":
-        e0, en = shard(epochs, rank, world_size)
-        d_accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
-        h_accum = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory()
+        d_accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev) if root else None
+        h_accum = torch.zeros((H, W, 4), dtype=torch.float32).pin_memory() if root else None
         samples_total = W * H * epochs
 
         def step_device():
-            d_accum.zero_()
-            ctx.render_distributed_device(cam, params, e0, en, d_accum.data_ptr(), stream)
-            if world_size > 1:
-                dist.all_reduce(d_accum, op=dist.ReduceOp.SUM)
+            group.render_distributed_device(cam, params, 0, epochs, d_accum.data_ptr() if root else 0, by_rows=by_rows)
+            return group.last_render_ms()
 
         def step_e2e():
-            h_accum.zero_()
-            if world_size == 1:
-                # host-buffer C-ABI entry: pinned accumulators travel H2D, are added to, and travel back
-                ctx.render_distributed(cam, params, e0, en, h_accum.numpy())
-            else:
-                # N > 1: the ranks' accumulators are summed on the devices, so the caller does the copies around the
-                # device-pointer entry of the same C ABI: pinned H2D, render, all-reduce, D2H of the reduced image
-                d_accum.copy_(h_accum, non_blocking=True)
-                ctx.render_distributed_device(cam, params, e0, en, d_accum.data_ptr(), stream)
-                dist.all_reduce(d_accum, op=dist.ReduceOp.SUM)
-                h_accum.copy_(d_accum, non_blocking=True)
-                torch.cuda.synchronize()
-            return float(h_accum[H // 2, W // 2, 3])
+            # the call a user makes: scene + camera + parameters in (host), the reduced frame out (pinned host buffer on
+            # rank 0).  The accumulators of a fresh frame start at zero ON the devices: nothing else travels H2D.
+            group.upload_scene(scene_world)
+            group.render_distributed(cam, params, 0, epochs, h_accum.numpy() if root else None, by_rows=by_rows)
+            return float(h_accum[H // 2, W // 2, 3]) if root else 0.0
 
-        h2d = d2h = W * H * 16
-        launches_per_step = 1
+        h2d, d2h = scene_bytes + ctypes.sizeof(b.Camera) + ctypes.sizeof(b.Params), W * H * 16
     else:
-        r0, rn = shard(H, rank, world_size)
-        p_rank = b.copy_params(params, row_begin=r0, row_count=rn)
-        d_rgb = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
-        h_rgb = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory()
+        d_rgb = torch.zeros((H, W, 3), dtype=torch.float32, device=dev) if root else None
+        h_rgb = torch.zeros((H, W, 3), dtype=torch.float32).pin_memory() if root else None
         samples_total = W * H
 
         def step_device():
-            ctx.render_whitted_device(cam, p_rank, d_rgb.data_ptr(), 0, stream)
-            if world_size > 1:
-                dist.all_reduce(d_rgb, op=dist.ReduceOp.SUM)   # disjoint rows: sum == gather
+            group.render_whitted_device(cam, params, d_rgb.data_ptr() if root else 0)
+            return group.last_render_ms()
 
         def step_e2e():
-            ctx.render_whitted(cam, p_rank, out_rgb=h_rgb.numpy(), want_prim_id=False)
-            return float(h_rgb[r0, W // 2, 0])
+            group.upload_scene(scene_world)
+            group.render_whitted(cam, params, out_rgb=h_rgb.numpy() if root else None, want_prim_id=False)
+            return float(h_rgb[H // 2, W // 2, 0]) if root else 0.0
 
-        h2d, d2h = 0, rn * W * 12
-        launches_per_step = 1
+        h2d, d2h = scene_bytes + ctypes.sizeof(b.Camera) + ctypes.sizeof(b.Params), W * H * 12
 
     def barrier():
         if world_size > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing ----------------------------------------------------------------------------
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing: CUDA events on the launching stream around render + collective, inside the library ------
     for _ in range(args.warmup):
         step_device()
     barrier()
     ctx.reset_stats()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if root else None
     if sampler: sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
     barrier()
-    ev0.record()
+    t0 = time.perf_counter()
+    ms_total = 0.0
     for _ in range(args.steps):
-        step_device()
-    ev1.record()
+        ms_total += step_device()
     barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if sampler else None
-    ms_total = ev0.elapsed_time(ev1)
     st = ctx.stats()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = max_over_ranks(ms_total)
+    wall_ms = max_over_ranks(wall_ms)
     ms_per_step = ms_total / args.steps
     value = samples_total / (ms_per_step * 1e-3) / 1e6
+    accepted = torch.tensor([float(st["samples"]) / args.steps], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(accepted, op=dist.ReduceOp.SUM)
+    accepted = float(accepted.item())
 
     # per-launch duration of the dominant kernel, measured live with CUDA events on the launching stream.
-    #  * wavefront: the dominant kernel is wf_cast_kernel (World::cast for every ray of a round); the library brackets
+    #  * wavefront: the dominant kernel is the cast kernel (World::cast for every ray of a round); the library brackets
     #    each of its launches with events (b200rt_set_kernel_timing) during one extra step;
     #  * megakernel / Whitted: one trace_kernel launch per step.
     barrier()
-    cast_launches = 0
     logic_ms = None
     wavefront = tracer == "distributed" and args.tracer == "wavefront"
     if wavefront:
         ctx.set_kernel_timing(True)
-        d_accum.zero_()
-        ctx.render_distributed_device(cam, params, e0, en, d_accum.data_ptr(), stream)
+        step_device()
         barrier()
         kst = ctx.stats()
         ctx.set_kernel_timing(False)
@@ -305,25 +325,14 @@ def run_b200(args):
         launches_per_step = kst["kernel_launches"]
         step_kernel_ms = kst["kernel_ms"]
     else:
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for a, c in kev:
-            if tracer == "distributed":
-                d_accum.zero_()
-                a.record()
-                ctx.render_distributed_device(cam, params, e0, en, d_accum.data_ptr(), stream)
-                c.record()
-            else:
-                a.record()
-                ctx.render_whitted_device(cam, p_rank, d_rgb.data_ptr(), 0, stream)
-                c.record()
+        step_device()
         barrier()
-        kernel_ms = [a.elapsed_time(c) for a, c in kev]
-        k_ms = sum(kernel_ms) / len(kernel_ms)
-        k_ms_total = k_ms
+        kst = ctx.stats()
+        k_ms = k_ms_total = step_kernel_ms = kst["kernel_ms"]
         cast_launches = 1
-        step_kernel_ms = k_ms
+        launches_per_step = 1
 
-    # ---- end-to-end through the host-buffer C ABI --------------------------------------------------------------
+    # ---- end-to-end through the host-buffer C ABI: wall clock around the call a user makes -----------------------------
     e2e_steps = max(1, min(args.steps, 3))
     step_e2e()
     barrier()
@@ -331,14 +340,10 @@ def run_b200(args):
     for _ in range(e2e_steps):
         step_e2e()
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
     e2e_value = samples_total / (e2e_ms * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (this rank's launch) -----------------------------------------------------
+    # ---- roofline of the dominant kernel (this rank's launches) ---------------------------------------------------------
     peaks, peak_src = measured_peaks()
     info = ctx.device_info()
     sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
@@ -348,21 +353,23 @@ def run_b200(args):
     flops = tri_pairs * FLOP_TRI + sph_pairs * FLOP_SPH          # algorithmic flop of one step on this rank
     achieved = flops / (k_ms_total * 1e-3) / 1e12                # ... over the device time of the dominant kernel's launches
     live_peak, live_mhz = ctx.measure_fp32_peak()
-    # scenes of one 64-triangle tile run the rays-in-lanes cast kernel (rt_wavefront.cu), larger ones the warp-transposed one
-    kname = (("wf_cast_rl_kernel" if scene_world.scene().n_triangles <= 64 else "wf_cast_kernel") if wavefront
+    # scenes of one 64-triangle tile run the rays-in-lanes cast kernel (rt_wavefront.cu), larger ones its tiled (TMA) form
+    kname = (("wf_cast_rl_kernel" if sc.n_triangles <= 64 else "wf_cast_rl_tiled_kernel") if wavefront
              else f"trace_kernel<{tracer}>")
-    # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload only)
-    traffic = None
+    # DRAM bytes per launch of the dominant kernel: NOT measured by this run - the figure of the committed ncu capture of
+    # the same command line (profiles/r2_traffic.json), reported with its source
+    traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if wavefront and not (args.width or args.height) and world_size == 1 and kname in tj:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        if wavefront and not reduced and world_size == 1 and kname in tj:
             traffic = tj[kname]["dram_bytes_per_launch"]
+            traffic_src = "profiles/r2_traffic.json: " + tj[kname].get("source", "ncu capture")
     except Exception:
         traffic = None
     n_l = max(cast_launches, 1)
     roofline = {
         "bound": "fp32", "kernel": kname, "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved / peak_tflops, "traffic": traffic,
+        "frac": achieved / peak_tflops, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": f"SMs({info['sm_count']}) x 128 lanes x 2 flop x sm_max_mhz({sm_max_mhz:.0f}, {peak_src} MEASURED_PEAKS.json)",
         "ffma_loop_tflops_live": live_peak, "frac_of_live_ffma_loop": achieved / live_peak if live_peak else None,
         "launches_per_step": cast_launches, "avg_launch_ms": k_ms,
@@ -376,47 +383,52 @@ def run_b200(args):
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only) ------------------
     cpu = None
-    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+    if root and world_size == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_binding as ob
-        cores = ob.max_threads()
-        rows, ep = 32, 1
-        p = b.copy_params(params, row_begin=H // 2 - rows // 2, row_count=rows)
-        t0 = time.perf_counter()
-        (ob.render_distributed(scene_world.scene(), cam, p, 0, ep) if tracer == "distributed"
-         else ob.render_whitted(scene_world.scene(), cam, p))
-        t_probe = time.perf_counter() - t0
-        scale = max(1.0, 15.0 / max(t_probe, 1e-3))
-        rows = int(min(H, max(32, round(rows * scale))))
-        p = b.copy_params(params, row_begin=H // 2 - rows // 2, row_count=rows)
-        t0 = time.perf_counter()
-        (ob.render_distributed(scene_world.scene(), cam, p, 0, ep) if tracer == "distributed"
-         else ob.render_whitted(scene_world.scene(), cam, p))
-        t_cpu = time.perf_counter() - t0
+        cores = ob.host_threads()
+        rows, ep = (1, 1) if args.workload == "c5" else (32, 1)    # (a C5 cast tests 100 420 primitives)
+
+        def cpu_run(rows_):
+            p = b.copy_params(params, row_begin=H // 2 - rows_ // 2, row_count=rows_)
+            t0 = time.perf_counter()
+            (ob.render_distributed(sc, cam, p, 0, ep, n_threads=cores) if tracer == "distributed"
+             else ob.render_whitted(sc, cam, p, n_threads=cores))
+            return time.perf_counter() - t0
+
+        t_probe = cpu_run(rows)
+        rows = int(min(H, max(rows, round(rows * max(1.0, 15.0 / max(t_probe, 1e-3))))))
+        t_cpu = cpu_run(rows)
         n = rows * W * ep
         cpu = {"value": n / t_cpu / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                "sample": f"rows [{H // 2 - rows // 2},{H // 2 - rows // 2 + rows}) x {ep} epoch of the same workload: {n} samples in {t_cpu:.1f} s"}
 
-    if rank == 0:
+    if root:
         line = {
-            "metric": "Mrays/s (primary samples/s, the reference's own 'rays/s', main.rs:1169)",
+            "metric": METRIC,
             "value": value, "unit": "Mrays/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc + (" [REDUCED SIZE: dev run]" if reduced else ""), "width": W, "height": H,
-                       "depth": depth, "epochs": epochs, "sharding": ("epochs" if tracer == "distributed" else "rows"),
-                       "cast_mode": "two_phase", "tracer": args.tracer if tracer == "distributed" else "megakernel", "l2": "path state + ray buffers (%.1f GB per 16-epoch batch) and the accumulation buffer (%.1f MB) exceed L2; scene records stay in registers / L1" % (W * H * 16 * 440 / 1e9, W * H * 16 / 1e6)},
+                       "depth": depth, "epochs": epochs, "sharding": ("rows" if (by_rows or tracer != "distributed") else "epochs"),
+                       "collective": "NCCL inside libb200rt.so (b200rt_group_*): " + ("ncclSend/ncclRecv gather of row bands to rank 0" if (by_rows or tracer != "distributed") else "one ncclReduce(sum) of the accumulators to rank 0"),
+                       "cast_mode": "two_phase", "tracer": args.tracer if tracer == "distributed" else "megakernel",
+                       "timing": "per step: CUDA events on the launching stream around accumulator clear + render + collective (b200rt_group_last_render_ms), max over ranks",
+                       "l2": "path state + ray buffers (%.1f GB per 16-epoch batch) and the accumulation buffer (%.1f MB) exceed L2; scene records stay in the constant bank / shared memory" % (W * H * 16 * 440 / 1e9, W * H * 16 / 1e6)},
+            "accepted_samples_per_s": accepted / (ms_per_step * 1e-3) / 1e6,
+            "wall_ms_per_step": wall_ms / args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms,
+                    "what": "wall clock around b200rt_group_upload_scene + b200rt_group_render_* with host buffers: scene / camera / parameters H2D, render, collective, D2H of the frame on rank 0"},
             "gpu_launches": int(launches_per_step) * args.steps, "clocks": clocks,
             "casts_per_s_in_dominant_kernel": st["casts"] / args.steps / (k_ms_total * 1e-3),
             "pair_tests_per_s_in_dominant_kernel": (tri_pairs + sph_pairs) / (k_ms_total * 1e-3),
         }
         print(json.dumps(line), flush=True)
+    group.close()
     if world_size > 1:
         dist.destroy_process_group()
-    ctx.close()
     return 0
 
 

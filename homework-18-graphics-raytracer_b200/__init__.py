@@ -19,7 +19,8 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(_PKG_DIR, "_lib", "libb200rt.so")   # B200RT_LIB: tuning builds
 
 # ---- error codes / enums (include/b200rt.h) ----------------------------------------------------------
-OK, ERR_INVALID, ERR_CUDA, ERR_NO_SCENE, ERR_NO_DEVICE, ERR_IO, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_SCENE, ERR_NO_DEVICE, ERR_IO, ERR_UNSUPPORTED, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6, -7
+GROUP_ID_BYTES = 128
 FACE_FRONT, FACE_BACK, FACE_BOTH = 0, 1, 2
 MATERIAL_COLOR, MATERIAL_GENERATIVE = 0, 1
 DIFFUSE_CONST, DIFFUSE_STRIPE_V, DIFFUSE_CHECKER_UPV = 0, 1, 2
@@ -104,7 +105,7 @@ class Stats(C.Structure):
         ("exact_confirms", C.c_uint64), ("samples", C.c_uint64), ("kernel_ms", C.c_float), ("h2d_ms", C.c_float),
         ("d2h_ms", C.c_float), ("wavefront_rounds", C.c_uint32), ("certify_fallbacks", C.c_uint64),
         ("cast_kernel_ms", C.c_float), ("logic_kernel_ms", C.c_float), ("cast_kernel_launches", C.c_uint32),
-        ("kernel_launches", C.c_uint32), ("filter_kernel_ms", C.c_float), ("reserved", C.c_uint32),
+        ("kernel_launches", C.c_uint32),
     ]
 
 
@@ -114,6 +115,9 @@ HIT_DTYPE = np.dtype([("prim_id", "<i4"), ("object_index", "<u4"), ("face_direct
                       ("position", "<f4", 3), ("normal", "<f4", 3), ("uv", "<f4", 2)])
 assert RAY_DTYPE.itemsize == C.sizeof(Ray) and HIT_DTYPE.itemsize == C.sizeof(Hit)
 
+# include/b200rt_dev.h: development micro-benchmarks (not part of the product ABI)
+DEV_SYMBOLS = ["b200rt_filter_bench", "b200rt_pipe_bench"]
+
 # every symbol include/b200rt.h declares
 EXPORTED_SYMBOLS = [
     "b200rt_create", "b200rt_destroy", "b200rt_strerror", "b200rt_last_cuda_error", "b200rt_device_info",
@@ -121,7 +125,13 @@ EXPORTED_SYMBOLS = [
     "b200rt_render_distributed_device", "b200rt_resolve_device", "b200rt_intersect", "b200rt_intersect_device",
     "b200rt_post_process", "b200rt_post_process_device", "b200rt_encode_srgb8", "b200rt_encode_srgb8_device",
     "b200rt_write_png_rgb8",
-    "b200rt_get_stats", "b200rt_reset_stats", "b200rt_set_kernel_timing", "b200rt_measure_fp32_peak", "b200rt_filter_bench", "b200rt_pipe_bench", "b200rt_world_new", "b200rt_world_free",
+    "b200rt_get_stats", "b200rt_reset_stats", "b200rt_set_kernel_timing", "b200rt_measure_fp32_peak",
+    "b200rt_group_create", "b200rt_group_unique_id", "b200rt_group_create_rank", "b200rt_group_destroy", "b200rt_group_size",
+    "b200rt_group_ctx", "b200rt_group_last_error", "b200rt_group_upload_scene", "b200rt_group_render_distributed",
+    "b200rt_group_render_distributed_device", "b200rt_group_render_distributed_rows",
+    "b200rt_group_render_distributed_rows_device", "b200rt_group_render_whitted", "b200rt_group_render_whitted_device",
+    "b200rt_group_last_render_ms",
+    "b200rt_world_new", "b200rt_world_free",
     "b200rt_world_push_object", "b200rt_world_push_triangle", "b200rt_world_push_flat_triangle",
     "b200rt_world_push_square", "b200rt_world_push_sphere", "b200rt_world_push_light", "b200rt_world_load_obj",
     "b200rt_world_scene", "b200rt_world_fixture", "b200rt_fixture_camera", "b200rt_default_params",
@@ -167,6 +177,21 @@ def load_library() -> C.CDLL:
         "b200rt_measure_fp32_peak": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "b200rt_filter_bench": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
         "b200rt_pipe_bench": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
+        "b200rt_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+        "b200rt_group_unique_id": (C.c_int, [vp, C.c_size_t]),
+        "b200rt_group_create_rank": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(vp)]),
+        "b200rt_group_destroy": (C.c_int, [vp]),
+        "b200rt_group_size": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "b200rt_group_ctx": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+        "b200rt_group_last_error": (C.c_char_p, [vp]),
+        "b200rt_group_upload_scene": (C.c_int, [vp, C.POINTER(Scene)]),
+        "b200rt_group_render_distributed": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), C.c_uint32, C.c_uint32, vp]),
+        "b200rt_group_render_distributed_device": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), C.c_uint32, C.c_uint32, vp]),
+        "b200rt_group_render_distributed_rows": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), C.c_uint32, C.c_uint32, vp]),
+        "b200rt_group_render_distributed_rows_device": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), C.c_uint32, C.c_uint32, vp]),
+        "b200rt_group_render_whitted": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), vp, vp, C.c_int]),
+        "b200rt_group_render_whitted_device": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), vp]),
+        "b200rt_group_last_render_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "b200rt_world_new": (vp, []),
         "b200rt_world_free": (None, [vp]),
         "b200rt_world_push_object": (C.c_int, [vp, C.POINTER(Material)]),
@@ -182,6 +207,8 @@ def load_library() -> C.CDLL:
         "b200rt_default_params": (None, [C.POINTER(Params)]),
     }
     for name, (res, args) in sig.items():
+        if not hasattr(lib, name) and name.startswith("b200rt_group_") and os.environ.get("B200RT_LIB"):
+            continue                                   # a tuning build of an older ABI (B200RT_LIB): no device groups
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
@@ -481,7 +508,8 @@ class Context:
         _check(self._lib.b200rt_encode_srgb8_device(self._h, d_rgb, n_values, d_out, stream), "encode_srgb8_device", self)
 
     def stats(self) -> dict:
-        s = Stats()
+        buf = (C.c_char * 256)()        # (room for the larger stats struct of an older tuning build, B200RT_LIB)
+        s = Stats.from_buffer(buf)
         _check(self._lib.b200rt_get_stats(self._h, C.byref(s)), "get_stats", self)
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
@@ -507,6 +535,116 @@ class Context:
         t, mhz = C.c_double(), C.c_double()
         _check(self._lib.b200rt_measure_fp32_peak(self._h, C.byref(t), C.byref(mhz)), "measure_fp32_peak", self)
         return t.value, mhz.value
+
+
+class Group:
+    """A device group (include/b200rt.h, "device groups"): one frame sharded over several GPUs, NCCL inside the library.
+
+    ``Group(devices=[0, 1, ...])`` drives every listed GPU from this process (ncclCommInitAll);
+    ``Group.rank(device, rank, n_ranks, unique_id)`` is one rank of a one-process-per-GPU job — rank 0 makes the id with
+    ``Group.unique_id()`` and the host program (torch.distributed, MPI, a file) hands it to the others.
+    Render calls are collective; the frame lands on rank 0."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None, _handle=None, _rank0: bool = True):
+        self._lib = load_library()
+        self._world = None
+        if _handle is not None:
+            self._h, self.is_root = _handle, _rank0
+            return
+        devs = list(devices if devices is not None else [0])
+        arr = (C.c_int * len(devs))(*devs)
+        h = C.c_void_p()
+        _check(self._lib.b200rt_group_create(arr, len(devs), C.byref(h)), "b200rt_group_create")
+        self._h, self.is_root = h, True
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_char * GROUP_ID_BYTES)()
+        _check(load_library().b200rt_group_unique_id(buf, GROUP_ID_BYTES), "b200rt_group_unique_id")
+        return bytes(buf)
+
+    @classmethod
+    def rank(cls, device: int, rank: int, n_ranks: int, unique_id: Optional[bytes]) -> "Group":
+        lib = load_library()
+        h = C.c_void_p()
+        idb = (C.c_char * GROUP_ID_BYTES)(*(unique_id or b"\0" * GROUP_ID_BYTES)[:GROUP_ID_BYTES])
+        _check(lib.b200rt_group_create_rank(int(device), int(rank), int(n_ranks), idb, GROUP_ID_BYTES, C.byref(h)),
+               "b200rt_group_create_rank")
+        return cls(_handle=h, _rank0=(rank == 0))
+
+    def _ck(self, code: int, what: str) -> int:
+        if code < 0:
+            raise B200rtError(code, what, strerror(code) + ": " + self._lib.b200rt_group_last_error(self._h).decode())
+        return code
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200rt_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        n, l = C.c_int(), C.c_int()
+        self._ck(self._lib.b200rt_group_size(self._h, C.byref(n), C.byref(l)), "group_size")
+        return n.value, l.value
+
+    def member(self, local_index: int = 0) -> "Context":
+        """The single-GPU context of a local member (borrowed: stats, device info)."""
+        h = C.c_void_p()
+        self._ck(self._lib.b200rt_group_ctx(self._h, local_index, C.byref(h)), "group_ctx")
+        ctx = Context.__new__(Context)
+        ctx._lib, ctx._h, ctx.device, ctx._world = self._lib, h, -1, None
+        ctx.close = lambda: None          # owned by the group
+        return ctx
+
+    def upload_scene(self, world_or_scene) -> None:
+        scene = world_or_scene.scene() if isinstance(world_or_scene, World) else world_or_scene
+        self._ck(self._lib.b200rt_group_upload_scene(self._h, C.byref(scene)), "group_upload_scene")
+        self._world = world_or_scene
+
+    def render_distributed(self, cam: Camera, params: Params, epoch_begin: int, epoch_count: int,
+                           out_accum: Optional[np.ndarray] = None, by_rows: bool = False):
+        """Epochs sharded over the ranks and summed on rank 0 (by_rows: rows sharded and gathered instead)."""
+        h, w = params.height, params.width
+        if out_accum is None and self.is_root:
+            out_accum = np.zeros((h, w, 4), dtype=np.float32)
+        ptr = out_accum.ctypes.data if out_accum is not None else None
+        fn = self._lib.b200rt_group_render_distributed_rows if by_rows else self._lib.b200rt_group_render_distributed
+        self._ck(fn(self._h, C.byref(cam), C.byref(params), epoch_begin, epoch_count, ptr), "group_render_distributed")
+        return out_accum
+
+    def render_distributed_device(self, cam: Camera, params: Params, epoch_begin: int, epoch_count: int, d_accum_root: int,
+                                  by_rows: bool = False):
+        fn = self._lib.b200rt_group_render_distributed_rows_device if by_rows else self._lib.b200rt_group_render_distributed_device
+        self._ck(fn(self._h, C.byref(cam), C.byref(params), epoch_begin, epoch_count, C.c_void_p(d_accum_root or None)),
+                 "group_render_distributed_device")
+
+    def render_whitted(self, cam: Camera, params: Params, out_rgb: Optional[np.ndarray] = None, want_prim_id: bool = True):
+        h, w = params.height, params.width
+        prim = None
+        if self.is_root:
+            if out_rgb is None:
+                out_rgb = np.zeros((h, w, 3), dtype=np.float32)
+            prim = np.full((h, w), -2, dtype=np.int32) if want_prim_id else None
+        self._ck(self._lib.b200rt_group_render_whitted(self._h, C.byref(cam), C.byref(params),
+                                                       out_rgb.ctypes.data if out_rgb is not None else None,
+                                                       prim.ctypes.data if prim is not None else None, 1 if want_prim_id else 0),
+                 "group_render_whitted")
+        return out_rgb, prim
+
+    def render_whitted_device(self, cam: Camera, params: Params, d_rgb_root: int):
+        self._ck(self._lib.b200rt_group_render_whitted_device(self._h, C.byref(cam), C.byref(params), C.c_void_p(d_rgb_root or None)),
+                 "group_render_whitted_device")
+
+    def last_render_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self._lib.b200rt_group_last_render_ms(self._h, C.byref(ms)), "group_last_render_ms")
+        return ms.value
 
 
 def render_main(ctx: "Context", cam: Camera, params: Params, epochs: int, out_path: Optional[str] = None,

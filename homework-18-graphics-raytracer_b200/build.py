@@ -58,6 +58,7 @@ def build_all(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(INCLUDE, "b200rt.h"))
+    headers.append(os.path.join(INCLUDE, "b200rt_dev.h"))
     headers.append(os.path.abspath(__file__))
     objs = []
 
@@ -100,6 +101,12 @@ def build_all(force: bool = False, verbose: bool = False) -> str:
              verbose)
     objs.append(o)
 
+    src = os.path.join(CSRC, "b200rt_group.cu")   # device groups (NCCL through dlopen: no link-time dependency)
+    o = obj("b200rt_group")
+    if force or _newer(o, [src] + headers):
+        _run([nvcc, *ARCH, *NVCC_COMMON, "-Xcompiler", "-fPIC", "-c", src, "-o", o], verbose)
+    objs.append(o)
+
     src = os.path.join(CSRC, "host_world.cpp")
     o = obj("host_world")
     if force or _newer(o, [src] + headers):
@@ -108,7 +115,7 @@ def build_all(force: bool = False, verbose: bool = False) -> str:
     objs.append(o)
 
     if force or _newer(LIB_PATH, objs):
-        _run([nvcc, *ARCH, "-shared", "-o", LIB_PATH, *objs], verbose)
+        _run([nvcc, *ARCH, "-shared", "-o", LIB_PATH, *objs, "-ldl", "-lpthread"], verbose)
     return LIB_PATH
 
 

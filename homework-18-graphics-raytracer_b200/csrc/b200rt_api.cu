@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "b200rt.h"
+#include "b200rt_dev.h"
 #include "hvec.h"
 #include "rt_types.h"
 #include "rt_wavefront.h"
@@ -41,6 +42,7 @@ struct b200rt_ctx {
     float scene_radius = 0.0f;   // max |vertex|, max |centre| + r
     float max_edge = 0.0f;
     void* d_filter = nullptr;  size_t d_filter_bytes = 0;
+    RlTileParam h_tile0{};     // tile 0 of the rays-in-lanes filter records, passed to the cast kernels by value
 
     // device scratch for the host-buffer entry points
     void* d_out = nullptr;  size_t d_out_bytes = 0;
@@ -90,6 +92,7 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
     const double S = 2.0 * ((double)origin_bound + (double)ctx->scene_radius + (double)ctx->max_edge);
     const double A = 64.0 * u * S, B = 128.0 * u * S;
     std::vector<float4> rec((size_t)std::max(n_tiles, 1u) * 256 * 2, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::memset(&ctx->h_tile0, 0, sizeof ctx->h_tile0);
     float4* plain = rec.data() + (size_t)std::max(n_tiles, 1u) * 256;   // second half: [tri][4] plain records
     auto up = [](double v) { float f = (float)v; if ((double)f < v) f = std::nextafter(f, INFINITY); return f; };
     for (uint32_t tile = 0; tile < n_tiles; ++tile) {
@@ -107,6 +110,7 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
                 float out[16];
                 out[0] = ex[0].x; out[1] = ex[0].y; out[2] = ex[0].z; out[3] = ex[0].w;
                 bool ok = std::isfinite(ex[0].x) && std::isfinite(ex[0].y) && std::isfinite(ex[0].z) && std::isfinite(ex[0].w);
+                double L[3] = {0.0, 0.0, 0.0}, w_plain[3] = {0.0, 0.0, 0.0};   // edge lengths |n x e_k| and unslacked offsets
                 for (int k = 0; k < 3 && ok; ++k) {
                     const double e[3] = {v[ea[k]][0] - v[eb[k]][0], v[ea[k]][1] - v[eb[k]][1], v[ea[k]][2] - v[eb[k]][2]};
                     const double M[3] = {n[1] * e[2] - n[2] * e[1], n[2] * e[0] - n[0] * e[2], n[0] * e[1] - n[1] * e[0]};
@@ -116,10 +120,34 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
                     const double c = m[0] * v[eb[k]][0] + m[1] * v[eb[k]][1] + m[2] * v[eb[k]][2];
                     out[4 + 4 * k + 0] = (float)m[0]; out[4 + 4 * k + 1] = (float)m[1]; out[4 + 4 * k + 2] = (float)m[2];
                     out[4 + 4 * k + 3] = up(-c + B);
+                    L[k] = len; w_plain[k] = -c;
                 }
                 if (ok) for (int q = 0; q < 16; ++q) vals[h][q] = out[q];
+                // plain record (rays-in-lanes loop): the edge function of the LONGEST edge r follows from the other two,
+                // L_p e_p + L_q e_q + L_r e_r = 2 Area  =>  e_r = c - a e_p - b e_q, a = L_p / L_r, b = L_q / L_r (<= 1).
+                // The loop evaluates it on the slacked e_p + B, e_q + B: c' = c + (a + b) B undoes their slack, + B is the
+                // edge's own (a > 4x margin over the rounding of a direct evaluation), + 16 u S covers what the
+                // dependent form adds to that rounding: a eps_p + b eps_q + two FMAs, eps <= 5 u S each.
+                // The plane row is scaled by 2^-108 (exact; an all-zero record stays all-zero: always a candidate).
+                float pl[16];
+                for (int q = 0; q < 16; ++q) pl[q] = vals[h][q];
+                if (ok) {
+                    const int r = (L[0] >= L[1] && L[0] >= L[2]) ? 0 : (L[1] >= L[2] ? 1 : 2);
+                    const int pq[2] = {(r + 1) % 3, (r + 2) % 3};
+                    const double a = L[pq[0]] / L[r], b = L[pq[1]] / L[r];
+                    const double c = (L[0] * w_plain[0] + L[1] * w_plain[1] + L[2] * w_plain[2]) / L[r];
+                    for (int q = 0; q < 4; ++q) { pl[q] = out[q] * kRlPlaneScale; pl[4 + q] = out[4 + 4 * pq[0] + q]; pl[8 + q] = out[4 + 4 * pq[1] + q]; }
+                    pl[12] = (float)a; pl[13] = (float)b; pl[14] = up(c + B * (1.0 + a + b) + 16.0 * u * S); pl[15] = 0.0f;
+                }
                 for (int k = 0; k < 4; ++k)
-                    plain[4 * (size_t)idx + k] = make_float4(vals[h][4 * k], vals[h][4 * k + 1], vals[h][4 * k + 2], vals[h][4 * k + 3]);
+                    plain[4 * (size_t)idx + k] = make_float4(pl[4 * k], pl[4 * k + 1], pl[4 * k + 2], pl[4 * k + 3]);
+                if (tile == 0) {   // the same record as a kernel parameter: multipliers | addends
+                    float4* tp = ctx->h_tile0.rec + 4 * (size_t)idx;
+                    tp[0] = make_float4(pl[0], pl[1], pl[2], pl[4]);
+                    tp[1] = make_float4(pl[5], pl[6], pl[8], pl[9]);
+                    tp[2] = make_float4(pl[10], pl[12], pl[13], 0.0f);
+                    tp[3] = make_float4(pl[3], pl[7], pl[11], pl[14]);
+                }
             }
             // interleave {a,b}: entry q -> float2; two entries per float4
             for (int k = 0; k < 8; ++k)
@@ -136,6 +164,8 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
     ctx->scene.tri_filter_plain = ctx->scene.tri_filter + (size_t)std::max(n_tiles, 1u) * 256;
     ctx->scene.origin_bound = origin_bound;
     ctx->scene.filter_A = up(A);
+    ctx->scene.filter_As = ctx->scene.filter_A * kRlPlaneScale;
+    ctx->scene.h_tile0 = &ctx->h_tile0;
     ctx->scene.filter_g = 3.814697265625e-6f;   // 2^-18
     return B200RT_OK;
 }
@@ -166,7 +196,7 @@ void make_camera(const b200rt_camera& c, DCamera& out) {
 int make_params(const b200rt_params& p, uint32_t epoch_begin, uint32_t epoch_count, DParams& o) {
     if (p.width == 0 || p.height == 0) return B200RT_ERR_INVALID;
     if (p.depth < 0 || p.depth > B200RT_MAX_DEPTH) return B200RT_ERR_UNSUPPORTED;
-    if (p.row_count && (p.row_begin >= p.height || p.row_begin + p.row_count > p.height)) return B200RT_ERR_INVALID;
+    if (p.row_count && (p.row_begin >= p.height || p.row_count > p.height - p.row_begin)) return B200RT_ERR_INVALID;   // (no u32 wrap)
     if (p.cast_mode > B200RT_CAST_BRUTE_EXACT) return B200RT_ERR_INVALID;
     if (p.tracer > B200RT_TRACER_MEGAKERNEL) return B200RT_ERR_INVALID;
     o.width = p.width; o.height = p.height;
@@ -196,7 +226,6 @@ int fetch_counters(b200rt_ctx* ctx) {
     ctx->stats.wavefront_rounds = ctx->last_rounds;
     ctx->stats.cast_kernel_ms = (float)ctx->wf_timing.cast_ms;
     ctx->stats.logic_kernel_ms = (float)ctx->wf_timing.logic_ms;
-    ctx->stats.filter_kernel_ms = (float)ctx->wf_timing.filter_ms;
     ctx->stats.cast_kernel_launches = (uint32_t)ctx->wf_timing.cast_launches;
     ctx->stats.kernel_launches = ctx->last_launches;
     return B200RT_OK;
@@ -215,6 +244,7 @@ const char* b200rt_strerror(int code) {
         case B200RT_ERR_NO_DEVICE: return "no usable CUDA device (libb200rt has no CPU fallback)";
         case B200RT_ERR_IO: return "OBJ file could not be read or parsed";
         case B200RT_ERR_UNSUPPORTED: return "unsupported parameter (depth > B200RT_MAX_DEPTH?)";
+        case B200RT_ERR_NCCL: return "NCCL unavailable or an NCCL call failed (see b200rt_group_last_error)";
         default: return "unknown error";
     }
 }
@@ -290,10 +320,22 @@ int b200rt_upload_scene(b200rt_ctx* ctx, const b200rt_scene* s) {
     if ((s->n_triangles && !s->triangles) || (s->n_spheres && !s->spheres) || (s->n_materials && !s->materials) ||
         (s->n_lights && !s->lights))
         return B200RT_ERR_INVALID;
+    // limits of the packed device formats: primitive id + 1 in 28 bits (ray meta), object id in 24 bits (hit meta),
+    // first light of a shadow chunk in 12 bits (path flags)
+    if ((uint64_t)s->n_triangles + s->n_spheres >= (1ull << 28) || s->n_materials >= (1u << 24) || s->n_lights >= 4096u)
+        return B200RT_ERR_UNSUPPORTED;
     for (uint32_t i = 0; i < s->n_triangles; ++i)
         if (s->triangles[i].object_index >= s->n_materials) return B200RT_ERR_INVALID;
     for (uint32_t i = 0; i < s->n_spheres; ++i)
         if (s->spheres[i].object_index >= s->n_materials) return B200RT_ERR_INVALID;
+    for (uint32_t k = 0; k < s->n_materials; ++k) {
+        const b200rt_material& m = s->materials[k];
+        if (m.kind > B200RT_MATERIAL_GENERATIVE) return B200RT_ERR_INVALID;
+        if (m.kind == B200RT_MATERIAL_GENERATIVE && (m.diffuse_fn > B200RT_DIFFUSE_CHECKER_UPV || m.normal_fn > B200RT_NORMAL_SINCOS_U))
+            return B200RT_ERR_INVALID;
+    }
+    for (uint32_t k = 0; k < s->n_lights; ++k)
+        if (s->lights[k].kind > B200RT_LIGHT_POINT) return B200RT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
 
     const uint32_t nt = s->n_triangles, ns = s->n_spheres, nm = s->n_materials, nl = s->n_lights;
@@ -560,7 +602,7 @@ int b200rt_render_distributed(b200rt_ctx* ctx, const b200rt_camera* cam, const b
     if (rc != B200RT_OK) return rc;
     const uint32_t r0 = params->row_count ? params->row_begin : 0u;
     const uint32_t rn = params->row_count ? params->row_count : params->height;
-    if (params->row_count && (r0 >= params->height || r0 + rn > params->height)) return B200RT_ERR_INVALID;
+    if (params->row_count && (r0 >= params->height || rn > params->height - r0)) return B200RT_ERR_INVALID;
     const size_t o = (size_t)r0 * params->width, cnt = (size_t)rn * params->width;
     // the accumulation buffer is ADDED to: it travels to the device and back
     CU(cudaEventRecord(ctx->ev2, ctx->stream));
@@ -647,6 +689,13 @@ int b200rt_intersect(b200rt_ctx* ctx, const b200rt_ray* rays, size_t n, uint32_t
     if (!ctx || (n && (!rays || !hits))) return B200RT_ERR_INVALID;
     if (!ctx->have_scene) return B200RT_ERR_NO_SCENE;
     if (n == 0) return B200RT_OK;
+    if (n > 0xffffffffull) return B200RT_ERR_UNSUPPORTED;
+    // FaceDirection is an enum in the reference (main.rs:52-57) and the exclusion an Option<PrimitiveIndex> (main.rs:69-75):
+    // reject what they cannot hold.  An exclusion index beyond the scene's primitives is legal (it never matches).
+    for (size_t i = 0; i < n; ++i)
+        if (rays[i].face_direction > B200RT_FACE_BOTH || rays[i].exclude_face > B200RT_FACE_BOTH ||
+            rays[i].exclude_prim < -1 || rays[i].exclude_prim >= (1 << 28) - 1)
+            return B200RT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure(ctx, &ctx->d_aux, &ctx->d_aux_bytes, n * sizeof(b200rt_ray));
     if (rc != B200RT_OK) return rc;

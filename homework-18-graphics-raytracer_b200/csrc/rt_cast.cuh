@@ -119,8 +119,12 @@ RT_DI void sphere_exact_test(float4 s, int32_t prim, const DRay& r, Best& best) 
     best.pos = r.o + r.d * t;                                                     // main.rs:304
 }
 
-// Winner-only work: barycentric normal / uv (main.rs:235-252) or sphere normal / uv (main.rs:305-313)
-RT_DI void finalize_hit(const DScene& sc, const Best& best, DHit& h, bool want_attrs = true) {
+// Winner-only work: barycentric normal / uv (main.rs:235-252) or sphere normal / uv (main.rs:305-313).
+//   exact / attr / sph: the record arrays (sc.tri_exact ... or shared-memory copies of them, same bits).
+//   sphere_uv = false skips acos / atan2 of a sphere hit whose material never reads uv (the caller knows: only
+//   GenerativeMaterial::approx takes uv, materials.rs:85-103); uv is then left 0.
+RT_DI void finalize_hit(const DScene& sc, const Best& best, DHit& h, bool want_attrs, const float4* __restrict__ exact,
+                        const float4* __restrict__ attr, const float4* __restrict__ sph, bool all_sphere_uv = true) {
     h.prim = best.prim;
     if (best.prim < 0) return;
     h.face = best.bf;
@@ -128,8 +132,8 @@ RT_DI void finalize_hit(const DScene& sc, const Best& best, DHit& h, bool want_a
     h.pos = best.pos;
     if (!want_attrs) return;    // shadow rays: only "is there a hit, and how far" is used (main.rs:435-447)
     if ((uint32_t)best.prim < sc.n_tris) {
-        const float4* ex = sc.tri_exact + 4 * (size_t)best.prim;
-        const float4* at = sc.tri_attr + 4 * (size_t)best.prim;
+        const float4* ex = exact + 4 * (size_t)best.prim;
+        const float4* at = attr + 4 * (size_t)best.prim;
         const float4 q0 = ex[0], q1 = ex[1], q2 = ex[2], q3 = ex[3];
         const float4 t0 = at[0], t1 = at[1], t2 = at[2], t3 = at[3];
         const f3 n = mk3(q0), v0 = mk3(q1), v1 = mk3(q2), v2 = mk3(q3);
@@ -143,13 +147,18 @@ RT_DI void finalize_hit(const DScene& sc, const Best& best, DHit& h, bool want_a
         h.uv.y = (w0 * b0 + w1 * b1) + w2 * b2;
     } else {
         const uint32_t j = (uint32_t)best.prim - sc.n_tris;
-        const float4 s = sc.sph[j];
+        const float4 s = sph[j];
         h.object = sc.sph_obj[j];
         const f3 tmp = normalize(best.pos - mk3(s));                              // main.rs:306
         h.normal = best.bf ? -tmp : tmp;
-        h.uv.x = nl_acosf(h.normal.y) / kPi;                                         // main.rs:311
-        h.uv.y = nl_atan2f(h.normal.z, h.normal.x) / (kPi * 2.0f) + 0.5f;            // main.rs:312
+        if (all_sphere_uv || sc.materials[h.object].kind == B200RT_MATERIAL_GENERATIVE) {
+            h.uv.x = nl_acosf(h.normal.y) / kPi;                                         // main.rs:311
+            h.uv.y = nl_atan2f(h.normal.z, h.normal.x) / (kPi * 2.0f) + 0.5f;            // main.rs:312
+        }
     }
+}
+RT_DI void finalize_hit(const DScene& sc, const Best& best, DHit& h, bool want_attrs = true) {
+    finalize_hit(sc, best, h, want_attrs, sc.tri_exact, sc.tri_attr, sc.sph);
 }
 
 // ---- brute-force exact cast (validation path, B200RT_CAST_BRUTE_EXACT) -------------------------
@@ -260,8 +269,9 @@ RT_DI uint2* cast_slot_masks(float4* s_rays) { return reinterpret_cast<uint2*>(s
 //   planes: the {n, d} rows (stride 4 float4) of the tile's triangles for the classification — sc.tri_exact, or a
 //   shared-memory copy of the plain filter records, whose first row holds the same bits (degenerate triangles are
 //   all-zero there: n.dir = 0, set U).
+//   exact: the exact records {n,d}{v0,obj}{v1}{v2} of the tile's triangles (sc.tri_exact + 4 * base, or a shared-memory copy).
 RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand, bool certify, const DRay& ray,
-                        Best& best, CastStats& cs, const float4* __restrict__ planes) {
+                        Best& best, CastStats& cs, const float4* __restrict__ planes, const float4* __restrict__ exact) {
     if (cand == 0ull) return;
     unsigned long long todo = cand;
     bool fast = false;
@@ -311,7 +321,7 @@ RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand
         while (todo) {                                // increasing primitive index
             const uint32_t i = (uint32_t)__ffsll((long long)todo) - 1u;
             todo &= todo - 1ull;
-            tri_exact_test(sc.tri_exact + 4 * (size_t)(base + i), (int32_t)(base + i), ray, best);
+            tri_exact_test(exact + 4 * (size_t)i, (int32_t)(base + i), ray, best);
             nan_seen |= best.t != best.t;
         }
         if (!fast) break;
@@ -417,13 +427,13 @@ RT_DI unsigned long long tile_candidates(const DScene& sc, uint32_t tile, uint2 
 // time — squared line-sphere distance |disp|^2 |dir|^2 - (disp.dir)^2 against r^2 with a 64u (r^2 + |disp|^2)
 // slack (both sides' rounding is <= 13u of that; NaNs pass) — then the exact test of the survivors in index
 // order.  Walking a mask lets lanes that pass DIFFERENT spheres run their exact tests in the same iteration.
-RT_DI void cast_spheres(const DScene& sc, const DRay& ray, bool trust, float dd, Best& best) {
+RT_DI void cast_spheres(const DScene& sc, const DRay& ray, bool trust, float dd, Best& best, const float4* __restrict__ sph) {
     for (uint32_t j0 = 0; j0 < sc.n_sph; j0 += 32u) {
         const uint32_t nj = min(32u, sc.n_sph - j0);
         uint32_t smask = 0u;
 #pragma unroll 4
         for (uint32_t j = 0; j < nj; ++j) {
-            const float4 s4 = sc.sph[j0 + j];
+            const float4 s4 = sph[j0 + j];
             const float ex = s4.x - ray.o.x, ey = s4.y - ray.o.y, ez = s4.z - ray.o.z;
             const float b = __fmaf_rn(ez, ray.d.z, __fmaf_rn(ey, ray.d.y, ex * ray.d.x));
             const float e2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, ex * ex));
@@ -436,10 +446,11 @@ RT_DI void cast_spheres(const DScene& sc, const DRay& ray, bool trust, float dd,
         while (smask) {
             const uint32_t j = (uint32_t)__ffs((int)smask) - 1u;
             smask &= smask - 1u;
-            sphere_exact_test(sc.sph[j0 + j], (int32_t)(sc.n_tris + j0 + j), ray, best);
+            sphere_exact_test(sph[j0 + j], (int32_t)(sc.n_tris + j0 + j), ray, best);
         }
     }
 }
+RT_DI void cast_spheres(const DScene& sc, const DRay& ray, bool trust, float dd, Best& best) { cast_spheres(sc, ray, trust, dd, best, sc.sph); }
 
 // Warp-collective cast: EVERY lane of the warp must call it (converged).  `active` lanes carry a ray.
 // s_rays: this warp's kCastSlotFloat4 staging slot in shared memory.  tile0: the lane's records of tile 0,
@@ -467,7 +478,7 @@ RT_DI void warp_cast(const DScene& sc, float4* __restrict__ s_rays, const TriPai
         filter_tile(sc, s_rays, c, n_act, lane);
         __syncwarp();
         if (active && !nan_ray) confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, s_mask[rank], trust), trust, ray, best, cs,
-                                 sc.tri_exact + 4 * (size_t)(tile * kTileTris));
+                                 sc.tri_exact + 4 * (size_t)(tile * kTileTris), sc.tri_exact + 4 * (size_t)(tile * kTileTris));
         __syncwarp();   // masks (and, after the last tile, the ray slots) are free again
     }
     if (active) {

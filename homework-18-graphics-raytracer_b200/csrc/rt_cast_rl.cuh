@@ -27,9 +27,14 @@ namespace b200rt {
 
 constexpr int kRlThreads = 128;                 // CTA size of the kernels built on cast_rays_in_lanes
 constexpr uint32_t kRlNoRay = 0xffffffffu;      // tag of an empty ray slot (IO tags must not use it)
+constexpr uint32_t kRlSphShared = 16u;          // spheres copied to shared memory (more: read from global memory)
+constexpr uint32_t kRlCullClasses = 8u;         // classes of statically culled triangles an IO can name (0 = none)
 
-struct RlShared {                               // 24.5 KB per CTA
-    float4 tile[4 * kTileTris];                 // plain filter records
+struct RlShared {                               // 28.4 KB per CTA (the filter records are a kernel parameter)
+    float4 exact[4 * kTileTris];                // exact records {n,d}{v0,obj}{v1}{v2}  (phase 2 never waits for L1 / L2)
+    float4 attr[4 * kTileTris];                 // vertex normals / uvs of the tile's triangles (winner only)
+    float4 sph[kRlSphShared];
+    uint2 cull[kRlCullClasses];
     float4 ro[4][kRlThreads];                   // {origin, ray meta}   of ray j of thread t
     float4 rd[4][kRlThreads];                   // {direction, tag}
     uint2 mk[4][kRlThreads];                    // candidate mask
@@ -39,41 +44,76 @@ RT_DI uint32_t rl_pack_ray_meta(uint32_t face, int32_t ex_prim, uint32_t ex_face
     return face | (ex_face << 2) | ((uint32_t)(ex_prim + 1) << 4);
 }
 
-// Phase 1 for one 64-triangle tile in shared memory and this lane's four rays (two packed pairs): keep[j] = the 64-bit
-// candidate mask of ray j (bit i = triangle i of the tile).
-RT_DI void rl_filter_tile(const float4* __restrict__ tile, const P2 (&ox)[2], const P2 (&oy)[2], const P2 (&oz)[2],
-                          const P2 (&dx)[2], const P2 (&dy)[2], const P2 (&dz)[2], const P2 (&cf)[2], const P2 A2,
-                          const float g, uint32_t (&keep)[4][2]) {
+#ifndef RL_LOOP_UNROLL
+#define RL_LOOP_UNROLL 2   // triangles per iteration of the filter loop (x 2 ray pairs = independent FFMA2 chains in flight)
+#endif
+constexpr int kRlLoopUnroll = RL_LOOP_UNROLL;
+
+// face modes of a block of rays: every ray Front / every ray Back / anything (the cull factor is a multiply)
+enum : int { kRlFront = 0, kRlBack = 1, kRlMixed = 2 };
+
+// one filter record as named scalars (multipliers n, m_p, m_q, a, b; addends d, w_p, w_q, c), and where it comes from
+struct RlRec { float nx, ny, nz, d, px, py, pz, wp, qx, qy, qz, wq, a, b, c; };
+struct RlRecShared {     // tri_filter_plain layout in shared memory: four broadcast LDS.128 per record
+    const float4* __restrict__ tile;
+    RT_DI RlRec operator()(int i) const {
+        const float4 q0 = tile[4 * i], q1 = tile[4 * i + 1], q2 = tile[4 * i + 2], q3 = tile[4 * i + 3];
+        return RlRec{q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z};
+    }
+};
+struct RlRecParam {      // RlTileParam layout in the constant bank: the multipliers travel through uniform registers
+    const RlTileParam& tp;
+    RT_DI RlRec operator()(int i) const {
+        const float4 u0 = tp.rec[4 * i], u1 = tp.rec[4 * i + 1], u2 = tp.rec[4 * i + 2], q3 = tp.rec[4 * i + 3];
+        return RlRec{u0.x, u0.y, u0.z, q3.x, u0.w, u1.x, u1.y, q3.y, u1.z, u1.w, u2.x, q3.z, u2.y, u2.z, q3.w};
+    }
+};
+
+// Phase 1 for one 64-triangle tile and this lane's four rays (two packed pairs): keep[j] = the 64-bit candidate mask of
+// ray j (bit i = triangle i of the tile).  Per ray x triangle pair, with the plane row scaled by s = 2^-108:
+//     nd = s n.dir   num = s (d - n.o)   r = rcp.approx.ftz(nd)   t = num r   p = o + t dir
+//     e_p = m_p.p + w_p   e_q = m_q.p + w_q   e_r = c - a e_p - b e_q
+//     keep = sign bit of  min(e_p, e_q, e_r, t, cull) + A s |r|
+// 19 FFMA2 / FMUL2 + 1 MUFU.RCP + 2 FMNMX3 + 1 SHF per pair of rays and triangle (20 with the cull multiply).
+//   * near-parallel guard: |n.dir| < g = 2^-18 makes nd subnormal, the reciprocal's FTZ turns it into r = +-inf, t, p and
+//     the edge functions into inf / NaN, and inf - inf (or any NaN) is the canonical NaN 0x7fffffff, sign bit clear: the
+//     pair is kept, as the filter's error analysis needs - without the FADD + FMNMX the guard used to cost;
+//   * cull = -r for Front rays, +r for Back rays (main.rs:185-188; FACE picks the sign at compile time, a block of mixed
+//     rays multiplies by the ray's own factor, 0 for Both): a pair whose face the ray culls has cull <= -2^108 and is
+//     rejected whenever |n.dir| >= g; below that the pair is kept whatever the sign of the fused dot product says.
+template <int FACE, class REC>
+RT_DI void rl_filter_tile(REC rec, const P2 (&ox)[2], const P2 (&oy)[2], const P2 (&oz)[2], const P2 (&dx)[2],
+                          const P2 (&dy)[2], const P2 (&dz)[2], const P2 (&cf)[2], const P2 As2, uint32_t (&keep)[4][2]) {
     // reject masks (bit set = rejected), triangle i in bit (31 - i) of its half
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         uint32_t rj0 = 0u, rj1 = 0u, rj2 = 0u, rj3 = 0u;
-#pragma unroll 2
+#pragma unroll kRlLoopUnroll
         for (int i = 0; i < 32; ++i) {
-            const float4* q = tile + 4 * (32 * half + i);
-            const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+            const RlRec q = rec(32 * half + i);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const P2 nd = p2_fma(p2_bc(q0.z), dz[k], p2_fma(p2_bc(q0.y), dy[k], p2_mul(p2_bc(q0.x), dx[k])));
-                const P2 num = p2_fma(p2_bc(-q0.z), oz[k], p2_fma(p2_bc(-q0.y), oy[k], p2_fma(p2_bc(-q0.x), ox[k], p2_bc(q0.w))));
+                const P2 nd = p2_fma(p2_bc(q.nz), dz[k], p2_fma(p2_bc(q.ny), dy[k], p2_mul(p2_bc(q.nx), dx[k])));
+                const P2 num = p2_fma(p2_bc(-q.nz), oz[k], p2_fma(p2_bc(-q.ny), oy[k], p2_fma(p2_bc(-q.nx), ox[k], p2_bc(q.d))));
                 float nda, ndb;
                 p2_unpack(nd, nda, ndb);
                 const float ra = rcp_approx(nda), rb = rcp_approx(ndb);
-                const P2 t = p2_mul(num, p2_pack(ra, rb));
-                const P2 cull = p2_mul(nd, cf[k]);
+                const P2 r2 = p2_pack(ra, rb);
+                const P2 t = p2_mul(num, r2);
                 const P2 px = p2_fma(t, dx[k], ox[k]), py = p2_fma(t, dy[k], oy[k]), pz = p2_fma(t, dz[k], oz[k]);
-                const P2 e0 = p2_fma(p2_bc(q1.z), pz, p2_fma(p2_bc(q1.y), py, p2_fma(p2_bc(q1.x), px, p2_bc(q1.w))));
-                const P2 e1 = p2_fma(p2_bc(q2.z), pz, p2_fma(p2_bc(q2.y), py, p2_fma(p2_bc(q2.x), px, p2_bc(q2.w))));
-                const P2 e2 = p2_fma(p2_bc(q3.z), pz, p2_fma(p2_bc(q3.y), py, p2_fma(p2_bc(q3.x), px, p2_bc(q3.w))));
+                const P2 e0 = p2_fma(p2_bc(q.pz), pz, p2_fma(p2_bc(q.py), py, p2_fma(p2_bc(q.px), px, p2_bc(q.wp))));
+                const P2 e1 = p2_fma(p2_bc(q.qz), pz, p2_fma(p2_bc(q.qy), py, p2_fma(p2_bc(q.qx), px, p2_bc(q.wq))));
+                const P2 e2 = p2_fma(p2_bc(-q.b), e1, p2_fma(p2_bc(-q.a), e0, p2_bc(q.c)));
                 float e0a, e0b, e1a, e1b, e2a, e2b, ta, tb, ca, cb;
-                p2_unpack(e0, e0a, e0b); p2_unpack(e1, e1a, e1b); p2_unpack(e2, e2a, e2b); p2_unpack(t, ta, tb); p2_unpack(cull, ca, cb);
+                p2_unpack(e0, e0a, e0b); p2_unpack(e1, e1a, e1b); p2_unpack(e2, e2a, e2b); p2_unpack(t, ta, tb);
+                if (FACE == kRlFront) { ca = -ra; cb = -rb; }
+                else if (FACE == kRlBack) { ca = ra; cb = rb; }
+                else { const P2 cull = p2_mul(r2, cf[k]); p2_unpack(cull, ca, cb); }
                 const float ma = fminf(fminf(fminf(e0a, e1a), e2a), fminf(ta, ca));
                 const float mb = fminf(fminf(fminf(e0b, e1b), e2b), fminf(tb, cb));
-                const P2 ms = p2_fma(A2, p2_pack(fabsf(ra), fabsf(rb)), p2_pack(ma, mb));
-                float msa, msb;
-                p2_unpack(ms, msa, msb);
-                // keep iff ms >= 0 or |nd| < g  <=>  max(ms, g - |nd|) is not negative (NaN ms: the second operand decides)
-                const float ka = fmaxf(msa, g - fabsf(nda)), kb = fmaxf(msb, g - fabsf(ndb));
+                const P2 ms = p2_fma(As2, p2_pack(fabsf(ra), fabsf(rb)), p2_pack(ma, mb));
+                float ka, kb;
+                p2_unpack(ms, ka, kb);
                 if (k == 0) { rj0 = __funnelshift_l(__float_as_uint(ka), rj0, 1); rj1 = __funnelshift_l(__float_as_uint(kb), rj1, 1); }
                 else        { rj2 = __funnelshift_l(__float_as_uint(ka), rj2, 1); rj3 = __funnelshift_l(__float_as_uint(kb), rj3, 1); }
             }
@@ -82,16 +122,42 @@ RT_DI void rl_filter_tile(const float4* __restrict__ tile, const P2 (&ox)[2], co
     }
 }
 
+// the loop for the face modes of a block of rays (warp-uniform `mode`)
+template <class REC>
+RT_DI void rl_filter_tile_mode(int mode, REC rec, const P2 (&ox)[2], const P2 (&oy)[2], const P2 (&oz)[2], const P2 (&dx)[2],
+                               const P2 (&dy)[2], const P2 (&dz)[2], const P2 (&cf)[2], const P2 As2, uint32_t (&keep)[4][2]) {
+    if (mode == kRlFront) rl_filter_tile<kRlFront>(rec, ox, oy, oz, dx, dy, dz, cf, As2, keep);
+    else if (mode == kRlBack) rl_filter_tile<kRlBack>(rec, ox, oy, oz, dx, dy, dz, cf, As2, keep);
+    else rl_filter_tile<kRlMixed>(rec, ox, oy, oz, dx, dy, dz, cf, As2, keep);
+}
+// cull factor of a ray for the mixed loop, and the block's mode from the warp's rays (empty slots fit any mode)
+RT_DI float rl_cull_factor(uint32_t face) { return face == kFront ? -1.0f : (face == kBack ? 1.0f : 0.0f); }
+RT_DI int rl_block_mode(uint32_t have_front, uint32_t have_back, uint32_t have_both) {
+    const bool f = __any_sync(kFullMask, have_front != 0u), b = __any_sync(kFullMask, have_back != 0u),
+               o = __any_sync(kFullMask, have_both != 0u);
+    return (!b && !o) ? kRlFront : ((!f && !o) ? kRlBack : kRlMixed);
+}
+
 // CTA-collective (kRlThreads threads): casts rays [0, n_work) of `io`, 128 rays per warp and iteration, work split over
-// the whole grid.  Call once per kernel; n_work may be 0.
+// the whole grid.  Call once per kernel; n_work may be 0.  The scene's one tile (filter, exact and attribute records), its
+// spheres and the IO's classes of statically culled triangles are copied to shared memory once per CTA.
 template <bool PREFETCH, class IO>
-RT_DI void cast_rays_in_lanes(const DScene& sc, IO io, const uint32_t n_work, RlShared& sh, CastStats& cs) {
+RT_DI void cast_rays_in_lanes(const DScene& sc, const RlTileParam& tp, IO io, const uint32_t n_work, RlShared& sh, CastStats& cs) {
     const uint32_t lane = threadIdx.x & 31u, tid = threadIdx.x;
     if (n_work == 0u) return;
-    for (uint32_t i = threadIdx.x; i < 4u * kTileTris; i += blockDim.x) sh.tile[i] = sc.tri_filter_plain[i];
+    for (uint32_t i = threadIdx.x; i < 4u * kTileTris; i += blockDim.x) {
+        const bool in = i < 4u * sc.n_tris;
+        sh.exact[i] = in ? sc.tri_exact[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        sh.attr[i] = in ? sc.tri_attr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (threadIdx.x < kRlSphShared) sh.sph[threadIdx.x] = threadIdx.x < sc.n_sph ? sc.sph[threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < kRlCullClasses) sh.cull[threadIdx.x] = io.cull_mask(sc, threadIdx.x);
     __syncthreads();
-    const P2 A2 = p2_bc(sc.filter_A);
-    const float g = sc.filter_g;
+    const float4* __restrict__ sph = sc.n_sph <= kRlSphShared ? sh.sph : sc.sph;
+    // candidates are triangles of the scene: the padding of the tile is masked off once
+    const uint32_t v_lo = sc.n_tris >= 32u ? 0xffffffffu : ((1u << sc.n_tris) - 1u);
+    const uint32_t v_hi = sc.n_tris >= 64u ? 0xffffffffu : (sc.n_tris > 32u ? ((1u << (sc.n_tris - 32u)) - 1u) : 0u);
+    const P2 As2 = p2_bc(sc.filter_As);
     // exactly 1.0f, but opaque to ptxas: a packed multiply by it MATERIALISES each ray operand in its own aligned
     // register pair (a plain pack is coalesced with the LDG.128 destination quads and re-packed inside the loop)
     const P2 one2 = p2_bc(__fmaf_rn(sc.filter_g, 0.0f, 1.0f));
@@ -101,8 +167,10 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, IO io, const uint32_t n_work, Rl
     const uint32_t n_blocks = (n_work + 127u) / 128u;
     for (uint32_t blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < n_blocks; blk += warps_total) {
         const uint32_t base = blk * 128u;
+        io.begin_block(base);
         // this lane's four rays: work indices base + lane + 32 j
         P2 ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], cf[2];
+        uint32_t trust4 = 0u, have_front = 0u, have_back = 0u, have_both = 0u;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             DRay r[2];
@@ -114,7 +182,12 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, IO io, const uint32_t n_work, Rl
                 r[h].o = mk3(0.f, 0.f, 0.f); r[h].d = mk3(0.f, 0.f, 1.f); r[h].face = kFront; r[h].ex_prim = -1; r[h].ex_face = kFront;
                 uint32_t tag = kRlNoRay;
                 if (idx < n_work && !io.load(idx, r[h], tag)) tag = kRlNoRay;
-                c[h] = r[h].face == kFront ? -kCullK : (r[h].face == kBack ? kCullK : 0.0f);
+                c[h] = rl_cull_factor(r[h].face);
+                if (tag != kRlNoRay) {
+                    have_front |= r[h].face == kFront; have_back |= r[h].face == kBack; have_both |= r[h].face > kBack;
+                    float dd;
+                    if (ray_trusted(sc, r[h], dd)) trust4 |= 1u << j;
+                }
                 sh.ro[j][tid] = make_float4(r[h].o.x, r[h].o.y, r[h].o.z, __uint_as_float(rl_pack_ray_meta(r[h].face, r[h].ex_prim, r[h].ex_face)));
                 sh.rd[j][tid] = make_float4(r[h].d.x, r[h].d.y, r[h].d.z, __uint_as_float(tag));
             }
@@ -124,6 +197,7 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, IO io, const uint32_t n_work, Rl
             dz[k] = p2_mul(p2_pack(r[0].d.z, r[1].d.z), one2);
             cf[k] = p2_mul(p2_pack(c[0], c[1]), one2);
         }
+        const int mode = rl_block_mode(have_front, have_back, have_both);
         // the handles of this lane's NEXT four rays are fetched now, their rows are pulled into L2 after the filter loop
         // (while phase 2 runs): the chain handle -> rows is two DRAM round trips otherwise
         uint32_t next[4];
@@ -136,17 +210,35 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, IO io, const uint32_t n_work, Rl
         }
         // phase 1: the candidate masks of this lane's four rays
         uint32_t keep[4][2];
-        rl_filter_tile(sh.tile, ox, oy, oz, dx, dy, dz, cf, A2, g, keep);
+        rl_filter_tile_mode(mode, RlRecParam{tp}, ox, oy, oz, dx, dy, dz, cf, As2, keep);
+#ifdef RL_DIAG_LOOP2   // timing experiment: the loop twice (the second result is masked by a run-time zero)
+        {
+            uint32_t keep2[4][2];
+            const P2 A2b = p2_bc(sc.filter_As + __uint_as_float(sc.n_tris_padded >> 31));
+            rl_filter_tile_mode(mode, RlRecParam{tp}, ox, oy, oz, dx, dy, dz, cf, A2b, keep2);
+            const uint32_t zero_rt = sc.n_tris_padded >> 31;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sh.mk[j][tid] = make_uint2(keep[j][0], keep[j][1]);
+            for (int j = 0; j < 4; ++j) { keep[j][0] |= keep2[j][0] & zero_rt; keep[j][1] |= keep2[j][1] & zero_rt; }
+        }
+#endif
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sh.mk[j][tid] = make_uint2(keep[j][0] & v_lo, keep[j][1] & v_hi);
         if (PREFETCH) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (next[j] != kRlNoRay) io.prefetch(next[j]);
         }
         // phase 2, ray by ray (every thread reads only its own slots: no barrier)
+#ifdef RL_DIAG_P2X2    // timing experiment: phase 2 twice (the first pass stores nothing)
+#pragma unroll 1
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = jj & 3;
+            const bool really = jj >= 4 || (sc.n_tris_padded >> 31) != 0u;
+#else
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
+            const bool really = true;
+#endif
             const float4 a = sh.ro[j][tid], b = sh.rd[j][tid];
             const uint32_t tag = __float_as_uint(b.w);
             if (tag == kRlNoRay) continue;
@@ -154,18 +246,20 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, IO io, const uint32_t n_work, Rl
             DRay r;
             r.o = mk3(a); r.d = mk3(b);
             r.face = meta & 3u; r.ex_face = (meta >> 2) & 3u; r.ex_prim = (int32_t)(meta >> 4) - 1;
-            float dd;
-            const bool trust = ray_trusted(sc, r, dd);
+            const bool trust = (trust4 >> j) & 1u;
             Best best;
             best_init(best);
-            const uint2 km = sh.mk[j][tid], cm = io.culled(sc, tag, 0u);
-            confirm_tile(sc, 0u, tile_candidates(sc, 0u, make_uint2(km.x & ~cm.x, km.y & ~cm.y), trust), trust, r, best, cs, sh.tile);
-            cast_spheres(sc, r, trust, dd, best);
+            const uint2 km = sh.mk[j][tid], cm = sh.cull[io.cull_class(tag)];
+            // untrusted rays (outside the filter's assumptions): every triangle of the scene
+            const uint32_t c_lo = trust ? (km.x & ~cm.x) : v_lo, c_hi = trust ? (km.y & ~cm.y) : v_hi;
+            confirm_tile(sc, 0u, ((unsigned long long)c_hi << 32) | (unsigned long long)c_lo, trust, r, best, cs, sh.exact, sh.exact);
+            cast_spheres(sc, r, trust, (r.d.x * r.d.x + r.d.y * r.d.y) + r.d.z * r.d.z, best, sph);
             DHit h;
             h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
-            finalize_hit(sc, best, h, io.want_attrs(tag));
+            finalize_hit(sc, best, h, io.want_attrs(tag), sh.exact, sh.attr, sph, io.all_sphere_uv());
             cs.casts += 1ull;
-            io.store(tag, h);
+            if (really) io.store(tag, h);
+            else if (h.t == -12345.0f) io.store(tag ^ 1u, h);    // (keeps the discarded pass alive; never true)
         }
     }
 }
@@ -278,8 +372,7 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     uint32_t parity0 = 0u, parity1 = 0u;
-    const P2 A2 = p2_bc(sc.filter_A);
-    const float g = sc.filter_g;
+    const P2 As2 = p2_bc(sc.filter_As);
     const P2 one2 = p2_bc(__fmaf_rn(sc.filter_g, 0.0f, 1.0f));   // see cast_rays_in_lanes
     const uint32_t n_blocks = (n_work + 127u) / 128u;
     const uint32_t warps_per_cta = blockDim.x >> 5;
@@ -291,8 +384,10 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
             if (n_tiles > 1u) rl_tma_load_tile(sh.tile[1], sc.tri_filter_plain + 4u * kTileTris, &sh.bar[1]);
         }
         const uint32_t base = (it * warps_per_cta + warp) * 128u;   // >= n_work: this warp idles through the pass
+        io.begin_block(base);
         P2 ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], cf[2];
         uint32_t valid4 = 0u, trust4 = 0u, nan4 = 0u;   // nan4: rays with a NaN component (cast_nan_ray_triangles)
+        uint32_t have_front = 0u, have_back = 0u, have_both = 0u;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             DRay r[2];
@@ -304,9 +399,10 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
                 r[h].o = mk3(0.f, 0.f, 0.f); r[h].d = mk3(0.f, 0.f, 1.f); r[h].face = kFront; r[h].ex_prim = -1; r[h].ex_face = kFront;
                 uint32_t tag = kRlNoRay;
                 if (base < n_work && idx < n_work && !io.load(idx, r[h], tag)) tag = kRlNoRay;
-                c[h] = r[h].face == kFront ? -kCullK : (r[h].face == kBack ? kCullK : 0.0f);
+                c[h] = rl_cull_factor(r[h].face);
                 float dd;
                 if (tag != kRlNoRay) {
+                    have_front |= r[h].face == kFront; have_back |= r[h].face == kBack; have_both |= r[h].face > kBack;
                     valid4 |= 1u << j;
                     if (ray_trusted(sc, r[h], dd)) trust4 |= 1u << j;
                     else if (ray_has_nan(r[h])) nan4 |= 1u << j;
@@ -324,6 +420,7 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
             cf[k] = p2_mul(p2_pack(c[0], c[1]), one2);
         }
         const bool warp_valid = __any_sync(kFullMask, valid4 != 0u);
+        const int mode = rl_block_mode(have_front, have_back, have_both);
 #pragma unroll 1
         for (uint32_t tile = 0; tile < n_tiles; ++tile) {
             const uint32_t buf = tile & 1u;
@@ -332,7 +429,7 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
             const float4* __restrict__ recs = sh.tile[buf];
             if (warp_valid) {                                       // warp-uniform: lanes without rays filter a dummy ray
                 uint32_t keep[4][2];
-                rl_filter_tile(recs, ox, oy, oz, dx, dy, dz, cf, A2, g, keep);
+                rl_filter_tile_mode(mode, RlRecShared{recs}, ox, oy, oz, dx, dy, dz, cf, As2, keep);
                 // untrusted rays without NaNs: the whole warp tests the tile for each of them (rl_coop_exact_tile)
                 const uint32_t coop4 = valid4 & ~trust4 & ~nan4;
 #pragma unroll 1
@@ -381,7 +478,8 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
                         rl_best_load(sh, j, tid, r, best);
                         const uint2 km = sh.mk[j][tid], cm = io.culled(sc, __float_as_uint(b.w), tile);
                         confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, make_uint2(km.x & ~cm.x, km.y & ~cm.y), trust),
-                                     trust, r, best, cs, recs);
+                                     trust, r, best, cs, sc.tri_exact + 4 * (size_t)(tile * kTileTris),
+                                     sc.tri_exact + 4 * (size_t)(tile * kTileTris));   // (the tile's plane rows are scaled: planes from the exact records)
                         rl_best_store(sh, j, tid, best);
                     }
                 }

@@ -565,6 +565,13 @@ __global__ void __launch_bounds__(TraceCfg<MODE>::kThreads, TraceCfg<MODE>::kMin
     }
 }
 
+// the public ray's enum fields, sanitised as the header states (out-of-range face = BOTH, out-of-range exclusion = none):
+// every cast path packs / compares them alike
+RT_DI void api_ray_fields(const DScene&, const b200rt_ray& in, DRay& r) {
+    r.face = min(in.face_direction, (uint32_t)kBoth); r.ex_face = min(in.exclude_face, (uint32_t)kBoth);
+    r.ex_prim = (in.exclude_prim < -1 || in.exclude_prim >= (1 << 28) - 1) ? -1 : in.exclude_prim;   // (28 bits in the packed ray)
+}
+
 // World::cast for a batch of rays (b200rt_intersect): one ray per lane, warp-collective two-phase cast.
 // This is K2, the intersection kernel on its own.
 template <int CAST>
@@ -584,8 +591,8 @@ __global__ void __launch_bounds__(128, 4) intersect_kernel(const DScene sc, cons
     r.o = mk3(0.f, 0.f, 0.f); r.d = mk3(0.f, 0.f, 1.f); r.face = kFront; r.ex_prim = -1; r.ex_face = kFront;
     if (active) {
         const b200rt_ray in = rays[i];
-        r.o = mk3(in.origin); r.d = mk3(in.direction); r.face = in.face_direction;
-        r.ex_prim = in.exclude_prim; r.ex_face = in.exclude_face;
+        r.o = mk3(in.origin); r.d = mk3(in.direction);
+        api_ray_fields(sc, in, r);
     }
     DHit h;
     h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
@@ -630,15 +637,20 @@ struct ApiRayIO {
     b200rt_hit* __restrict__ hits;
     RT_DI bool load(uint32_t idx, DRay& r, uint32_t& tag) const {
         const b200rt_ray in = rays[idx];
-        r.o = mk3(in.origin); r.d = mk3(in.direction); r.face = in.face_direction;
-        r.ex_prim = in.exclude_prim; r.ex_face = in.exclude_face;
+        r.o = mk3(in.origin); r.d = mk3(in.direction);
+        r.face = min(in.face_direction, (uint32_t)kBoth); r.ex_face = min(in.exclude_face, (uint32_t)kBoth);
+        r.ex_prim = (in.exclude_prim < -1 || in.exclude_prim >= (1 << 28) - 1) ? -1 : in.exclude_prim;
         tag = idx;
         return true;
     }
+    RT_DI void begin_block(uint32_t) const {}
     RT_DI uint32_t peek(uint32_t) const { return 0u; }
     RT_DI void prefetch(uint32_t) const {}
     RT_DI bool want_attrs(uint32_t) const { return true; }
+    RT_DI bool all_sphere_uv() const { return true; }     // the public Hit carries uv for every primitive (main.rs:305-313)
     RT_DI uint2 culled(const DScene&, uint32_t, uint32_t) const { return make_uint2(0u, 0u); }
+    RT_DI uint32_t cull_class(uint32_t) const { return 0u; }
+    RT_DI uint2 cull_mask(const DScene&, uint32_t) const { return make_uint2(0u, 0u); }
     RT_DI void store(uint32_t tag, const DHit& h) const {
         b200rt_hit o;
         o.prim_id = h.prim;
@@ -653,7 +665,8 @@ struct ApiRayIO {
     }
 };
 }  // namespace
-__global__ void __launch_bounds__(kRlThreads, INTERSECT_RL_MIN_BLOCKS) intersect_rl_kernel(const DScene sc, const b200rt_ray* __restrict__ rays,
+__global__ void __launch_bounds__(kRlThreads, INTERSECT_RL_MIN_BLOCKS) intersect_rl_kernel(const DScene sc, const __grid_constant__ RlTileParam tp,
+                                                                                          const b200rt_ray* __restrict__ rays,
                                                                                           uint32_t n, b200rt_hit* __restrict__ hits,
                                                                                           DCounters* __restrict__ cnt) {
     __shared__ RlShared sh;
@@ -661,7 +674,7 @@ __global__ void __launch_bounds__(kRlThreads, INTERSECT_RL_MIN_BLOCKS) intersect
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
     const ApiRayIO io{rays, hits};
-    cast_rays_in_lanes<false>(sc, io, n, sh, cs);
+    cast_rays_in_lanes<false>(sc, tp, io, n, sh, cs);
     if (cnt) {
         unsigned long long n_casts = cs.casts, n_conf = cs.confirms, n_fb = cs.fallbacks;
 #pragma unroll
@@ -771,7 +784,7 @@ cudaError_t launch_intersect(const DScene& sc, const b200rt_ray* d_rays, size_t 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sc.n_tris_padded == (uint32_t)kTileTris) {
             const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * INTERSECT_RL_MIN_BLOCKS, (n + 511) / 512);
-            intersect_rl_kernel<<<grid, kRlThreads, 0, stream>>>(sc, d_rays, (uint32_t)n, d_hits, d_cnt);
+            intersect_rl_kernel<<<grid, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, d_rays, (uint32_t)n, d_hits, d_cnt);
         } else {   // larger scenes: the tiles stream through shared memory (TMA)
             const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * 5, (n + 511) / 512);
             intersect_rl_tiled_kernel<<<grid, kRlThreads, 0, stream>>>(sc, d_rays, (uint32_t)n, d_hits, d_cnt);

@@ -15,11 +15,28 @@
 //   tri_attr[4*i + 0..3]    {n0.xyz, uv0.x} {n1.xyz, uv0.y} {n2.xyz, uv1.x} {uv1.y, uv2.x, uv2.y, 0}
 //        Read once per cast, for the winning triangle only (normal / uv interpolation).
 //   sph[j]                  {c.xyz, r}     sph_obj[j] = object index
+//   tri_filter_plain[4*i + 0..3]   the rays-in-lanes filter records, one triangle after the other (tiles stream through
+//        shared memory):  {n.xyz, d} * 2^-108   {m_p.xyz, w_p}   {m_q.xyz, w_q}   {a, b, c, 0}
+//        * the plane row is SCALED by 2^-108 (exact): n.dir comes out as nd 2^-108, which is subnormal exactly when
+//          |n.dir| < g = 2^-18; rcp.approx.ftz flushes a subnormal input to zero and returns +-inf, every estimate of the
+//          pair turns inf / NaN and the pair is kept - the filter's near-parallel guard costs no instruction.  t = num / nd
+//          is unchanged (both scaled), the slack A |1/nd| uses filter_As = A 2^-108.
+//        * the signed distance to the third (the LONGEST) edge follows from the other two, L_p e_p + L_q e_q + L_r e_r =
+//          2 Area for every point: e_r = c - a e_p - b e_q with a = L_p / L_r <= 1, b = L_q / L_r <= 1 (2 packed FMAs
+//          instead of 3; slack folded into c).
+//   RlTileParam (scenes of one tile)   the same 16 numbers per triangle, multipliers and addends apart, handed to the cast
+//        kernels as a KERNEL PARAMETER (constant bank): {n.xyz 2^-108, m_p.x} {m_p.yz, m_q.xy} {m_q.z, a, b, 0} and
+//        {d 2^-108, w_p, w_q, c}.  The multipliers reach the FFMA2s through uniform registers (LDCU -> FFMA2 R, R, UR, R):
+//        no shared-memory loads in the loop and one vector-register operand less per instruction.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "b200rt.h"
+
+// Measured alternatives of the rays-in-lanes filter loop that are NOT built (B200, cast of a 16-epoch 4K batch):
+// a slack A|r|(1 + |r|) instead of the near-parallel guard widened the band around every triangle at grazing incidence,
+// the nearest candidate then failed its exact test and the certified select fell back ten times as often (96.2 ms vs 90.1).
 
 namespace b200rt {
 
@@ -62,6 +79,8 @@ struct DScene {
     uint32_t n_tris_padded;  // tri_filter is padded to a multiple of kTileTris (padding is masked off)
     float origin_bound;      // filter slack was derived for ray origins with |o| <= origin_bound
     float filter_A;          // slack per unit |1/(n.dir)|   (64u * 2S)
+    float filter_As;         // filter_A * 2^-108: the same slack against the scaled plane rows of the rays-in-lanes records
+    const struct RlTileParam* h_tile0;   // HOST pointer (launchers only): tile 0 of the scene as a kernel parameter
     float filter_g;          // |n.dir| below this always passes the filter (2^-18)
 };
 
@@ -92,6 +111,12 @@ struct DCounters {  // device-side statistics, one 64-bit atomic per CTA at kern
 };
 
 constexpr int kTileTris = 64;  // triangles per shared-memory tile (64 x 64 B = 4 KB)
+constexpr float kRlPlaneScale = 3.0814879110195774e-33f;   // 2^-108: g * 2^-108 = 2^-126, the smallest normal f32
+
+// tile 0 of a scene as a kernel parameter (see the layout notes above): 4 KB in the constant bank
+struct RlTileParam {
+    float4 rec[4 * kTileTris];
+};
 
 // launchers (rt_kernels.cu)
 cudaError_t launch_whitted(const DScene& sc, const DCamera& cam, const DParams& p, float* d_rgb, int32_t* d_prim,

@@ -279,13 +279,26 @@ namespace {
 struct WfRayIO {
     WfBuffers wb;
     WfWork work;
+    // the list the current 128-ray block lies in (lists are padded to whole blocks: warp-uniform, set by begin_block)
+    const uint32_t* cur_list = nullptr;
+    uint32_t cur_first = 0u, cur_count = 0u, cur_slot = 0u;
+    RT_DI void begin_block(uint32_t base) {
+        const uint32_t block = base >> 7;
+        const uint32_t k = (block >= work.first_block[1] ? 1u : 0u) + (block >= work.first_block[2] ? 1u : 0u) +
+                           (block >= work.first_block[3] ? 1u : 0u) + (block >= work.first_block[4] ? 1u : 0u);
+        cur_slot = k;
+        cur_first = (k == 0u ? work.first_block[0] : k == 1u ? work.first_block[1] : k == 2u ? work.first_block[2] : k == 3u ? work.first_block[3] : work.first_block[4]) * 128u;
+        cur_count = k == 0u ? work.count[0] : k == 1u ? work.count[1] : k == 2u ? work.count[2] : k == 3u ? work.count[3] : work.count[4];
+        cur_list = work.lists + (size_t)k * work.n;
+    }
     RT_DI bool load(uint32_t idx, DRay& r, uint32_t& tag) const {
-        const uint32_t item = work.item(idx);
-        if (item == 0xffffffffu) return false;
-        const PathMem pm{wb.st, wb.req, item >> 3};
-        if ((item & 7u) == 0u) pm.get_ray(r);
-        else pm.get_shadow_ray((item & 7u) - 1u, r);
-        tag = item;
+        const uint32_t i = idx - cur_first;
+        if (i >= cur_count) return false;                    // padding of the list
+        const uint32_t pid = cur_list[i];
+        const PathMem pm{wb.st, wb.req, pid};
+        if (cur_slot == 0u) pm.get_ray(r);
+        else pm.get_shadow_ray(cur_slot - 1u, r);
+        tag = (pid << 3) | cur_slot;
         return true;
     }
     RT_DI uint32_t peek(uint32_t idx) const { return work.item(idx); }
@@ -299,11 +312,18 @@ struct WfRayIO {
         }
     }
     RT_DI bool want_attrs(uint32_t tag) const { return (tag & 7u) == 0u; }   // shadow rays: main.rs:435-447
+    RT_DI bool all_sphere_uv() const { return false; }                       // uv of a sphere hit only where a material reads it
     // shadow slot s of a one-chunk scene is light s: a directional light's shadow ray culls the same triangles everywhere
     RT_DI uint2 culled(const DScene& sc, uint32_t tag, uint32_t tile) const {
         const uint32_t slot = tag & 7u;
         if (slot == 0u || sc.shadow_cull == nullptr) return make_uint2(0u, 0u);
         return sc.shadow_cull[(size_t)(slot - 1u) * (sc.n_tris_padded / kTileTris) + tile];
+    }
+    // one-tile scenes: the class of a ray is its slot, the masks are copied to shared memory once per CTA
+    RT_DI uint32_t cull_class(uint32_t tag) const { return tag & 7u; }
+    RT_DI uint2 cull_mask(const DScene& sc, uint32_t cls) const {
+        if (cls == 0u || cls > 4u || sc.shadow_cull == nullptr || cls > sc.n_lights) return make_uint2(0u, 0u);
+        return sc.shadow_cull[(size_t)(cls - 1u) * (sc.n_tris_padded / kTileTris)];
     }
     RT_DI void store(uint32_t tag, const DHit& h) const {
         const uint32_t pid = tag >> 3, slot = tag & 7u;
@@ -317,7 +337,8 @@ struct WfRayIO {
     }
 };
 }  // namespace
-__global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf,
+__global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_kernel(const DScene sc, const __grid_constant__ RlTileParam tp,
+                                                                                      const WfBuffers wb, const uint32_t buf,
                                                                                       DCounters* __restrict__ cnt) {
     __shared__ RlShared sh;
     const uint32_t lane = threadIdx.x & 31u;
@@ -327,8 +348,9 @@ __global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_
     if (n_work == 0u) return;
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
-    const WfRayIO io{wb, wk};
-    cast_rays_in_lanes<WF_CAST_RL_PREFETCH != 0>(sc, io, wk.n_virtual(), sh, cs);
+    WfRayIO io;
+    io.wb = wb; io.work = wk;
+    cast_rays_in_lanes<WF_CAST_RL_PREFETCH != 0>(sc, tp, io, wk.n_virtual(), sh, cs);
     if (cnt) {
         unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
 #pragma unroll
@@ -361,7 +383,8 @@ __global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_TILED_MIN_BLOCKS) wf_ca
     if (n_work == 0u) return;
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
-    const WfRayIO io{wb, wk};
+    WfRayIO io;
+    io.wb = wb; io.work = wk;
     cast_rays_in_lanes_tiled(sc, io, wk.n_virtual(), sh, cs);
     if (cnt) {
         unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
@@ -992,7 +1015,7 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                 cudaEventRecord(ev_a, stream);
             }
             if (rays_in_lanes) {
-                wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
+                wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, wb, buf, d_cnt);
             } else if (rays_in_lanes_tiled) {
                 wf_cast_rl_tiled_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
             } else {

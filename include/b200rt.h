@@ -13,9 +13,10 @@
  *   - caller owns every host buffer; the library owns device memory.  `*_device` variants take
  *     device pointers that the caller (e.g. a torch tensor) owns and enqueue on `cuda_stream`
  *     (a cudaStream_t; NULL = the CUDA default stream) without synchronising.
- *   - one context per host thread and per GPU.  Multi-GPU = one process (context) per GPU; rows
- *     or epochs are sharded by the caller through b200rt_params.row_begin/row_count and the
- *     epoch_begin/epoch_count arguments.
+ *   - one context per host thread and per GPU.  Multi-GPU: a b200rt_group (below) shards a frame over
+ *     the GPUs of one process or over one rank per process and reduces / gathers on rank 0 with NCCL;
+ *     a caller can also shard by hand through b200rt_params.row_begin/row_count and the
+ *     epoch_begin/epoch_count arguments of the single-GPU entry points.
  *   - there is no CPU fallback: without a CUDA device b200rt_create fails with B200RT_ERR_NO_DEVICE.
  *   - primitive ids (reference PrimitiveIndex, primitives.rs:31-34) are int32:
  *       triangle i -> i, sphere j -> n_triangles + j, miss -> -1   (reference iteration order,
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B200RT_VERSION 1
+#define B200RT_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------------ */
 enum {
@@ -41,7 +42,8 @@ enum {
     B200RT_ERR_NO_SCENE = -3,   /* render/intersect before b200rt_upload_scene                 */
     B200RT_ERR_NO_DEVICE = -4,  /* no usable CUDA device: there is no CPU fallback            */
     B200RT_ERR_IO = -5,         /* OBJ file could not be read / parsed (reference: main.rs:785) */
-    B200RT_ERR_UNSUPPORTED = -6 /* e.g. recursion depth above B200RT_MAX_DEPTH                 */
+    B200RT_ERR_UNSUPPORTED = -6,/* e.g. recursion depth above B200RT_MAX_DEPTH                 */
+    B200RT_ERR_NCCL = -7        /* device groups: libnccl.so.2 missing or an NCCL call failed; b200rt_group_last_error() */
 };
 
 /* ---- scene PODs: 1:1 with the reference's Rust types -------------------------------------- */
@@ -187,8 +189,6 @@ typedef struct b200rt_stats {
     float logic_kernel_ms;         /* sum over the shading / scatter kernels between them         */
     uint32_t cast_kernel_launches;
     uint32_t kernel_launches;      /* kernels launched by the last render call (always counted) */
-    float filter_kernel_ms;        /* always 0 (the split filter / owner cast of round 1 was removed; kept for layout) */
-    uint32_t reserved;
 } b200rt_stats;
 
 typedef struct b200rt_ctx b200rt_ctx;
@@ -243,7 +243,10 @@ int b200rt_encode_srgb8_device(b200rt_ctx* ctx, const float* d_rgb, size_t n_val
  * target's directory and renamed over `path` (a reader never sees a partial file).  Host-only: no context, no GPU. */
 int b200rt_write_png_rgb8(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height);
 
-/* World::cast, main.rs:180-326, for n rays. */
+/* World::cast, main.rs:180-326, for n rays.  face_direction / exclude_face must be B200RT_FACE_* and exclude_prim in
+ * [-1, 2^28 - 2] (-1 = no exclusion; an id beyond the scene's primitives never matches, as in the reference): the
+ * host-buffer entry returns B200RT_ERR_INVALID otherwise; the _device entry cannot look at the rays and treats an
+ * out-of-range face as BOTH and an out-of-range exclusion as none. */
 int b200rt_intersect(b200rt_ctx* ctx, const b200rt_ray* rays, size_t n, uint32_t cast_mode,
                      b200rt_hit* hits);
 int b200rt_intersect_device(b200rt_ctx* ctx, const b200rt_ray* d_rays, size_t n, uint32_t cast_mode,
@@ -259,14 +262,50 @@ int b200rt_reset_stats(b200rt_ctx* ctx);
  * TFLOP/s (2 flop per FFMA lane) — the live denominator bench.py reports beside the nominal one. */
 int b200rt_measure_fp32_peak(b200rt_ctx* ctx, double* tflops, double* sm_mhz_effective);
 
-/* K2 micro-benchmark: the ray x triangle filter loop of the two-phase cast in isolation (one 64-triangle
- * shared-memory tile, `iters` passes per ray).  variant 0 = scalar FFMA, 1 = FFMA2 over triangle pairs,
- * 2 / 3 = FFMA2 over ray pairs with 2 / 4 rays per thread.  Returns the kernel time and pair-test count. */
-int b200rt_filter_bench(b200rt_ctx* ctx, int variant, int blocks_per_sm, int iters, float* kernel_ms,
-                        uint64_t* pair_tests);
-
-/* Pipe calibration loops (dev tool): returns warp-instructions per clock per SM sub-partition at sm_mhz. */
-int b200rt_pipe_bench(b200rt_ctx* ctx, int variant, float* kernel_ms, double* inst_per_clk_per_smsp);
+/* ---- device groups: one frame over several GPUs --------------------------------- */
+/* The reference's render loop is host code (main.rs:1086-1173); its pixel samples are independent, so a group shards
+ * them without any exchange in the data path:
+ *   epochs (stochastic pass, main.rs:1129): rank g renders epochs [g*E/G, (g+1)*E/G) of the full frame into its own
+ *          PhotonAccumulator buffer; ONE ncclReduce(sum) to rank 0 over NVLink ends the render;
+ *   rows   (Whitted pass, main.rs:1090): rank g renders rows [g*H/G, (g+1)*H/G) of the requested band; the disjoint
+ *          bands are gathered on rank 0 (ncclSend / ncclRecv): bitwise the single-GPU frame.
+ * A group is every GPU of ONE process (b200rt_group_create: ncclCommInitAll; the library runs one host thread per
+ * device while a render is in flight) or ONE RANK per process (b200rt_group_create_rank: ncclCommInitRank with an id
+ * from b200rt_group_unique_id on rank 0 that the host program hands to every rank).  Calls are collective: every rank
+ * makes the same call with the same camera / params / epoch range.  Results land on rank 0 only; they are FRESH
+ * frames (accumulators start at zero on the devices: nothing but the arguments travels host -> device).
+ * NCCL (libnccl.so.2) is loaded at run time by the first group call; groups of one GPU do not need it. */
+typedef struct b200rt_group b200rt_group;
+#define B200RT_GROUP_ID_BYTES 128
+int b200rt_group_create(const int* device_ids, int n_devices, b200rt_group** out_group);
+int b200rt_group_unique_id(void* id_out, size_t id_bytes);                    /* id_bytes >= B200RT_GROUP_ID_BYTES */
+int b200rt_group_create_rank(int device_id, int rank, int n_ranks, const void* unique_id, size_t id_bytes,
+                             b200rt_group** out_group);
+int b200rt_group_destroy(b200rt_group* group);
+int b200rt_group_size(const b200rt_group* group, int* n_ranks, int* n_local);
+/* the context of local member `local_index` (stats, device info); owned by the group */
+int b200rt_group_ctx(b200rt_group* group, int local_index, b200rt_ctx** out_ctx);
+const char* b200rt_group_last_error(const b200rt_group* group);
+int b200rt_group_upload_scene(b200rt_group* group, const b200rt_scene* scene);   /* replicated on every member */
+/* out_accum = [h][w][4] {sum.rgb, weight_sum} on the process that holds rank 0 (ignored elsewhere, may be NULL). */
+int b200rt_group_render_distributed(b200rt_group* group, const b200rt_camera* cam, const b200rt_params* params,
+                                    uint32_t epoch_begin, uint32_t epoch_count, float* out_accum);
+/* d_accum_root: device buffer on rank 0's GPU that receives the reduced frame (NULL elsewhere); synchronous. */
+int b200rt_group_render_distributed_device(b200rt_group* group, const b200rt_camera* cam, const b200rt_params* params,
+                                           uint32_t epoch_begin, uint32_t epoch_count, float* d_accum_root);
+/* The same frame sharded by ROWS instead (every rank renders all the epochs of its band; the bands are gathered on rank
+ * 0): the split for frames of few epochs, e.g. the 10 M one-sample "photons" of a 4000 x 2500 frame. */
+int b200rt_group_render_distributed_rows(b200rt_group* group, const b200rt_camera* cam, const b200rt_params* params,
+                                         uint32_t epoch_begin, uint32_t epoch_count, float* out_accum);
+int b200rt_group_render_distributed_rows_device(b200rt_group* group, const b200rt_camera* cam, const b200rt_params* params,
+                                                uint32_t epoch_begin, uint32_t epoch_count, float* d_accum_root);
+/* out_rgb = [h][w][3], out_prim_id = [h][w] (only with want_prim_ids, which every rank passes alike), on rank 0. */
+int b200rt_group_render_whitted(b200rt_group* group, const b200rt_camera* cam, const b200rt_params* params,
+                                float* out_rgb, int32_t* out_prim_id, int want_prim_ids);
+int b200rt_group_render_whitted_device(b200rt_group* group, const b200rt_camera* cam, const b200rt_params* params,
+                                       float* d_rgb_root);
+/* device time of the last group render on the slowest local member, render + collective, without the D2H copy */
+int b200rt_group_last_render_ms(const b200rt_group* group, float* ms);
 
 /* ---- host-side scene construction (World builder; no GPU needed) --------------------------- */
 /* Mirrors World::new / push_object / ObjectProxy::push_triangle(s) / push_sphere / push_light

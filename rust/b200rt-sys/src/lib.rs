@@ -12,6 +12,7 @@ pub const B200RT_ERR_NO_SCENE: c_int = -3;
 pub const B200RT_ERR_NO_DEVICE: c_int = -4; // there is no CPU fallback
 pub const B200RT_ERR_IO: c_int = -5;
 pub const B200RT_ERR_UNSUPPORTED: c_int = -6;
+pub const B200RT_ERR_NCCL: c_int = -7; // device groups only
 
 pub const B200RT_FACE_FRONT: u32 = 0; // FaceDirection, main.rs:52-66
 pub const B200RT_FACE_BACK: u32 = 1;
@@ -173,12 +174,12 @@ pub struct b200rt_stats {
     pub logic_kernel_ms: f32,
     pub cast_kernel_launches: u32,
     pub kernel_launches: u32,
-    pub filter_kernel_ms: f32,
-    pub reserved: u32,
 }
 
 /// opaque: one context per host thread and GPU
 pub enum b200rt_ctx {}
+/// opaque: a device group (several GPUs render one frame; NCCL inside the library)
+pub enum b200rt_group {}
 /// opaque: the host-side `World` builder (main.rs:161-178, 705-746, 778-807)
 pub enum b200rt_world {}
 
@@ -216,6 +217,30 @@ extern "C" {
     pub fn b200rt_get_stats(ctx: *mut b200rt_ctx, out: *mut b200rt_stats) -> c_int;
     pub fn b200rt_reset_stats(ctx: *mut b200rt_ctx) -> c_int;
     pub fn b200rt_set_kernel_timing(ctx: *mut b200rt_ctx, enabled: c_int) -> c_int;
+
+    // device groups: the epoch loop of main.rs:1129-1173 (or the rows of main.rs:1090) sharded over GPUs, reduced on rank 0
+    pub fn b200rt_group_create(device_ids: *const c_int, n_devices: c_int, out_group: *mut *mut b200rt_group) -> c_int;
+    pub fn b200rt_group_unique_id(id_out: *mut c_void, id_bytes: usize) -> c_int;
+    pub fn b200rt_group_create_rank(device_id: c_int, rank: c_int, n_ranks: c_int, unique_id: *const c_void, id_bytes: usize,
+                                    out_group: *mut *mut b200rt_group) -> c_int;
+    pub fn b200rt_group_destroy(group: *mut b200rt_group) -> c_int;
+    pub fn b200rt_group_size(group: *const b200rt_group, n_ranks: *mut c_int, n_local: *mut c_int) -> c_int;
+    pub fn b200rt_group_ctx(group: *mut b200rt_group, local_index: c_int, out_ctx: *mut *mut b200rt_ctx) -> c_int;
+    pub fn b200rt_group_last_error(group: *const b200rt_group) -> *const c_char;
+    pub fn b200rt_group_upload_scene(group: *mut b200rt_group, scene: *const b200rt_scene) -> c_int;
+    pub fn b200rt_group_render_distributed(group: *mut b200rt_group, cam: *const b200rt_camera, params: *const b200rt_params,
+                                           epoch_begin: u32, epoch_count: u32, out_accum: *mut f32) -> c_int;
+    pub fn b200rt_group_render_distributed_device(group: *mut b200rt_group, cam: *const b200rt_camera, params: *const b200rt_params,
+                                                  epoch_begin: u32, epoch_count: u32, d_accum_root: *mut f32) -> c_int;
+    pub fn b200rt_group_render_distributed_rows(group: *mut b200rt_group, cam: *const b200rt_camera, params: *const b200rt_params,
+                                                epoch_begin: u32, epoch_count: u32, out_accum: *mut f32) -> c_int;
+    pub fn b200rt_group_render_distributed_rows_device(group: *mut b200rt_group, cam: *const b200rt_camera, params: *const b200rt_params,
+                                                       epoch_begin: u32, epoch_count: u32, d_accum_root: *mut f32) -> c_int;
+    pub fn b200rt_group_render_whitted(group: *mut b200rt_group, cam: *const b200rt_camera, params: *const b200rt_params,
+                                       out_rgb: *mut f32, out_prim_id: *mut i32, want_prim_ids: c_int) -> c_int;
+    pub fn b200rt_group_render_whitted_device(group: *mut b200rt_group, cam: *const b200rt_camera, params: *const b200rt_params,
+                                              d_rgb_root: *mut f32) -> c_int;
+    pub fn b200rt_group_last_render_ms(group: *const b200rt_group, ms: *mut f32) -> c_int;
 
     // the builder surface for hosts without the Rust World (the reference crate lowers its own World instead)
     pub fn b200rt_world_new() -> *mut b200rt_world;

@@ -78,6 +78,42 @@ def load():
     return lib
 
 
+class GoldenFixture:
+    """The reference's scene literal, camera and default parameters from tests/golden/fixture_scene.npz: plain ctypes
+    records backed by numpy arrays — libb200rt.so is not loaded (bench.py's reference arm runs the oracle only)."""
+
+    def __init__(self):
+        z = np.load(os.path.join(ROOT, "tests", "golden", "fixture_scene.npz"))
+        self._keep = {k: np.ascontiguousarray(z[k]) for k in ("triangles", "spheres", "materials", "lights")}
+        s = b.Scene()
+        for name, typ, ptr_field, n_field in (("triangles", b.Triangle, "triangles", "n_triangles"),
+                                              ("spheres", b.Sphere, "spheres", "n_spheres"),
+                                              ("materials", b.Material, "materials", "n_materials"),
+                                              ("lights", b.Light, "lights", "n_lights")):
+            arr = self._keep[name]
+            setattr(s, ptr_field, C.cast(arr.ctypes.data, C.POINTER(typ)))
+            setattr(s, n_field, arr.size // C.sizeof(typ))
+        self.scene = s
+        self.camera = b.Camera.from_buffer_copy(z["camera"].tobytes())
+        self._params = z["params"].tobytes()
+
+    def params(self, **overrides):
+        p = b.Params.from_buffer_copy(self._params)
+        for k, v in overrides.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        return p
+
+
+def host_threads() -> int:
+    """Host cores this process may run on (torchrun exports OMP_NUM_THREADS=1: not what omp_get_max_threads says)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def f3(v):
     return (C.c_float * 3)(*[float(x) for x in v])
 

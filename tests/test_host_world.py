@@ -127,3 +127,20 @@ def test_obj_errors(b200rt, tmp_path):
         o.load_obj(str(empty))
     lib = b200rt.load_library()
     assert lib.b200rt_world_push_sphere(w._h, 99, (C.c_float * 3)(0, 0, 0), 1.0) == b200rt.ERR_INVALID   # unknown object
+
+
+def test_golden_fixture_scene_equals_the_builder(b200rt, fixture_world):
+    """tests/golden/fixture_scene.npz (what bench.py's reference arm renders, without loading libb200rt.so) is the
+    scene literal of main.rs:810-1075 as World.fixture() builds it, byte for byte; same camera and defaults."""
+    import ctypes as C
+    import oracle_binding as ob
+    g = ob.GoldenFixture()
+    s, t = fixture_world.scene(), g.scene
+    for n_field, ptr_field, typ in (("n_triangles", "triangles", b200rt.Triangle), ("n_spheres", "spheres", b200rt.Sphere),
+                                    ("n_materials", "materials", b200rt.Material), ("n_lights", "lights", b200rt.Light)):
+        n = getattr(s, n_field)
+        assert n == getattr(t, n_field), n_field
+        assert C.string_at(getattr(s, ptr_field), n * C.sizeof(typ)) == C.string_at(getattr(t, ptr_field), n * C.sizeof(typ)), ptr_field
+    assert bytes(g.camera) == bytes(b200rt.fixture_camera())
+    assert bytes(g.params()) == bytes(b200rt.default_params())
+    assert g.params(width=64).width == 64

@@ -16,4 +16,5 @@ flops = s["tri_pair_tests"] * 36.0 + s["sph_pair_tests"] * 28.0
 peak = 148 * 128 * 2 * 1.965e9
 print(os.environ.get("B200RT_LIB", "default"), os.environ.get("B200RT_WF_CAST", "default"),
       f"total {s['kernel_ms']:.1f} cast {s['cast_kernel_ms']:.1f} logic {s['logic_kernel_ms']:.1f}",
-      f"| cast roofline {flops / (s['cast_kernel_ms'] * 1e-3) / peak:.3f}", flush=True)
+      f"| cast roofline {flops / (s['cast_kernel_ms'] * 1e-3) / peak:.3f}",
+      f"| exact/cast {s['exact_confirms'] / max(s['casts'], 1):.3f} fallback/cast {s['certify_fallbacks'] / max(s['casts'], 1):.5f} casts {s['casts']}", flush=True)
