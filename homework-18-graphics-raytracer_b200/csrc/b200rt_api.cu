@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -265,6 +266,7 @@ int b200rt_create(int device_id, b200rt_ctx** out_ctx) {
         return B200RT_ERR_NO_DEVICE;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    // (cudaLimitMaxL2FetchGranularity = 32 / 64 / 128 was measured on B200 in round 2: no effect on any kernel of the tracer.)
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device_id);
     ctx->sm_clock_khz = khz;

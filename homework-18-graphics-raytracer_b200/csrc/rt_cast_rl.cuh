@@ -14,9 +14,11 @@
 // back from a per-thread shared-memory slot (no dynamically indexed register arrays, no local memory).
 //
 // IO (a small struct, by value) connects the loop to its rays and results:
-//     bool     load(uint32_t idx, DRay& r, uint32_t& tag)   ray of work index idx (idx < n_work); tag travels to store()
-//     uint32_t peek(uint32_t idx)                            the handle (!= kRlNoRay) prefetch() wants for work index idx
-//     void     prefetch(uint32_t handle)                     hint: the ray behind the handle is loaded in the lane's next block
+//     void     begin_block(uint32_t base)                   the warp is about to load work indices [base, base + 128)
+//     uint32_t item(uint32_t idx)                           the tag of work index idx (idx < n_work), kRlNoRay for an empty slot
+//     void     fetch(uint32_t tag, DRay& r)                 the ray behind a tag; the tag travels to store().  A block's four
+//                                                           item() loads are issued before its fetch()es: two round trips to
+//                                                           memory per block instead of eight
 //     bool     want_attrs(uint32_t tag)                      false: only "is there a hit, and how far" is needed
 //     uint2    culled(const DScene&, uint32_t tag, uint32_t tile)   triangles of the tile this ray is known to cull
 //     void     store(uint32_t tag, const DHit& h)
@@ -141,7 +143,7 @@ RT_DI int rl_block_mode(uint32_t have_front, uint32_t have_back, uint32_t have_b
 // CTA-collective (kRlThreads threads): casts rays [0, n_work) of `io`, 128 rays per warp and iteration, work split over
 // the whole grid.  Call once per kernel; n_work may be 0.  The scene's one tile (filter, exact and attribute records), its
 // spheres and the IO's classes of statically culled triangles are copied to shared memory once per CTA.
-template <bool PREFETCH, class IO>
+template <class IO>
 RT_DI void cast_rays_in_lanes(const DScene& sc, const RlTileParam& tp, IO io, const uint32_t n_work, RlShared& sh, CastStats& cs) {
     const uint32_t lane = threadIdx.x & 31u, tid = threadIdx.x;
     if (n_work == 0u) return;
@@ -162,7 +164,6 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, const RlTileParam& tp, IO io, co
     // register pair (a plain pack is coalesced with the LDG.128 destination quads and re-packed inside the loop)
     const P2 one2 = p2_bc(__fmaf_rn(sc.filter_g, 0.0f, 1.0f));
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    const uint32_t stride = warps_total * 128u;
     // (n_work + stride may exceed 2^32: the block loop counts blocks, not indices)
     const uint32_t n_blocks = (n_work + 127u) / 128u;
     for (uint32_t blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < n_blocks; blk += warps_total) {
@@ -171,17 +172,36 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, const RlTileParam& tp, IO io, co
         // this lane's four rays: work indices base + lane + 32 j
         P2 ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], cf[2];
         uint32_t trust4 = 0u, have_front = 0u, have_back = 0u, have_both = 0u;
+        uint32_t tags[4];
+        DRay rays4[4];
+#ifdef RL_SEQ_LOAD
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t idx = base + lane + 32u * (uint32_t)j;
+            tags[j] = idx < n_work ? io.item(idx) : kRlNoRay;
+            rays4[j].o = mk3(0.f, 0.f, 0.f); rays4[j].d = mk3(0.f, 0.f, 1.f); rays4[j].face = kFront; rays4[j].ex_prim = -1; rays4[j].ex_face = kFront;
+            if (tags[j] != kRlNoRay) io.fetch(tags[j], rays4[j]);
+        }
+#else
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t idx = base + lane + 32u * (uint32_t)j;
+            tags[j] = idx < n_work ? io.item(idx) : kRlNoRay;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            rays4[j].o = mk3(0.f, 0.f, 0.f); rays4[j].d = mk3(0.f, 0.f, 1.f); rays4[j].face = kFront; rays4[j].ex_prim = -1; rays4[j].ex_face = kFront;
+            if (tags[j] != kRlNoRay) io.fetch(tags[j], rays4[j]);
+        }
+#endif
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            DRay r[2];
+            DRay (&r)[2] = reinterpret_cast<DRay (&)[2]>(rays4[2 * k]);
             float c[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * k + h;
-                const uint32_t idx = base + lane + 32u * (uint32_t)j;
-                r[h].o = mk3(0.f, 0.f, 0.f); r[h].d = mk3(0.f, 0.f, 1.f); r[h].face = kFront; r[h].ex_prim = -1; r[h].ex_face = kFront;
-                uint32_t tag = kRlNoRay;
-                if (idx < n_work && !io.load(idx, r[h], tag)) tag = kRlNoRay;
+                const uint32_t tag = tags[j];
                 c[h] = rl_cull_factor(r[h].face);
                 if (tag != kRlNoRay) {
                     have_front |= r[h].face == kFront; have_back |= r[h].face == kBack; have_both |= r[h].face > kBack;
@@ -198,16 +218,6 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, const RlTileParam& tp, IO io, co
             cf[k] = p2_mul(p2_pack(c[0], c[1]), one2);
         }
         const int mode = rl_block_mode(have_front, have_back, have_both);
-        // the handles of this lane's NEXT four rays are fetched now, their rows are pulled into L2 after the filter loop
-        // (while phase 2 runs): the chain handle -> rows is two DRAM round trips otherwise
-        uint32_t next[4];
-        if (PREFETCH) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t idx = base + stride + lane + 32u * (uint32_t)j;
-                next[j] = (blk + warps_total < n_blocks && idx < n_work) ? io.peek(idx) : kRlNoRay;
-            }
-        }
         // phase 1: the candidate masks of this lane's four rays
         uint32_t keep[4][2];
         rl_filter_tile_mode(mode, RlRecParam{tp}, ox, oy, oz, dx, dy, dz, cf, As2, keep);
@@ -223,11 +233,6 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, const RlTileParam& tp, IO io, co
 #endif
 #pragma unroll
         for (int j = 0; j < 4; ++j) sh.mk[j][tid] = make_uint2(keep[j][0] & v_lo, keep[j][1] & v_hi);
-        if (PREFETCH) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (next[j] != kRlNoRay) io.prefetch(next[j]);
-        }
         // phase 2, ray by ray (every thread reads only its own slots: no barrier)
 #ifdef RL_DIAG_P2X2    // timing experiment: phase 2 twice (the first pass stores nothing)
 #pragma unroll 1
@@ -388,17 +393,26 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
         P2 ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], cf[2];
         uint32_t valid4 = 0u, trust4 = 0u, nan4 = 0u;   // nan4: rays with a NaN component (cast_nan_ray_triangles)
         uint32_t have_front = 0u, have_back = 0u, have_both = 0u;
+        uint32_t tags[4];
+        DRay rays4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t idx = base + lane + 32u * (uint32_t)j;
+            tags[j] = (base < n_work && idx < n_work) ? io.item(idx) : kRlNoRay;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            rays4[j].o = mk3(0.f, 0.f, 0.f); rays4[j].d = mk3(0.f, 0.f, 1.f); rays4[j].face = kFront; rays4[j].ex_prim = -1; rays4[j].ex_face = kFront;
+            if (tags[j] != kRlNoRay) io.fetch(tags[j], rays4[j]);
+        }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            DRay r[2];
+            DRay (&r)[2] = reinterpret_cast<DRay (&)[2]>(rays4[2 * k]);
             float c[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * k + h;
-                const uint32_t idx = base + lane + 32u * (uint32_t)j;
-                r[h].o = mk3(0.f, 0.f, 0.f); r[h].d = mk3(0.f, 0.f, 1.f); r[h].face = kFront; r[h].ex_prim = -1; r[h].ex_face = kFront;
-                uint32_t tag = kRlNoRay;
-                if (base < n_work && idx < n_work && !io.load(idx, r[h], tag)) tag = kRlNoRay;
+                const uint32_t tag = tags[j];
                 c[h] = rl_cull_factor(r[h].face);
                 float dd;
                 if (tag != kRlNoRay) {

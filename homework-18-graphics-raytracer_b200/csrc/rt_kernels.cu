@@ -635,17 +635,14 @@ namespace {
 struct ApiRayIO {
     const b200rt_ray* __restrict__ rays;
     b200rt_hit* __restrict__ hits;
-    RT_DI bool load(uint32_t idx, DRay& r, uint32_t& tag) const {
-        const b200rt_ray in = rays[idx];
+    RT_DI uint32_t item(uint32_t idx) const { return idx; }
+    RT_DI void fetch(uint32_t tag, DRay& r) const {
+        const b200rt_ray in = rays[tag];
         r.o = mk3(in.origin); r.d = mk3(in.direction);
         r.face = min(in.face_direction, (uint32_t)kBoth); r.ex_face = min(in.exclude_face, (uint32_t)kBoth);
         r.ex_prim = (in.exclude_prim < -1 || in.exclude_prim >= (1 << 28) - 1) ? -1 : in.exclude_prim;
-        tag = idx;
-        return true;
     }
     RT_DI void begin_block(uint32_t) const {}
-    RT_DI uint32_t peek(uint32_t) const { return 0u; }
-    RT_DI void prefetch(uint32_t) const {}
     RT_DI bool want_attrs(uint32_t) const { return true; }
     RT_DI bool all_sphere_uv() const { return true; }     // the public Hit carries uv for every primitive (main.rs:305-313)
     RT_DI uint2 culled(const DScene&, uint32_t, uint32_t) const { return make_uint2(0u, 0u); }
@@ -674,7 +671,7 @@ __global__ void __launch_bounds__(kRlThreads, INTERSECT_RL_MIN_BLOCKS) intersect
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
     const ApiRayIO io{rays, hits};
-    cast_rays_in_lanes<false>(sc, tp, io, n, sh, cs);
+    cast_rays_in_lanes(sc, tp, io, n, sh, cs);
     if (cnt) {
         unsigned long long n_casts = cs.casts, n_conf = cs.confirms, n_fb = cs.fallbacks;
 #pragma unroll

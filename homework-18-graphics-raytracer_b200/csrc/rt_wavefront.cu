@@ -27,6 +27,7 @@
 //   q   [2][6][n] path ids per consumer segment (double buffered by round parity)       48 B
 //   work[2][5][n] cast work: one list of path ids per ray slot (path ray, 4 shadow rays)  40 B
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdlib>
 #include <string>
 
@@ -60,7 +61,13 @@ static_assert(kStateRows == WF_STATE_ROWS, "state rows");
 static_assert(ROW_CTRL % 2 == 0 && ROW_RNG == ROW_CTRL + 1 && ROW_ACC % 2 == 0 && ROW_T == ROW_ACC + 1 && ROW_HPOS % 2 == 0 &&
               ROW_HNORMAL == ROW_HPOS + 1 && ROW_HDIR % 2 == 0 && ROW_HDIR0 == ROW_HDIR + 1 && ROW_PEND % 2 == 0 &&
               ROW_NADJ == ROW_PEND + 1 && ROW_HI_POS % 2 == 0 && ROW_SUM == ROW_HI_POS + 1, "rows that travel together share a sector");
+#if WF_REQ_HP
+enum : int { REQ_O = 0, REQ_D = 1, REQ_SD3 = 2, REQ_HP = 4, REQ_SD0 = 5 };
+RT_DI int req_shadow_row(uint32_t s) { return s < 3u ? REQ_SD0 + (int)s : REQ_SD3; }
+#else
 enum : int { REQ_O = 0, REQ_D = 1, REQ_SHADOW_D = 2 };
+RT_DI int req_shadow_row(uint32_t s) { return REQ_SHADOW_D + (int)s; }
+#endif
 
 // flags word of ROW_CTRL
 enum : uint32_t {
@@ -131,11 +138,20 @@ struct PathMem {
         r.o = mk3(a); r.d = mk3(b); r.face = m & 3u; r.ex_face = (m >> 2) & 3u; r.ex_prim = (int32_t)(m >> 4) - 1;
     }
     // .w: the spot light's angular factor, so that get_shade does not evaluate the light a second time
-    RT_DI void put_shadow_dir(uint32_t s, f3 d, float angular = 0.0f) const { req[(size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + s] = make_float4(d.x, d.y, d.z, angular); }
-    RT_DI float4 get_shadow_dir(uint32_t s) const { return req[(size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + s]; }
+    RT_DI void put_shadow_dir(uint32_t s, f3 d, float angular = 0.0f) const { req[(size_t)pid * WF_REQ_ROWS + req_shadow_row(s)] = make_float4(d.x, d.y, d.z, angular); }
+    RT_DI float4 get_shadow_dir(uint32_t s) const { return req[(size_t)pid * WF_REQ_ROWS + req_shadow_row(s)]; }
+#if WF_REQ_HP
+    // the origin / exclusion of the shadow rays: a copy of the current hit next to their directions
+    RT_DI void put_shadow_origin(f3 p, int32_t prim) const { req[(size_t)pid * WF_REQ_ROWS + REQ_HP] = make_float4(p.x, p.y, p.z, __int_as_float(prim)); }
+    RT_DI void put_req_pad() const { req[(size_t)pid * WF_REQ_ROWS + REQ_SD3 + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#endif
     // shadow ray of light slot s (main.rs:423-431): from the current hit, back faces only, the hit primitive excluded
     RT_DI void get_shadow_ray(uint32_t s, DRay& r) const {
-        const float4 a = ld(ROW_HPOS), b = req[(size_t)pid * WF_REQ_ROWS + REQ_SHADOW_D + s];
+#if WF_REQ_HP
+        const float4 a = req[(size_t)pid * WF_REQ_ROWS + REQ_HP], b = req[(size_t)pid * WF_REQ_ROWS + req_shadow_row(s)];
+#else
+        const float4 a = ld(ROW_HPOS), b = req[(size_t)pid * WF_REQ_ROWS + req_shadow_row(s)];
+#endif
         r.o = mk3(a); r.d = mk3(b); r.face = kBack; r.ex_prim = __float_as_int(a.w); r.ex_face = kBack;
     }
 };
@@ -268,9 +284,8 @@ __global__ void __launch_bounds__(128, WF_CAST_MIN_BLOCKS) wf_cast_kernel(const 
 // The work list of the round is the ray source: item = path << 3 | slot; slot 0 = the path ray, 1..4 = shadow rays whose
 // origin / exclusion is the path's current hit.  The items of the warp's NEXT block are re-read after the filter loop to
 // pull their rows into L2 while phase 2 runs (the chain work[] -> path -> rows is two DRAM round trips otherwise).
-#ifndef WF_CAST_RL_PREFETCH
-#define WF_CAST_RL_PREFETCH 1
-#endif
+// (A prefetch.global.L2 of the rows of the warp's next block while phase 2 runs was measured on B200 in round 2: 86.0 ms
+// per 16-epoch 4K batch with it, 78.5 without - it pulls whole 128-byte lines where the loads touch one 32-byte sector.)
 RT_DI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifndef WF_CAST_RL_MIN_BLOCKS
 #define WF_CAST_RL_MIN_BLOCKS 6   // measured on B200, cast of a 16-epoch 4K batch: 4 -> 108.1 ms, 5 -> 103.1, 6 -> 101.1 (latency-bound phase 2)
@@ -279,7 +294,10 @@ namespace {
 struct WfRayIO {
     WfBuffers wb;
     WfWork work;
-    // the list the current 128-ray block lies in (lists are padded to whole blocks: warp-uniform, set by begin_block)
+    // the list the current 128-ray block lies in (lists are padded to whole blocks: warp-uniform, set by begin_block).
+    // (Visiting the lists interleaved in groups, so that the slots of a path are cast close in time, was measured on B200
+    // in round 2: the DRAM traffic did not drop - the rows are over-fetched by DRAM granularity, not re-read - and the
+    // cast of a 16-epoch 4K batch took 94.7 ms instead of 81.3.)
     const uint32_t* cur_list = nullptr;
     uint32_t cur_first = 0u, cur_count = 0u, cur_slot = 0u;
     RT_DI void begin_block(uint32_t base) {
@@ -291,25 +309,14 @@ struct WfRayIO {
         cur_count = k == 0u ? work.count[0] : k == 1u ? work.count[1] : k == 2u ? work.count[2] : k == 3u ? work.count[3] : work.count[4];
         cur_list = work.lists + (size_t)k * work.n;
     }
-    RT_DI bool load(uint32_t idx, DRay& r, uint32_t& tag) const {
+    RT_DI uint32_t item(uint32_t idx) const {
         const uint32_t i = idx - cur_first;
-        if (i >= cur_count) return false;                    // padding of the list
-        const uint32_t pid = cur_list[i];
-        const PathMem pm{wb.st, wb.req, pid};
+        return i < cur_count ? (cur_list[i] << 3) | cur_slot : 0xffffffffu;     // (padding of the list: no ray)
+    }
+    RT_DI void fetch(uint32_t tag, DRay& r) const {
+        const PathMem pm{wb.st, wb.req, tag >> 3};
         if (cur_slot == 0u) pm.get_ray(r);
         else pm.get_shadow_ray(cur_slot - 1u, r);
-        tag = (pid << 3) | cur_slot;
-        return true;
-    }
-    RT_DI uint32_t peek(uint32_t idx) const { return work.item(idx); }
-    RT_DI void prefetch(uint32_t item) const {
-        const size_t pid = item >> 3;
-        const uint32_t slot = item & 7u;
-        if (slot == 0u) prefetch_l2(wb.req + pid * WF_REQ_ROWS + REQ_O);
-        else {
-            prefetch_l2(wb.st + pid * kStateRows + ROW_HPOS);
-            prefetch_l2(wb.req + pid * WF_REQ_ROWS + REQ_SHADOW_D + (slot - 1u));
-        }
     }
     RT_DI bool want_attrs(uint32_t tag) const { return (tag & 7u) == 0u; }   // shadow rays: main.rs:435-447
     RT_DI bool all_sphere_uv() const { return false; }                       // uv of a sphere hit only where a material reads it
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
     WfRayIO io;
     io.wb = wb; io.work = wk;
-    cast_rays_in_lanes<WF_CAST_RL_PREFETCH != 0>(sc, tp, io, wk.n_virtual(), sh, cs);
+    cast_rays_in_lanes(sc, tp, io, wk.n_virtual(), sh, cs);
     if (cnt) {
         unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
 #pragma unroll
@@ -782,8 +789,15 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                     if (need || li0 + 4u >= sc.n_lights) break;
                     li0 += 4u;
                 }
+#if WF_REQ_HP
+                // whole sectors: {hit, dir 0} {dir 1, dir 2} {dir 3, -}
+                if (need) { pm.put_shadow_origin(h.pos, h.prim); if (!(need & 1u)) pm.put_shadow_dir(0, mk3(0.f, 0.f, 0.f)); }
+                if (need & 0x6u) { if (!(need & 2u)) pm.put_shadow_dir(1, mk3(0.f, 0.f, 0.f)); if (!(need & 4u)) pm.put_shadow_dir(2, mk3(0.f, 0.f, 0.f)); }
+                if (need & 0x8u) pm.put_req_pad();
+#else
                 if (need & 0x3u) { if (!(need & 1u)) pm.put_shadow_dir(0, mk3(0.f, 0.f, 0.f)); if (!(need & 2u)) pm.put_shadow_dir(1, mk3(0.f, 0.f, 0.f)); }   // whole sectors
                 if (need & 0xcu) { if (!(need & 4u)) pm.put_shadow_dir(2, mk3(0.f, 0.f, 0.f)); if (!(need & 8u)) pm.put_shadow_dir(3, mk3(0.f, 0.f, 0.f)); }
+#endif
                 flags = (flags & ~((0xfffu << F_LI0_SHIFT) | (15u << F_NEED_SHIFT))) | (li0 << F_LI0_SHIFT) | (need << F_NEED_SHIFT);
                 n_shadow = (uint32_t)__popc(need);
                 out = OUT_SHADE;      // with need == 0 the path passes through the SHADE segment of the next round with no cast
@@ -840,7 +854,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
             if (seg == WF_SEG_SHADE) {
                 prefetch_l2(st_a + ROW_ACC);                                          // + ROW_T
                 prefetch_l2(wb.sres + (size_t)pid_ahead * 4u);
-                prefetch_l2(rq_a + REQ_SHADOW_D); prefetch_l2(rq_a + REQ_SHADOW_D + 2);
+                prefetch_l2(rq_a + req_shadow_row(0)); prefetch_l2(rq_a + req_shadow_row(2));
             }
             if (seg != WF_SEG_SHADE || FUSED) { prefetch_l2(rq_a + REQ_O); prefetch_l2(wb.res + (size_t)pid_ahead * 2u); }
         }

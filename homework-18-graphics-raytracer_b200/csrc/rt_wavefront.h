@@ -33,7 +33,18 @@ struct WfControl {
 
 constexpr int WF_STATE_ROWS = 12;   // float4 rows of path state (192 B = 6 sectors)
 constexpr uint32_t WF_WORK_PER_PATH = 5u;   // cast items a path can request in one round: its path ray + 4 shadow rays
-constexpr int WF_REQ_ROWS = 6;      // path ray (2) + 4 shadow directions (96 B = 3 sectors)
+// WF_REQ_HP = 1 lays the request rows of a path out in the 64-byte units DRAM moves: unit 0 {origin, meta} {direction}
+// {shadow dir 3} {-}, unit 1 {hit position, prim} {shadow dir 0} {1} {2}, so that a shadow ray of light slot 0..2 finds its
+// origin and direction in ONE unit instead of two.  Measured on B200 (round 2, 16-epoch 4K batch): cast 79.3 ms against
+// 79.5, shading kernels 86.1 against 82.5 (the extra row written per level costs more than the cast gains): OFF.
+#ifndef WF_REQ_HP
+#define WF_REQ_HP 0
+#endif
+#if WF_REQ_HP
+constexpr int WF_REQ_ROWS = 8;      // 128 B
+#else
+constexpr int WF_REQ_ROWS = 6;      // path ray (2) + 4 shadow directions (96 B = 3 sectors); shadow origins from the path state
+#endif
 #ifndef WF_LOGIC_MIN_BLOCKS
 #define WF_LOGIC_MIN_BLOCKS 2
 #endif

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import scene_util
-from test_gpu_parity import assert_hits_equal, check_whitted, random_rays, rel_err
+from test_gpu_parity import assert_hits_equal, assert_stochastic_agreement, check_whitted, random_rays, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -40,9 +40,47 @@ def test_c5_shape_whitted_and_samples(b200rt, oracle, mesh_ctx):
     cam = b200rt.fixture_camera()
     acc = ctx.render_distributed(cam, params, 0, 1)
     o_acc, _ = oracle.render_distributed(world.scene(), cam, params, 0, 1)
-    assert np.array_equal(acc[..., 3], o_acc[..., 3])
-    bad = (rel_err(acc[..., :3], o_acc[..., :3]).max(axis=2) > 1e-3).mean()
-    assert bad < 5e-3, bad
+    assert_stochastic_agreement(acc, o_acc, "C5 shape 200x125 x 1 epoch, 3264 triangles", 1, min_psnr=35.0)
+
+
+def test_c5_full_size_pixel_sample(b200rt, oracle, tmp_path_factory):
+    """C5 at its REAL size: fixture scene + the 100 352-triangle OBJ height field (1570 tiles), 4000x2500,
+    one stochastic sample per pixel.  The oracle renders 2000 pixels of the frame (40 rows x 50 columns, one sample
+    each: ~0.7 M ray x primitive tests per pixel sample on the CPU); the GPU renders those rows of the full frame through
+    the tiled TMA cast and must produce the same samples: same accepted set, colours to libm ulps."""
+    from concurrent.futures import ThreadPoolExecutor
+    world, ntri = scene_util.fixture_plus_mesh(b200rt, tmp_path_factory.mktemp("mesh_full"), n=225)
+    assert ntri == 100352
+    ctx = b200rt.Context(0)
+    ctx.upload_scene(world)
+    cam = b200rt.fixture_camera()
+    W, H = 4000, 2500
+    params = b200rt.default_params(width=W, height=H, seed=0)
+    rng = np.random.default_rng(2025)
+    rows = np.sort(rng.choice(np.arange(700, 2300), size=40, replace=False))      # rows that see the mesh and the room
+    cols = np.sort(rng.choice(W, size=50, replace=False))
+    scene = world.scene()
+
+    def one(yx):
+        return oracle.sample_distributed(scene, cam, params, int(yx[0]), int(yx[1]), 0)
+
+    todo = [(y, x) for y in rows for x in cols]
+    with ThreadPoolExecutor(max_workers=oracle.host_threads()) as pool:          # ctypes drops the GIL
+        o = np.array(list(pool.map(one, todo)), dtype=np.float32).reshape(len(rows), len(cols), 3)
+    g = np.zeros((len(rows), len(cols), 4), dtype=np.float32)
+    for i, y in enumerate(rows):
+        acc = ctx.render_distributed(cam, b200rt.copy_params(params, row_begin=int(y), row_count=1), 0, 1)
+        g[i] = acc[y, cols]
+    normal = np.isfinite(o).all(axis=2) & ((np.abs(o) >= np.finfo(np.float32).tiny) & (np.abs(o) < np.inf)).all(axis=2)
+    assert np.array_equal(g[..., 3] == 1.0, normal)                       # the is_normal filter accepts the same samples
+    assert normal.mean() > 0.5
+    err = np.abs(g[..., :3] - o) / np.maximum(np.maximum(np.abs(o), np.abs(g[..., :3])), 1e-3)
+    err = np.where(normal[..., None], err, 0.0)
+    moved = (err.max(axis=2) > 1e-3).sum()
+    print(f"C5 full size: {normal.sum()} accepted of {normal.size} samples, {moved} moved, max rel err of the others "
+          f"{np.where(err.max(axis=2) > 1e-3, 0.0, err.max(axis=2)).max():.2e}")
+    assert moved <= 4, moved
+    ctx.close()
 
 
 def test_ragged_triangle_counts(b200rt, oracle):
@@ -165,5 +203,4 @@ def test_c4_4k_epoch_properties(b200rt, oracle, gpu_ctx, fixture_world):
     o_acc, _ = oracle.render_distributed(fixture_world.scene(), cam, band, 0, 4)
     assert np.array_equal(g[1040:1088, :, 3], o_acc[1040:1088, :, 3])
     assert np.array_equal(g[1040:1088].view(np.uint32), a[1040:1088].view(np.uint32))     # band == same rows of the full frame
-    bad = (rel_err(g[1040:1088, :, :3], o_acc[1040:1088, :, :3]).max(axis=2) > 1e-3).mean()
-    assert bad < 2e-3, bad
+    assert_stochastic_agreement(g[1040:1088], o_acc[1040:1088], "C4 band 3840x48 x 4 epochs", 4)

@@ -108,24 +108,44 @@ def test_intersect_empty(b200rt, gpu_ctx):
     assert gpu_ctx.intersect(rays).shape == (0,)
 
 
+# Measured on B200 (round 2, 1280x960 x 8 epochs = 9.8 M samples): 22 pixels with a moved sample (1.8e-5 of the pixels),
+# 5 pixels whose accepted-sample count differs (a libm ulp makes a sample exactly 0, which the is_normal filter of
+# main.rs:1157-1160 drops), PSNR of the mean images 82 dB.  The bounds leave a factor of ~10 for other CUDA / glibc libm
+# versions; a path that really differs shows up as 100x these.
+MOVED_BOUND = 2e-4
+COUNT_DIFF_BOUND = 4e-5
+
+
+def assert_stochastic_agreement(acc, o_acc, what, epochs, min_psnr=40.0):
+    from parity_util import stochastic_agreement
+    s = stochastic_agreement(acc, o_acc)
+    print(f"{what}: {s}")
+    n_px = int(np.prod(np.asarray(acc).shape[:-1]))
+    assert s["count_diff"] <= max(2, int(COUNT_DIFF_BOUND * n_px * epochs)), s   # the is_normal filter accepts the same samples
+    assert s["nonfinite_mismatch"] == 0, s
+    assert s["frac_moved"] <= max(MOVED_BOUND, 2.0 / n_px), s   # pixels in which a libm ulp moved a sample across a silhouette
+    assert s["max_abs"] <= 8.0 * s["peak"] * epochs + 1e-6 or s["frac_moved"] == 0.0, s   # ... and by no more than samples can
+    assert s["psnr"] >= min_psnr, s                     # north_star: converged-mean PSNR >= 40 dB at equal sample count
+    return s
+
+
 def test_distributed_samples_match_oracle(b200rt, oracle, gpu_ctx, fixture_world):
     """C4 semantics at small size: 4 epochs, per-pixel {sum.rgb, count} against the oracle."""
     cam = b200rt.fixture_camera()
     params = b200rt.default_params(width=320, height=240, seed=7)
     acc = gpu_ctx.render_distributed(cam, params, 0, 4)
     o_acc, cnt = oracle.render_distributed(fixture_world.scene(), cam, params, 0, 4)
-    assert np.array_equal(acc[..., 3], o_acc[..., 3])           # same samples accepted by the is_normal filter
-    err = rel_err(acc[..., :3], o_acc[..., :3])
-    # libm differences (sinf/cosf/acosf/powf/logf) perturb scattered directions by ulps; geometry amplifies that at
-    # silhouettes, so a handful of samples may land on another primitive
-    frac_bad = (err.max(axis=2) > 1e-3).mean()
-    assert frac_bad < 2e-3, frac_bad
-    mean_g = oracle.resolve(acc)
-    mean_o = oracle.resolve(o_acc)
-    peak = np.percentile(mean_o @ np.array([0.2126729, 0.7151522, 0.0721750], dtype=np.float32), 99)
-    mse = np.mean((mean_g - mean_o) ** 2)
-    psnr = 10 * np.log10(peak * peak / max(mse, 1e-30))
-    assert psnr >= 40.0, psnr
+    assert_stochastic_agreement(acc, o_acc, "320x240 x 4 epochs", 4)
+
+
+def test_distributed_reference_frame_psnr(b200rt, oracle, gpu_ctx, fixture_world):
+    """The reference's own frame size (1280x960, main.rs:1084-1085), 8 epochs: PSNR of the mean images and the
+    fraction of moved samples at a size where a pixel sees more silhouettes than at 320x240."""
+    cam = b200rt.fixture_camera()
+    params = b200rt.default_params(width=1280, height=960, seed=11)
+    acc = gpu_ctx.render_distributed(cam, params, 0, 8)
+    o_acc, cnt = oracle.render_distributed(fixture_world.scene(), cam, params, 0, 8, n_threads=oracle.host_threads())
+    assert_stochastic_agreement(acc, o_acc, "1280x960 x 8 epochs", 8)
 
 
 def test_distributed_epoch_split_additive(b200rt, gpu_ctx):
@@ -237,7 +257,7 @@ def test_wavefront_depth0_and_many_lights(b200rt, oracle, gpu_ctx, fixture_world
         acc = gpu_ctx.render_distributed(cam, p, 0, 3)
         o_acc, _ = oracle.render_distributed(fixture_world.scene(), cam, p, 0, 3)
         assert np.array_equal(acc[..., 3], o_acc[..., 3])
-        assert (rel_err(acc[..., :3], o_acc[..., :3]).max(axis=2) > 1e-3).mean() < 2e-3
+        assert_stochastic_agreement(acc, o_acc, "fused levels / light counts", 3, min_psnr=35.0)
     w = b200rt.World.fixture()
     for k in range(3):
         w.push_light(b200rt.point_light([1.0 + k, 2.0, 1.5 - k], [0.3, 0.4, 0.5]))
@@ -252,7 +272,7 @@ def test_wavefront_depth0_and_many_lights(b200rt, oracle, gpu_ctx, fixture_world
     # libm ulps (CUDA vs glibc powf / sincosf) can move a scattered ray across a silhouette: a sample or two may be
     # dropped by the is_normal filter on one side only
     assert (acc[..., 3] != o_acc[..., 3]).sum() <= 3
-    assert (rel_err(acc[..., :3], o_acc[..., :3]).max(axis=2) > 1e-3).mean() < 2e-3
+    assert_stochastic_agreement(acc, o_acc, "depth 0 / many lights", 2, min_psnr=35.0)
     ctx.close()
 
 
