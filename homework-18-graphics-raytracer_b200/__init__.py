@@ -105,7 +105,7 @@ class Stats(C.Structure):
         ("exact_confirms", C.c_uint64), ("samples", C.c_uint64), ("kernel_ms", C.c_float), ("h2d_ms", C.c_float),
         ("d2h_ms", C.c_float), ("wavefront_rounds", C.c_uint32), ("certify_fallbacks", C.c_uint64),
         ("cast_kernel_ms", C.c_float), ("logic_kernel_ms", C.c_float), ("cast_kernel_launches", C.c_uint32),
-        ("kernel_launches", C.c_uint32),
+        ("kernel_launches", C.c_uint32), ("primary_kernel_ms", C.c_float), ("reserved", C.c_uint32),
     ]
 
 

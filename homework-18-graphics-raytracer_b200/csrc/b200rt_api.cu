@@ -228,6 +228,7 @@ int fetch_counters(b200rt_ctx* ctx) {
     ctx->stats.cast_kernel_ms = (float)ctx->wf_timing.cast_ms;
     ctx->stats.logic_kernel_ms = (float)ctx->wf_timing.logic_ms;
     ctx->stats.cast_kernel_launches = (uint32_t)ctx->wf_timing.cast_launches;
+    ctx->stats.primary_kernel_ms = (float)ctx->wf_timing.primary_ms;
     ctx->stats.kernel_launches = ctx->last_launches;
     return B200RT_OK;
 }
@@ -554,7 +555,7 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
     CU(cudaEventRecord(ctx->ev0, st));
     ctx->last_rounds = 0;
     ctx->last_launches = 0;
-    ctx->wf_timing.cast_ms = ctx->wf_timing.logic_ms = ctx->wf_timing.filter_ms = 0.0;
+    ctx->wf_timing.cast_ms = ctx->wf_timing.logic_ms = ctx->wf_timing.primary_ms = 0.0;
     ctx->wf_timing.cast_launches = 0;
     if (epoch_count) {
         if (params->tracer == B200RT_TRACER_MEGAKERNEL || params->cast_mode == B200RT_CAST_BRUTE_EXACT) {

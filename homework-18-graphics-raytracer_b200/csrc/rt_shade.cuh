@@ -45,6 +45,19 @@ RT_DI MatEval material_approx(const DMaterial* __restrict__ mats, uint32_t objec
 // materials.rs:40-44
 RT_DI f3 adjust_normal(const MatEval& m, f3 normal) { return rotate(from_arc(mk3(0.0f, 0.0f, 1.0f), normal), m.normal_ts); }
 
+// powf(x, e) of the Phong lobe (materials.rs:63: x = max(R.V, 0) in [0, 1 + ulps], e = 1 / (smoothness + eps) up to 8.4e6)
+// without the libm call where its result is known: x = 0 gives 0, and x^e below 2^-160 - decided on MUFU.LG2, whose
+// absolute error of 2^-22 moves e * log2(x) by less than 2.1 - rounds to +0 in any powf (half the smallest subnormal is
+// 2^-150).  Mirror-like materials (e = 1e5: x^e underflows for every x < 0.9989) skip the ~90 instructions of powf nearly always.
+RT_DI float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RT_DI float phong_pow(float x, float e) {
+    if (e > 0.0f) {                                     // (any material the builder accepts; otherwise plain powf)
+        if (x == 0.0f) return 0.0f;
+        if (x < 1.0f && e * lg2_approx(x) < -170.0f) return 0.0f;
+    }
+    return nl_powf(x, e);
+}
+
 // materials.rs:46-53
 RT_DI f3 get_diffuse(const MatEval& m, f3 n, f3 l) {
     const float cosine = dot(l, n);
@@ -58,7 +71,7 @@ RT_DI f3 get_specular(const MatEval& m, f3 n, f3 view, f3 l) {
     const f3 reflected_ray = 2.0f * cosine * n - l;
     const float specular = 1.0f / (m.smoothness + kF32Epsilon);
     const float energy_conserving = (specular + 8.0f) / (8.0f * kPi);
-    const float amount = nl_powf(fmaxf(dot(reflected_ray, view), 0.0f), specular) * energy_conserving;
+    const float amount = phong_pow(fmaxf(dot(reflected_ray, view), 0.0f), specular) * energy_conserving;
     return m.specular * amount;
 }
 // The two material constants of get_specular (materials.rs:60-62), for callers that evaluate several lights: the same
@@ -74,7 +87,7 @@ RT_DI f3 get_specular(const MatEval& m, const SpecConst& c, f3 n, f3 view, f3 l)
     const float cosine = dot(l, n);
     if (cosine <= 0.0f) return mk3(0.0f, 0.0f, 0.0f);
     const f3 reflected_ray = 2.0f * cosine * n - l;
-    const float amount = nl_powf(fmaxf(dot(reflected_ray, view), 0.0f), c.exponent) * c.energy;
+    const float amount = phong_pow(fmaxf(dot(reflected_ray, view), 0.0f), c.exponent) * c.energy;
     return m.specular * amount;
 }
 

@@ -193,6 +193,28 @@ RT_DI WfWork wf_work(const WfBuffers& wb, uint32_t buf) {
     return w;
 }
 
+// Camera::shoot_focus for pixel (px, py), sample `sample_idx` of the launch (main.rs:101-127, 1143-1149): seeds the
+// sample's stream and draws the lens offsets (Box-Muller on two stream uniforms).  ONE definition for the
+// pass that opens a sample and for the round-0 cast / consumer that regenerate it: same expressions, same bits.
+RT_DI void wf_open_sample(const DCamera& cam, const DParams& p, uint32_t px, uint32_t py, uint32_t sample_idx, Rng& rng, DRay& ray) {
+    const f3 cam_toward = mk3(cam.toward), cam_x = mk3(cam.x), cam_y = mk3(cam.y);
+    float clip_x, clip_y;
+    clip_y = ((float)p.height / 2.0f - (float)py) / (float)p.height;   // main.rs:1094
+    clip_x = ((float)px - (float)p.width / 2.0f) / (float)p.height;    // main.rs:1095
+    const f3 pinhole_dir = normalize(clip_x * cam_x + clip_y * cam_y + cam_toward);   // main.rs:110
+    rng_init(rng, p.seed_lo, p.seed_hi, py, px, p.epoch_begin + sample_idx);
+    const float u1 = 1.0f - rng_uniform(rng);
+    const float u2 = rng_uniform(rng);
+    const float radius = sqrtf(-2.0f * nl_logf(u1));
+    const float ang = 2.0f * kPi * u2;
+    const float2 sca = nl_sincosf(ang);
+    const float xoffset = p.blur * (radius * sca.y);
+    const float yoffset = p.blur * (radius * sca.x);
+    ray.d = normalize(pinhole_dir * p.focus + cam_x * xoffset + cam_y * yoffset);        // main.rs:115-117
+    ray.o = mk3(cam.center) + normalize(cam_toward) * cam.near - (cam_x * xoffset + cam_y * yoffset);  // :118-120
+    ray.face = kFront; ray.ex_prim = -1; ray.ex_face = kFront;
+}
+
 }  // namespace
 
 // ---- cast --------------------------------------------------------------------------------------------------
@@ -410,6 +432,72 @@ __global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_TILED_MIN_BLOCKS) wf_ca
     }
 }
 
+// ---- round 0 of the rays-in-lanes casts: the first camera ray of every slot, generated in the cast (no INIT pass, no
+// request rows, no work list).  Work index = path id; the result goes where the consumer (WF_SEG_PRIMARY0) reads it.
+namespace {
+struct WfPrimaryIO {
+    WfBuffers wb;
+    DCamera cam;
+    DParams p;
+    RT_DI void begin_block(uint32_t) const {}
+    RT_DI uint32_t item(uint32_t idx) const { return idx; }
+    RT_DI void fetch(uint32_t pid, DRay& r) const {
+        const uint32_t pix = pid % wb.n_pixels, e_lane = pid / wb.n_pixels;
+        Rng rng;
+        wf_open_sample(cam, p, pix % p.width, p.row_begin + pix / p.width, e_lane, rng, r);
+    }
+    RT_DI bool want_attrs(uint32_t) const { return true; }
+    RT_DI bool all_sphere_uv() const { return false; }
+    RT_DI uint2 culled(const DScene&, uint32_t, uint32_t) const { return make_uint2(0u, 0u); }
+    RT_DI uint32_t cull_class(uint32_t) const { return 0u; }
+    RT_DI uint2 cull_mask(const DScene&, uint32_t) const { return make_uint2(0u, 0u); }
+    RT_DI void store(uint32_t pid, const DHit& h) const {
+        const uint32_t m2 = h.prim >= 0 ? (h.face | (h.object << 8)) : 0u;
+        st_rows2(wb.res + (size_t)pid * 2u, make_float4(__int_as_float(h.prim), u2f(m2), h.t, h.uv.x),
+                 make_float4(h.normal.x, h.normal.y, h.normal.z, h.uv.y));
+    }
+};
+RT_DI void wf_cast_tail(const DScene& sc, const CastStats& cs, uint32_t n_work, DCounters* __restrict__ cnt) {
+    if (!cnt) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+        n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
+    }
+    if (lane == 0u && n_conf) atomicAdd(&cnt->confirms, n_conf);
+    if (lane == 0u && n_fb) atomicAdd(&cnt->fallbacks, n_fb);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&cnt->casts, (unsigned long long)n_work);
+        atomicAdd(&cnt->tri_pairs, (unsigned long long)n_work * sc.n_tris);
+        atomicAdd(&cnt->sph_pairs, (unsigned long long)n_work * sc.n_sph);
+    }
+}
+}  // namespace
+__global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_primary_kernel(const DScene sc, const __grid_constant__ RlTileParam tp,
+                                                                                              const DCamera cam, const DParams p, const WfBuffers wb,
+                                                                                              const uint32_t buf, DCounters* __restrict__ cnt) {
+    __shared__ RlShared sh;
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    const WfPrimaryIO io{wb, cam, p};
+    cast_rays_in_lanes(sc, tp, io, wb.n, sh, cs);
+    wf_cast_tail(sc, cs, wb.n, cnt);
+}
+__global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_TILED_MIN_BLOCKS) wf_cast_rl_tiled_primary_kernel(const DScene sc, const DCamera cam, const DParams p,
+                                                                                                          const WfBuffers wb, const uint32_t buf,
+                                                                                                          DCounters* __restrict__ cnt) {
+    __shared__ RlTiledShared sh;
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    const WfPrimaryIO io{wb, cam, p};
+    cast_rays_in_lanes_tiled(sc, io, wb.n, sh, cs);
+    wf_cast_tail(sc, cs, wb.n, cnt);
+}
+
 // ---- logic -------------------------------------------------------------------------------------------------
 
 // One instantiation per segment: each is a small kernel (the code of the other segments is compiled out), so it keeps
@@ -430,6 +518,7 @@ template <int SEG, bool FUSED = false> struct LogicCfg { static constexpr int kM
 template <> struct LogicCfg<WF_SEG_PRIMARY, false> { static constexpr int kMinBlocks = WF_PRIMARY_MIN_BLOCKS, kThreads = 256; };
 template <> struct LogicCfg<WF_SEG_BOUNCE, true> { static constexpr int kMinBlocks = WF_FUSED_BOUNCE_MIN_BLOCKS, kThreads = 256; };
 template <> struct LogicCfg<WF_SEG_INIT, false> { static constexpr int kMinBlocks = 4, kThreads = 256; };
+template <> struct LogicCfg<WF_SEG_PRIMARY0, false> { static constexpr int kMinBlocks = WF_PRIMARY_MIN_BLOCKS, kThreads = 256; };
 template <> struct LogicCfg<WF_SEG_REFR, false> { static constexpr int kMinBlocks = 4, kThreads = 256; };
 // shade + arrival + next level in one pass
 template <> struct LogicCfg<WF_SEG_SHADE, true> { static constexpr int kMinBlocks = WF_FUSED_SHADE_MIN_BLOCKS, kThreads = WF_FUSED_SHADE_THREADS; };
@@ -445,28 +534,28 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t nbuf = buf ^ 1u;
-    const uint32_t n_this = SEG == WF_SEG_INIT ? wb.n : wb.ctl->c[buf].seg[SEG];
+    constexpr bool kIndexed = SEG == WF_SEG_INIT || SEG == WF_SEG_PRIMARY0;      // no queue: path id = index
+    const uint32_t n_this = kIndexed ? wb.n : wb.ctl->c[buf].seg[SEG];
     const uint32_t total_chunks = (n_this + 31u) >> 5;
-    const f3 cam_toward = mk3(cam.toward), cam_x = mk3(cam.x), cam_y = mk3(cam.y);
     const uint32_t n_epochs = p.epoch_count;
     unsigned long long n_samples = 0ull;
 
     // the path of this lane in the warp's NEXT chunk is fetched one iteration ahead, and its rows are pulled into L2
     // before the current chunk's stores and queue atomics: the chain queue -> path -> rows is otherwise two DRAM round
     // trips at the top of every iteration of a kernel that runs 4-6 warps per sub-partition
-    const uint32_t* __restrict__ q_this = wb.q + ((size_t)buf * WF_SEG_COUNT + seg) * wb.n;
+    const uint32_t* __restrict__ q_this = wb.q + ((size_t)buf * WF_SEG_COUNT + (kIndexed ? 0 : seg)) * wb.n;
     uint32_t pid_ahead = 0u;
-    if (seg != WF_SEG_INIT && WF_LOGIC_PREFETCH) {
+    if (!kIndexed && WF_LOGIC_PREFETCH) {
         const uint32_t k0 = gw * 32u + lane;
         if (gw < total_chunks && k0 < n_this) pid_ahead = q_this[k0];
     }
     for (uint32_t chunk = gw; chunk < total_chunks; chunk += n_warps) {
         const uint32_t k = chunk * 32u + lane;
         const bool valid = k < n_this;
-        const uint32_t pid = !valid ? 0u : (seg == WF_SEG_INIT ? k : (WF_LOGIC_PREFETCH ? pid_ahead : q_this[k]));
+        const uint32_t pid = !valid ? 0u : (kIndexed ? k : (WF_LOGIC_PREFETCH ? pid_ahead : q_this[k]));
         const PathMem pm{wb.st, wb.req, pid};
         bool valid_ahead = false;
-        if (seg != WF_SEG_INIT && WF_LOGIC_PREFETCH) {
+        if (!kIndexed && WF_LOGIC_PREFETCH) {
             const uint32_t k_ahead = (chunk + n_warps) * 32u + lane;
             valid_ahead = chunk + n_warps < total_chunks && k_ahead < n_this;
             if (valid_ahead) pid_ahead = q_this[k_ahead];
@@ -499,7 +588,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         const uint32_t px = pix % p.width, py = p.row_begin + pix / p.width;
 
         // ---- load: only the rows this segment reads -----------------------------------------------------------------
-        if (valid && seg != WF_SEG_INIT) {
+        if (valid && !kIndexed) {
             constexpr bool kNeedRng = seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE || (FUSED && seg == WF_SEG_BOUNCE);
             float4 r0, r1 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (kNeedRng) pm.ld2(ROW_CTRL, r0, r1); else r0 = pm.ld(ROW_CTRL);
@@ -599,6 +688,26 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
 
         if (seg == WF_SEG_INIT) {
             do_finish = valid;
+        } else if (seg == WF_SEG_PRIMARY0) {
+            // the slot's first sample: the round-0 cast generated its camera ray from the index; regenerate it (and the
+            // sample's stream) instead of reading what an INIT pass would have stored (main.rs:1133-1155)
+            if (valid) {
+                sample_idx = e_lane;
+                depth = p.depth; flags = 0u;
+                wf_open_sample(cam, p, px, py, sample_idx, rng, ray);
+                w_rng = true;
+                float4 a, b;
+                ld_rows2(wb.res + (size_t)pid * 2u, a, b);
+                DHit hc;
+                hc.prim = __float_as_int(a.x);
+                const uint32_t meta = f2u(a.y);
+                hc.face = meta & 1u; hc.object = meta >> 8; hc.t = a.z;
+                hc.pos = ray.o + ray.d * hc.t;                                         // main.rs:210 / 304
+                hc.normal = mk3(b); hc.uv.x = a.w; hc.uv.y = b.w;
+                w_acc = true;
+                if (hc.prim < 0) do_finish = true;
+                else { h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face; w_hit = true; w_dirs = true; do_level = true; }
+            }
         } else if (seg == WF_SEG_PRIMARY || seg == WF_SEG_BOUNCE) {
             if (valid) {
                 float4 a, b;
@@ -713,7 +822,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         }
 
         // ---- top of distributed_ray_trace for the current hit (main.rs:521-554), then the bounce ray ---------------------
-        if (seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE || (FUSED && seg == WF_SEG_BOUNCE)) {
+        if (seg == WF_SEG_PRIMARY || seg == WF_SEG_PRIMARY0 || seg == WF_SEG_SHADE || (FUSED && seg == WF_SEG_BOUNCE)) {
             if (do_level) {
                 if (!pre_level && depth <= 0) {
                     if (flags & F_A_KNOWN) { acc = acc + T * a_shade; do_finish = true; }    // main.rs:525-527
@@ -809,12 +918,15 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
             if (do_finish) {
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (seg != WF_SEG_INIT) {
-                    sum = pm.ld(ROW_SUM);
-                    if (is_normal_f32(acc.x) && is_normal_f32(acc.y) && is_normal_f32(acc.z)) {   // main.rs:1157-1160
+                    // (a slot's first sample starts its accumulator: no INIT pass zeroed it when round 0 ran fused)
+                    const bool first = wb.fused_primary != 0u && sample_idx == e_lane;
+                    if (!first) sum = pm.ld(ROW_SUM);
+                    const bool accepted = is_normal_f32(acc.x) && is_normal_f32(acc.y) && is_normal_f32(acc.z);   // main.rs:1157-1160
+                    if (accepted) {
                         sum.x += acc.x; sum.y += acc.y; sum.z += acc.z; sum.w += 1.0f;            // photon.rs:30-31
                         n_samples += 1ull;
-                        pm.sv(ROW_SUM, sum);
                     }
+                    if (accepted || first) pm.sv(ROW_SUM, sum);
                     sample_idx += wb.epar;
                 } else {
                     sample_idx = e_lane;
@@ -824,22 +936,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 else {
                     acc = mk3(0.f, 0.f, 0.f); T = mk3(1.f, 1.f, 1.f); depth = p.depth; flags = 0u;
                     w_acc = false; w_hit = false; w_dirs = false; w_pend = false; w_nadj = false;
-                    // Camera::shoot_focus, main.rs:101-127 (Box-Muller on two stream uniforms)
-                    float clip_x, clip_y;
-                    clip_y = ((float)p.height / 2.0f - (float)py) / (float)p.height;   // main.rs:1094
-                    clip_x = ((float)px - (float)p.width / 2.0f) / (float)p.height;    // main.rs:1095
-                    const f3 pinhole_dir = normalize(clip_x * cam_x + clip_y * cam_y + cam_toward);   // main.rs:110
-                    rng_init(rng, p.seed_lo, p.seed_hi, py, px, p.epoch_begin + sample_idx);
-                    const float u1 = 1.0f - rng_uniform(rng);
-                    const float u2 = rng_uniform(rng);
-                    const float radius = sqrtf(-2.0f * nl_logf(u1));
-                    const float ang = 2.0f * kPi * u2;
-                    const float2 sca = nl_sincosf(ang);
-                    const float xoffset = p.blur * (radius * sca.y);
-                    const float yoffset = p.blur * (radius * sca.x);
-                    ray.d = normalize(pinhole_dir * p.focus + cam_x * xoffset + cam_y * yoffset);        // main.rs:115-117
-                    ray.o = mk3(cam.center) + normalize(cam_toward) * cam.near - (cam_x * xoffset + cam_y * yoffset);  // :118-120
-                    ray.face = kFront; ray.ex_prim = -1; ray.ex_face = kFront;
+                    wf_open_sample(cam, p, px, py, sample_idx, rng, ray);   // Camera::shoot_focus, main.rs:101-127
                     w_rng = true;
                     out = OUT_PRIMARY;
                 }
@@ -862,7 +959,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         if (valid && out != OUT_RETIRE) {
             const float4 ctrl = make_float4(u2f(flags), __int_as_float(depth), u2f(rng.draws), u2f(sample_idx));
             // (the INIT pass streams over consecutive paths: measured faster with 128-bit stores, 8.5 vs 12.4 ms per batch)
-            constexpr bool kW = seg != WF_SEG_INIT;
+            constexpr bool kW = seg != WF_SEG_INIT;   // (the INIT pass streams over consecutive paths)
             const float4 rng_row = make_float4(u2f(rng.b[0]), u2f(rng.b[1]), u2f(rng.b[2]), u2f(rng.b[3]));
             if (kW) { if (w_rng) pm.sv2(ROW_CTRL, ctrl, rng_row); else pm.sv(ROW_CTRL, ctrl); }
             else { pm.sv(ROW_CTRL, ctrl); if (w_rng) pm.sv(ROW_RNG, rng_row); }   // (merged branches of 128-bit stores were scalarised)
@@ -983,7 +1080,7 @@ static WfBuffers wf_carve(void* workspace, uint32_t n_paths, uint32_t n_pixels, 
     wb.sres = reinterpret_cast<float2*>(b + off);              off = align(off + n * 32);
     wb.q = reinterpret_cast<uint32_t*>(b + off);               off = align(off + n * 2 * WF_SEG_COUNT * 4);
     wb.work = reinterpret_cast<uint32_t*>(b + off);            off = align(off + n * 2 * WF_WORK_PER_PATH * 4);
-    wb.n = n_paths; wb.n_pixels = n_pixels; wb.epar = epar;
+    wb.n = n_paths; wb.n_pixels = n_pixels; wb.epar = epar; wb.fused_primary = 0u;
     return wb;
 }
 
@@ -992,7 +1089,7 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                                          uint32_t* h_pinned_retired, cudaEvent_t ev_poll, cudaStream_t stream,
                                          uint32_t* rounds_out, uint32_t* launches_out, WfKernelTiming* timing) {
     const uint32_t n_pixels = p.width * p.row_count;
-    const WfBuffers wb = wf_carve(workspace, n_paths, n_pixels, epar);
+    WfBuffers wb = wf_carve(workspace, n_paths, n_pixels, epar);
     cudaError_t e = cudaMemsetAsync(wb.ctl, 0, sizeof(WfControl), stream);
     if (e != cudaSuccess) return e;
     const int cast_blocks = sm_count * WF_CAST_MIN_BLOCKS;
@@ -1008,8 +1105,14 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     const char* fused_env = getenv("B200RT_WF_FUSED_LEVELS");
     const bool fused = sc.n_lights <= 4u && !(fused_env && fused_env[0] == '0');
     auto logic_blocks = [&](int min_blocks) { return sm_count * min_blocks; };
-    // round 0: every slot opens its first sample
-    wf_logic_kernel<WF_SEG_INIT, false><<<logic_blocks(LogicCfg<WF_SEG_INIT>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, 1u, d_cnt);
+    // Round 0.  With a rays-in-lanes cast the first camera ray of every slot is generated inside the cast and consumed by
+    // the PRIMARY0 pass (path id = index): no INIT pass, no request rows, no work list (B200RT_WF_FUSED_PRIMARY=0 keeps
+    // the INIT pass, as the warp-transposed cast does).  Otherwise: every slot opens its first sample in an INIT pass.
+    const char* fp_env = getenv("B200RT_WF_FUSED_PRIMARY");
+    const bool fused_primary = (rays_in_lanes || rays_in_lanes_tiled) && !(fp_env && fp_env[0] == '0');
+    wb.fused_primary = fused_primary ? 1u : 0u;
+    if (!fused_primary)
+        wf_logic_kernel<WF_SEG_INIT, false><<<logic_blocks(LogicCfg<WF_SEG_INIT>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, 1u, d_cnt);
     uint32_t round = 0, buf = 0;
     uint32_t group = 8;
     for (;;) {
@@ -1028,7 +1131,10 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                 ev_b = timing->pool[2 * (round - first_round_of_group) + 1];
                 cudaEventRecord(ev_a, stream);
             }
-            if (rays_in_lanes) {
+            if (round == 0u && fused_primary) {
+                if (rays_in_lanes) wf_cast_rl_primary_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, cam, p, wb, buf, d_cnt);
+                else wf_cast_rl_tiled_primary_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            } else if (rays_in_lanes) {
                 wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, wb, buf, d_cnt);
             } else if (rays_in_lanes_tiled) {
                 wf_cast_rl_tiled_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
@@ -1036,6 +1142,8 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                 wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
             }
             if (timing) cudaEventRecord(ev_b, stream);
+            if (round == 0u && fused_primary)
+                wf_logic_kernel<WF_SEG_PRIMARY0, false><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY0>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
             wf_logic_kernel<WF_SEG_PRIMARY, false><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
             if (fused) {
                 wf_logic_kernel<WF_SEG_SHADE, true><<<logic_blocks(LogicCfg<WF_SEG_SHADE, true>::kMinBlocks), LogicCfg<WF_SEG_SHADE, true>::kThreads, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
@@ -1058,8 +1166,8 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
             for (uint32_t g = 0; g < round - first_round_of_group; ++g) {
                 float ms = 0.0f;
                 cudaEventElapsedTime(&ms, timing->pool[2 * g], timing->pool[2 * g + 1]);
-                timing->cast_ms += ms;
-                timing->cast_launches += 1;
+                if (first_round_of_group + g == 0u && fused_primary) timing->primary_ms += ms;   // a different kernel: camera rays + cast
+                else { timing->cast_ms += ms; timing->cast_launches += 1; }
                 if (g + 1 < round - first_round_of_group) {       // cast end -> next cast start = the logic kernels of the round
                     cudaEventElapsedTime(&ms, timing->pool[2 * g + 1], timing->pool[2 * g + 2]);
                     timing->logic_ms += ms;
@@ -1072,7 +1180,7 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     }
     wf_combine_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(wb, p, reinterpret_cast<float4*>(d_accum));
     if (rounds_out) *rounds_out = round;
-    if (launches_out) *launches_out += 2u + round * ((p.depth <= 0 ? 6u : 5u));
+    if (launches_out) *launches_out += 2u + round * ((p.depth <= 0 ? 6u : 5u));   // (INIT or PRIMARY0) + combine + per round
     return cudaGetLastError();
 }
 

@@ -17,7 +17,10 @@ enum : int {
     WF_SEG_BOUNCE,     // reflected / scattered / escaped ray (main.rs:564, 583, 603)
     WF_SEG_SHB,        // no cast: get_shade still has to start (depth-0 primary hit)
     WF_SEG_REFR,       // a step of get_refract (main.rs:371, 380)
-    WF_SEG_COUNT
+    WF_SEG_COUNT,
+    // round 0 with the rays-in-lanes cast: no INIT pass and no queue - the cast generates every slot's first camera ray
+    // from its index, and this segment (path id = index) regenerates it, consumes the hit and opens the sample
+    WF_SEG_PRIMARY0 = WF_SEG_COUNT
 };
 
 struct WfCounters {          // per round parity
@@ -58,13 +61,14 @@ struct WfBuffers {
     uint32_t* q;             // [2][WF_SEG_COUNT][n]
     uint32_t* work;          // [2][WF_WORK_PER_PATH][n]: one list of path ids per ray slot
     uint32_t n, n_pixels, epar;
+    uint32_t fused_primary;  // round 0 ran without an INIT pass: a slot's first sample starts its accumulator row
 };
 
 // Per-kernel device times of a wavefront render (filled when the caller asks for them): CUDA events on the
 // launching stream around every wf_cast_kernel launch.
 struct WfKernelTiming {
     std::vector<cudaEvent_t> pool;
-    double cast_ms = 0.0, logic_ms = 0.0, filter_ms = 0.0;
+    double cast_ms = 0.0, logic_ms = 0.0, primary_ms = 0.0;   // primary_ms: the round-0 cast that generates the camera rays
     uint64_t cast_launches = 0;
 };
 

@@ -189,6 +189,9 @@ typedef struct b200rt_stats {
     float logic_kernel_ms;         /* sum over the shading / scatter kernels between them         */
     uint32_t cast_kernel_launches;
     uint32_t kernel_launches;      /* kernels launched by the last render call (always counted) */
+    float primary_kernel_ms;       /* (kernel timing) the round-0 cast that also generates the camera rays: one primary cast
+                                      per pixel sample, NOT part of cast_kernel_ms / cast_kernel_launches */
+    uint32_t reserved;
 } b200rt_stats;
 
 typedef struct b200rt_ctx b200rt_ctx;

@@ -174,6 +174,8 @@ pub struct b200rt_stats {
     pub logic_kernel_ms: f32,
     pub cast_kernel_launches: u32,
     pub kernel_launches: u32,
+    pub primary_kernel_ms: f32,
+    pub reserved: u32,
 }
 
 /// opaque: one context per host thread and GPU
