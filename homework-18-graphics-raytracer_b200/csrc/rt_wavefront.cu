@@ -81,7 +81,8 @@ enum : uint32_t {
     // fused levels (scenes of <= 4 lights): the next level's select / scatter ran when the hit was reached, and its
     // ray travels in the same round as the hit's shadow rays
     F_PRE = 1u << 23,           // a path ray (bounce, or the first inside ray of get_refract) is in flight with the shadow rays
-    F_BLACK = 1u << 24          // the next level ends the sample black (main.rs:559-561 / 366-368): close it after get_shade
+    F_BLACK = 1u << 24,         // the next level ends the sample black (main.rs:559-561 / 366-368): close it after get_shade
+    F_FRESH = 1u << 25          // radiance / throughput are still the opening values (0, 1): their rows were not written yet
 };
 enum : uint32_t { SH_FINAL = 0, SH_NEXT_MIX = 1, SH_NEXT_REFR = 2 };
 
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 h_dir = mk3(r7); h.uv.x = r7.w;
                 h_dir_orig = mk3(r8); h.uv.y = r8.w;
             }
-            if (seg == WF_SEG_SHADE) {
+            if (seg == WF_SEG_SHADE && !(flags & F_FRESH)) {   // (fresh: acc = 0, T = 1 as initialised above)
                 float4 ra, rt;
                 pm.ld2(ROW_ACC, ra, rt);
                 acc = mk3(ra); T = mk3(rt);
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         // one step of get_refract after an inside ray came back (main.rs:371-402)
         auto refract_step = [&](const float4 a, const float4 b) {
             const int32_t hprim = __float_as_int(a.x);
-            if (hprim < 0) { if (seg == WF_SEG_REFR) acc = mk3(pm.ld(ROW_ACC)); do_finish = true; return; }   // Infinite
+            if (hprim < 0) { if (seg == WF_SEG_REFR && !(flags & F_FRESH)) acc = mk3(pm.ld(ROW_ACC)); do_finish = true; return; }   // Infinite
             const uint32_t meta = f2u(a.y);
             const uint32_t hi_face = meta & 1u;
             const f3 hi_pos = ray.o + ray.d * a.z, hi_normal = mk3(b);
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 w_pend = true;
                 out = OUT_REFR;
             } else if (!have_out) {
-                if (seg == WF_SEG_REFR) acc = mk3(pm.ld(ROW_ACC));
+                if (seg == WF_SEG_REFR && !(flags & F_FRESH)) acc = mk3(pm.ld(ROW_ACC));
                 do_finish = true;                                                  // Trapped
             } else {                                                               // main.rs:392-402, then 603
                 DRay e;
@@ -704,7 +705,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 hc.face = meta & 1u; hc.object = meta >> 8; hc.t = a.z;
                 hc.pos = ray.o + ray.d * hc.t;                                         // main.rs:210 / 304
                 hc.normal = mk3(b); hc.uv.x = a.w; hc.uv.y = b.w;
-                w_acc = true;
+                flags |= F_FRESH;                       // acc = 0, T = 1: the first pass that changes them stores them
                 if (hc.prim < 0) do_finish = true;
                 else { h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face; w_hit = true; w_dirs = true; do_level = true; }
             }
@@ -715,14 +716,14 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 load_path_hit(a, b, hc);
                 const bool hit = hc.prim >= 0;
                 if (seg == WF_SEG_PRIMARY) {                                           // main.rs:1150-1155
-                    // a fresh sample: acc = 0, T = 1 (set when the sample was opened; not stored until they change)
-                    w_acc = true;
+                    // a fresh sample: acc = 0, T = 1 (not stored until they change: F_FRESH)
+                    flags |= F_FRESH;
                     if (!hit) do_finish = true;
                     else { h = hc; h_dir = ray.d; h_dir_orig = ray.d; h_rayface = ray.face; w_hit = true; w_dirs = true; do_level = true; }
                 } else {
                     const uint32_t ray_type = (flags >> F_RAYTYPE_SHIFT) & 3u;
                     if (!hit) {
-                        if (ray_type == 2u) { acc = mk3(pm.ld(ROW_ACC)); do_finish = true; }                 // main.rs:606-608
+                        if (ray_type == 2u) { if (!(flags & F_FRESH)) acc = mk3(pm.ld(ROW_ACC)); do_finish = true; }   // main.rs:606-608
                         else {                                                                               // main.rs:572-574 / 591-593
                             flags = (flags & ~((3u << F_PURPOSE_SHIFT) | F_PRE | F_BLACK)) | (SH_FINAL << F_PURPOSE_SHIFT);
                             do_shade_begin = true;
@@ -796,6 +797,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                     do_shade_begin = true;
                 } else {
                     w_acc = true;
+                    flags &= ~F_FRESH;
                     if (purpose == SH_FINAL) {
                         acc = acc + T * shade;
                         do_finish = true;
@@ -846,7 +848,9 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                     // scatter_hit, main.rs:539-554
                     const f3 base_dir = ray_type == 0u ? -h.normal : h_dir;
                     const float exponent = ray_type == 0u ? 1.0f : mat.smoothness;
-                    const float phi = nl_acosf(nl_powf(1.0f - rng_range(rng, 0.0f, 1.0f), exponent));
+                    // (a diffuse bounce scatters with exponent 1: powf(x, 1) = x exactly, as the IEEE pow of the reference)
+                    const float su = 1.0f - rng_range(rng, 0.0f, 1.0f);
+                    const float phi = nl_acosf(exponent == 1.0f ? su : nl_powf(su, exponent));
                     const float theta = rng_range(rng, -kPi, kPi);
                     const quat from_z = from_arc(mk3(0.0f, 0.0f, 1.0f), normalize(base_dir));
                     const float2 scp = nl_sincosf(phi), sct = nl_sincosf(theta);
@@ -943,7 +947,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
             }
         }
 
-        if (seg != WF_SEG_INIT && WF_LOGIC_PREFETCH && valid_ahead) {
+        if (seg != WF_SEG_INIT && WF_LOGIC_PREFETCH == 1 && valid_ahead) {   // (2: only the path id travels ahead)
             const float4* st_a = wb.st + (size_t)pid_ahead * kStateRows;
             const float4* rq_a = wb.req + (size_t)pid_ahead * WF_REQ_ROWS;
             prefetch_l2(st_a + ROW_CTRL);                                             // + ROW_RNG
