@@ -156,6 +156,39 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
                     make_float4(vals[0][2 * k], vals[1][2 * k], vals[0][2 * k + 1], vals[1][2 * k + 1]);
         }
     }
+    // Plane runs of tile 0 (the kernel-parameter records): CONSECUTIVE triangles of (nearly) one plane - the two halves of a
+    // square, the fan of a polygon - share n.dir, d - n.o, the reciprocal, t and the plane point in the loop, which
+    // evaluates them once per run, on the plane of the run's first triangle (flag in the spare slot of the record).
+    // Consecutive only: candidate bits stay in primitive order, which the exact walk's tie rule needs (main.rs:229-233).
+    // A member's own plane {n, d} (the reference's bits) differs from the run's by dn, dd (a few ulps: its normal comes
+    // from other edges): that moves the filter's t by at most (dd + |dn| (O + T)) / |n.dir|, T <= O + V + E - a slack of
+    // the A kind, added (twice over) to the A the run loop uses.  Phase 2 classifies with each triangle's own plane.
+    double a_runs = 0.0;
+    {
+        const double O = origin_bound, V = ctx->scene_radius, E = ctx->max_edge;
+        bool have_run = false;
+        double rn[3] = {0, 0, 0}, rd = 0;
+        for (uint32_t idx = 0; idx < (uint32_t)kTileTris; ++idx) {
+            float4* tp = ctx->h_tile0.rec + 4 * (size_t)idx;
+            bool start = true;
+            const bool live = idx < nt && (tp[0].x != 0.0f || tp[0].y != 0.0f || tp[0].z != 0.0f);   // (degenerate: all-zero record)
+            if (live) {
+                const float4 e0 = ctx->h_tri_exact[4 * (size_t)idx];
+                const double n[3] = {e0.x, e0.y, e0.z}, d = e0.w;
+                if (have_run) {
+                    const double dn = std::sqrt((n[0] - rn[0]) * (n[0] - rn[0]) + (n[1] - rn[1]) * (n[1] - rn[1]) + (n[2] - rn[2]) * (n[2] - rn[2]));
+                    const double dd = std::fabs(d - rd);
+                    if (dn <= 2e-6 && dd <= 2e-6 * std::max(1.0, std::fabs(rd))) {
+                        start = false;
+                        a_runs = std::max(a_runs, dd + dn * (2.0 * O + V + E));
+                    }
+                }
+                if (start) { rn[0] = n[0]; rn[1] = n[1]; rn[2] = n[2]; rd = d; }
+                have_run = true;
+            } else have_run = false;
+            tp[2].w = start ? 1.0f : 0.0f;
+        }
+    }
     CU(cudaDeviceSynchronize());   // a kernel of an earlier launch may still read the old records
     int rc = ensure(ctx, &ctx->d_filter, &ctx->d_filter_bytes, rec.size() * sizeof(float4));
     if (rc != B200RT_OK) return rc;
@@ -166,6 +199,7 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
     ctx->scene.origin_bound = origin_bound;
     ctx->scene.filter_A = up(A);
     ctx->scene.filter_As = ctx->scene.filter_A * kRlPlaneScale;
+    ctx->scene.filter_As_runs = up(A + 2.0 * a_runs) * kRlPlaneScale;
     ctx->scene.h_tile0 = &ctx->h_tile0;
     ctx->scene.filter_g = 3.814697265625e-6f;   // 2^-18
     return B200RT_OK;

@@ -124,6 +124,66 @@ RT_DI void rl_filter_tile(REC rec, const P2 (&ox)[2], const P2 (&oy)[2], const P
     }
 }
 
+// The same filter over the kernel-parameter tile with PLANE RUNS: a record whose flag is set starts a run and computes
+// nd, num, r, t and the plane point p for the lane's rays; the records after it (same plane up to ulps, see pack_filter)
+// reuse them and only evaluate their edge functions: 9 instead of 19 FFMA2 per pair of rays and triangle, no MUFU.  The
+// fixture scene's 64 triangles are 26 planes (14 squares, 12 pentagon fans).  The flag is warp-uniform (a uniform branch).
+template <int FACE>
+RT_DI void rl_filter_tile_runs(const RlTileParam& tp, const P2 (&ox)[2], const P2 (&oy)[2], const P2 (&oz)[2], const P2 (&dx)[2],
+                               const P2 (&dy)[2], const P2 (&dz)[2], const P2 (&cf)[2], const P2 As2, uint32_t (&keep)[4][2]) {
+    P2 T[2], PX[2], PY[2], PZ[2], R2[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) T[k] = PX[k] = PY[k] = PZ[k] = R2[k] = 0ull;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t rj0 = 0u, rj1 = 0u, rj2 = 0u, rj3 = 0u;
+#pragma unroll kRlLoopUnroll
+        for (int i = 0; i < 32; ++i) {
+            const int ti = 32 * half + i;
+            const float4 u2 = tp.rec[4 * ti + 2], q3 = tp.rec[4 * ti + 3];
+            if (__float_as_uint(u2.w) != 0u) {                      // a new plane
+                const float4 u0 = tp.rec[4 * ti];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const P2 nd = p2_fma(p2_bc(u0.z), dz[k], p2_fma(p2_bc(u0.y), dy[k], p2_mul(p2_bc(u0.x), dx[k])));
+                    const P2 num = p2_fma(p2_bc(-u0.z), oz[k], p2_fma(p2_bc(-u0.y), oy[k], p2_fma(p2_bc(-u0.x), ox[k], p2_bc(q3.x))));
+                    float nda, ndb;
+                    p2_unpack(nd, nda, ndb);
+                    R2[k] = p2_pack(rcp_approx(nda), rcp_approx(ndb));
+                    T[k] = p2_mul(num, R2[k]);
+                    PX[k] = p2_fma(T[k], dx[k], ox[k]); PY[k] = p2_fma(T[k], dy[k], oy[k]); PZ[k] = p2_fma(T[k], dz[k], oz[k]);
+                }
+            }
+            const float4 u0 = tp.rec[4 * ti], u1 = tp.rec[4 * ti + 1];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const P2 e0 = p2_fma(p2_bc(u1.y), PZ[k], p2_fma(p2_bc(u1.x), PY[k], p2_fma(p2_bc(u0.w), PX[k], p2_bc(q3.y))));
+                const P2 e1 = p2_fma(p2_bc(u2.x), PZ[k], p2_fma(p2_bc(u1.w), PY[k], p2_fma(p2_bc(u1.z), PX[k], p2_bc(q3.z))));
+                const P2 e2 = p2_fma(p2_bc(-u2.z), e1, p2_fma(p2_bc(-u2.y), e0, p2_bc(q3.w)));
+                float e0a, e0b, e1a, e1b, e2a, e2b, ta, tb, ra, rb, ca, cb;
+                p2_unpack(e0, e0a, e0b); p2_unpack(e1, e1a, e1b); p2_unpack(e2, e2a, e2b); p2_unpack(T[k], ta, tb); p2_unpack(R2[k], ra, rb);
+                if (FACE == kRlFront) { ca = -ra; cb = -rb; }
+                else if (FACE == kRlBack) { ca = ra; cb = rb; }
+                else { const P2 cull = p2_mul(R2[k], cf[k]); p2_unpack(cull, ca, cb); }
+                const float ma = fminf(fminf(fminf(e0a, e1a), e2a), fminf(ta, ca));
+                const float mb = fminf(fminf(fminf(e0b, e1b), e2b), fminf(tb, cb));
+                const P2 ms = p2_fma(As2, p2_pack(fabsf(ra), fabsf(rb)), p2_pack(ma, mb));
+                float ka, kb;
+                p2_unpack(ms, ka, kb);
+                if (k == 0) { rj0 = __funnelshift_l(__float_as_uint(ka), rj0, 1); rj1 = __funnelshift_l(__float_as_uint(kb), rj1, 1); }
+                else        { rj2 = __funnelshift_l(__float_as_uint(ka), rj2, 1); rj3 = __funnelshift_l(__float_as_uint(kb), rj3, 1); }
+            }
+        }
+        keep[0][half] = ~__brev(rj0); keep[1][half] = ~__brev(rj1); keep[2][half] = ~__brev(rj2); keep[3][half] = ~__brev(rj3);
+    }
+}
+RT_DI void rl_filter_tile_runs_mode(int mode, const RlTileParam& tp, const P2 (&ox)[2], const P2 (&oy)[2], const P2 (&oz)[2], const P2 (&dx)[2],
+                                    const P2 (&dy)[2], const P2 (&dz)[2], const P2 (&cf)[2], const P2 As2, uint32_t (&keep)[4][2]) {
+    if (mode == kRlFront) rl_filter_tile_runs<kRlFront>(tp, ox, oy, oz, dx, dy, dz, cf, As2, keep);
+    else if (mode == kRlBack) rl_filter_tile_runs<kRlBack>(tp, ox, oy, oz, dx, dy, dz, cf, As2, keep);
+    else rl_filter_tile_runs<kRlMixed>(tp, ox, oy, oz, dx, dy, dz, cf, As2, keep);
+}
+
 // the loop for the face modes of a block of rays (warp-uniform `mode`)
 template <class REC>
 RT_DI void rl_filter_tile_mode(int mode, REC rec, const P2 (&ox)[2], const P2 (&oy)[2], const P2 (&oz)[2], const P2 (&dx)[2],
@@ -159,7 +219,14 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, const RlTileParam& tp, IO io, co
     // candidates are triangles of the scene: the padding of the tile is masked off once
     const uint32_t v_lo = sc.n_tris >= 32u ? 0xffffffffu : ((1u << sc.n_tris) - 1u);
     const uint32_t v_hi = sc.n_tris >= 64u ? 0xffffffffu : (sc.n_tris > 32u ? ((1u << (sc.n_tris - 32u)) - 1u) : 0u);
+#ifndef RL_PLANE_RUNS
+#define RL_PLANE_RUNS 1
+#endif
+#if RL_PLANE_RUNS
+    const P2 As2 = p2_bc(sc.filter_As_runs);
+#else
     const P2 As2 = p2_bc(sc.filter_As);
+#endif
     // exactly 1.0f, but opaque to ptxas: a packed multiply by it MATERIALISES each ray operand in its own aligned
     // register pair (a plain pack is coalesced with the LDG.128 destination quads and re-packed inside the loop)
     const P2 one2 = p2_bc(__fmaf_rn(sc.filter_g, 0.0f, 1.0f));
@@ -220,7 +287,11 @@ RT_DI void cast_rays_in_lanes(const DScene& sc, const RlTileParam& tp, IO io, co
         const int mode = rl_block_mode(have_front, have_back, have_both);
         // phase 1: the candidate masks of this lane's four rays
         uint32_t keep[4][2];
+#if RL_PLANE_RUNS
+        rl_filter_tile_runs_mode(mode, tp, ox, oy, oz, dx, dy, dz, cf, As2, keep);
+#else
         rl_filter_tile_mode(mode, RlRecParam{tp}, ox, oy, oz, dx, dy, dz, cf, As2, keep);
+#endif
 #ifdef RL_DIAG_LOOP2   // timing experiment: the loop twice (the second result is masked by a run-time zero)
         {
             uint32_t keep2[4][2];

@@ -27,7 +27,9 @@
 //   RlTileParam (scenes of one tile)   the same 16 numbers per triangle, multipliers and addends apart, handed to the cast
 //        kernels as a KERNEL PARAMETER (constant bank): {n.xyz 2^-108, m_p.x} {m_p.yz, m_q.xy} {m_q.z, a, b, 0} and
 //        {d 2^-108, w_p, w_q, c}.  The multipliers reach the FFMA2s through uniform registers (LDCU -> FFMA2 R, R, UR, R):
-//        no shared-memory loads in the loop and one vector-register operand less per instruction.
+//        no shared-memory loads in the loop and one vector-register operand less per instruction.  The spare slot is 1.0
+//        where a triangle starts a new PLANE RUN: consecutive triangles of one plane (the halves of a square, the fan of a
+//        polygon) share the plane terms of the run's first triangle in the loop (b200rt_api.cu, pack_filter).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -80,6 +82,7 @@ struct DScene {
     float origin_bound;      // filter slack was derived for ray origins with |o| <= origin_bound
     float filter_A;          // slack per unit |1/(n.dir)|   (64u * 2S)
     float filter_As;         // filter_A * 2^-108: the same slack against the scaled plane rows of the rays-in-lanes records
+    float filter_As_runs;    // ... for the loop over RlTileParam, whose coplanar runs share the plane of their first triangle
     const struct RlTileParam* h_tile0;   // HOST pointer (launchers only): tile 0 of the scene as a kernel parameter
     float filter_g;          // |n.dir| below this always passes the filter (2^-18)
 };
