@@ -122,7 +122,7 @@ DEV_SYMBOLS = ["b200rt_filter_bench", "b200rt_pipe_bench"]
 EXPORTED_SYMBOLS = [
     "b200rt_create", "b200rt_destroy", "b200rt_strerror", "b200rt_last_cuda_error", "b200rt_device_info",
     "b200rt_upload_scene", "b200rt_render_whitted", "b200rt_render_whitted_device", "b200rt_render_distributed",
-    "b200rt_render_distributed_device", "b200rt_resolve_device", "b200rt_intersect", "b200rt_intersect_device",
+    "b200rt_render_distributed_device", "b200rt_render_distributed_strips_device", "b200rt_resolve_device", "b200rt_intersect", "b200rt_intersect_device",
     "b200rt_post_process", "b200rt_post_process_device", "b200rt_encode_srgb8", "b200rt_encode_srgb8_device",
     "b200rt_write_png_rgb8",
     "b200rt_get_stats", "b200rt_reset_stats", "b200rt_set_kernel_timing", "b200rt_measure_fp32_peak",
@@ -163,6 +163,8 @@ def load_library() -> C.CDLL:
         "b200rt_render_distributed": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), C.c_uint32, C.c_uint32, vp]),
         "b200rt_render_distributed_device": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), C.c_uint32,
                                                        C.c_uint32, vp, vp]),
+        "b200rt_render_distributed_strips_device": (C.c_int, [vp, C.POINTER(Camera), C.POINTER(Params), C.c_uint32, C.c_uint32, vp, vp,
+                                                              C.c_uint32, C.c_uint32, C.c_uint32]),
         "b200rt_resolve_device": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
         "b200rt_intersect": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp]),
         "b200rt_intersect_device": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, vp, vp]),

@@ -237,6 +237,7 @@ int make_params(const b200rt_params& p, uint32_t epoch_begin, uint32_t epoch_cou
     o.width = p.width; o.height = p.height;
     o.row_begin = p.row_count ? p.row_begin : 0u;
     o.row_count = p.row_count ? p.row_count : p.height;
+    o.strip_rows = 1u << 30; o.strip_parts = 1u; o.strip_part = 0u; o.local_row0 = 0u;   // contiguous rows
     o.depth = p.depth;
     o.threshold = p.threshold;
     o.refract_max_distance = p.refract_max_distance;
@@ -572,8 +573,26 @@ int b200rt_render_whitted(b200rt_ctx* ctx, const b200rt_camera* cam, const b200r
     return B200RT_OK;
 }
 
+static int render_distributed_device_impl(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
+                                          uint32_t epoch_begin, uint32_t epoch_count, float* d_accum, void* cuda_stream,
+                                          uint32_t strip_rows, uint32_t strip_parts, uint32_t strip_part);
+
 int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
                                      uint32_t epoch_begin, uint32_t epoch_count, float* d_accum, void* cuda_stream) {
+    return render_distributed_device_impl(ctx, cam, params, epoch_begin, epoch_count, d_accum, cuda_stream, 0u, 1u, 0u);
+}
+
+int b200rt_render_distributed_strips_device(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
+                                            uint32_t epoch_begin, uint32_t epoch_count, float* d_accum, void* cuda_stream,
+                                            uint32_t strip_rows, uint32_t n_parts, uint32_t part) {
+    if (strip_rows == 0u || n_parts == 0u || part >= n_parts) return B200RT_ERR_INVALID;
+    if (params && (params->tracer == B200RT_TRACER_MEGAKERNEL || params->cast_mode == B200RT_CAST_BRUTE_EXACT)) return B200RT_ERR_UNSUPPORTED;
+    return render_distributed_device_impl(ctx, cam, params, epoch_begin, epoch_count, d_accum, cuda_stream, strip_rows, n_parts, part);
+}
+
+static int render_distributed_device_impl(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
+                                          uint32_t epoch_begin, uint32_t epoch_count, float* d_accum, void* cuda_stream,
+                                          uint32_t strip_rows, uint32_t strip_parts, uint32_t strip_part) {
     if (!ctx || !cam || !params || !d_accum) return B200RT_ERR_INVALID;
     if (!ctx->have_scene) return B200RT_ERR_NO_SCENE;
     if (((uintptr_t)d_accum & 15u) != 0) return B200RT_ERR_INVALID;  // float4 accumulators
@@ -585,6 +604,14 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
     CU(cudaSetDevice(ctx->device));
     rc = ensure_origin_bound(ctx, *cam, *params);
     if (rc != B200RT_OK) return rc;
+    if (strip_parts > 1u) {
+        // this launch owns the strips s of the band with s % strip_parts == strip_part: count its rows
+        const uint32_t R = dp.row_count;
+        uint32_t mine = 0u;
+        for (uint32_t s0 = strip_part * strip_rows; s0 < R; s0 += strip_parts * strip_rows) mine += std::min(strip_rows, R - s0);
+        dp.strip_rows = strip_rows; dp.strip_parts = strip_parts; dp.strip_part = strip_part;
+        dp.row_count = mine;                 // local rows; frame rows through wf_frame_row
+    }
     cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the CUDA default stream
     CU(cudaEventRecord(ctx->ev0, st));
     ctx->last_rounds = 0;
@@ -612,7 +639,8 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
                 const uint32_t en = std::min(epar, epoch_count - e0);
                 for (uint32_t r = 0; r < dp.row_count; r += band_rows) {
                     DParams band = dp;
-                    band.row_begin = dp.row_begin + r;
+                    if (dp.strip_parts > 1u) band.local_row0 = r;          // (strips: sub-bands of the launch's LOCAL rows)
+                    else band.row_begin = dp.row_begin + r;
                     band.row_count = std::min(band_rows, dp.row_count - r);
                     band.epoch_begin = epoch_begin + e0;
                     band.epoch_count = en;

@@ -70,6 +70,8 @@ NcclApi& nccl() {
     return api;
 }
 
+constexpr uint32_t kStripRows = 16u;   // rows per strip of the row-sharded stochastic frame ("interleaved 16-row strips")
+
 // contiguous split [g*T/G, (g+1)*T/G)  
 void shard_range(uint32_t total, int rank, int world, uint32_t* begin, uint32_t* count) {
     const uint64_t b = (uint64_t)rank * total / (uint64_t)world, e = (uint64_t)(rank + 1) * total / (uint64_t)world;
@@ -159,8 +161,8 @@ int for_members(b200rt_group* g, F f) {
     return B200RT_OK;
 }
 
-// by_rows = false: epochs sharded, one ncclReduce(sum) to rank 0;  by_rows = true: rows sharded (every rank renders all the
-// epochs of its band: a frame of ONE epoch - 10 M "photons" of C5 - has nothing else to split), bands gathered on rank 0
+// by_rows = false: epochs sharded, one ncclReduce(sum) to rank 0;  by_rows = true: rows sharded in interleaved strips (every
+// rank renders all the epochs of its rows: a frame of ONE epoch - 10 M "photons" of C5 - has nothing else to split)
 int render_distributed_member(b200rt_group* g, Member& m, const b200rt_camera* cam, const b200rt_params* params,
                               uint32_t epoch_begin, uint32_t epoch_count, float* out_accum, float* d_out_accum, bool by_rows) {
     m.rc = B200RT_OK;
@@ -174,7 +176,6 @@ int render_distributed_member(b200rt_group* g, Member& m, const b200rt_camera* c
         if (rc != B200RT_OK) return rc;
         d_acc = static_cast<float*>(m.d_buf);
     }
-    const uint32_t r_base = params->row_count ? params->row_begin : 0u, r_total = params->row_count ? params->row_count : H;
     GCU(m, cudaEventRecord(m.ev0, m.stream));
     // a fresh frame: the accumulators start at zero on the device (nothing travels host -> device but the arguments)
     GCU(m, cudaMemsetAsync(d_acc, 0, n * sizeof(float), m.stream));
@@ -185,28 +186,14 @@ int render_distributed_member(b200rt_group* g, Member& m, const b200rt_camera* c
         if (rc != B200RT_OK) return fail(m, rc, std::string("b200rt_render_distributed_device: ") + b200rt_last_cuda_error(m.ctx));
         if (g->n_ranks > 1) GNC(m, nccl().Reduce(d_acc, d_acc, n, ncclFloat, ncclSum, 0, m.comm, m.stream));
     } else {
-        uint32_t r0, rn;
-        shard_range(r_total, m.rank, g->n_ranks, &r0, &rn);
-        if (rn) {
-            b200rt_params p = *params;
-            p.row_begin = r_base + r0;
-            p.row_count = rn;
-            int rc = b200rt_render_distributed_device(m.ctx, cam, &p, epoch_begin, epoch_count, d_acc, m.stream);
-            if (rc != B200RT_OK) return fail(m, rc, std::string("b200rt_render_distributed_device: ") + b200rt_last_cuda_error(m.ctx));
-        }
-        if (g->n_ranks > 1) {
-            GNC(m, nccl().GroupStart());
-            if (m.rank == 0) {
-                for (int r = 1; r < g->n_ranks; ++r) {
-                    uint32_t q0, qn;
-                    shard_range(r_total, r, g->n_ranks, &q0, &qn);
-                    if (qn) GNC(m, nccl().Recv(d_acc + 4 * (size_t)(r_base + q0) * W, (size_t)qn * W * 4, ncclFloat, r, m.comm, m.stream));
-                }
-            } else if (rn) {
-                GNC(m, nccl().Send(d_acc + 4 * (size_t)(r_base + r0) * W, (size_t)rn * W * 4, ncclFloat, 0, m.comm, m.stream));
-            }
-            GNC(m, nccl().GroupEnd());
-        }
+        // rows in 16-row strips, strip s to rank s % G; the accumulators of the ranks have disjoint supports (zero
+        // elsewhere), so one ncclReduce(sum) assembles the frame: bitwise what one GPU renders (x + 0 = x)
+        int rc;
+        if (g->n_ranks == 1) rc = b200rt_render_distributed_device(m.ctx, cam, params, epoch_begin, epoch_count, d_acc, m.stream);
+        else rc = b200rt_render_distributed_strips_device(m.ctx, cam, params, epoch_begin, epoch_count, d_acc, m.stream, kStripRows,
+                                                          (uint32_t)g->n_ranks, (uint32_t)m.rank);
+        if (rc != B200RT_OK) return fail(m, rc, std::string("b200rt_render_distributed_strips_device: ") + b200rt_last_cuda_error(m.ctx));
+        if (g->n_ranks > 1) GNC(m, nccl().Reduce(d_acc, d_acc, n, ncclFloat, ncclSum, 0, m.comm, m.stream));
     }
     GCU(m, cudaEventRecord(m.ev1, m.stream));
     if (m.rank == 0 && out_accum)

@@ -99,7 +99,11 @@ struct DCamera {
 };
 
 struct DParams {
-    uint32_t width, height, row_begin, row_count;
+    uint32_t width, height, row_begin, row_count;   // row_count LOCAL rows are rendered, local row L = frame row wf_frame_row(p, L)
+    // Rows in STRIPS (wavefront tracer only): the band starting at row_begin is cut into strips of strip_rows rows and this
+    // launch owns the strips s with s % strip_parts == strip_part; local_row0 = index of the launch's first local row among
+    // the owned rows.  strip_parts = 1: every row, contiguous (strip_rows is then 2^30).
+    uint32_t strip_rows, strip_parts, strip_part, local_row0;
     int32_t depth;
     float threshold, refract_max_distance;
     uint32_t tir_retries;
@@ -108,6 +112,12 @@ struct DParams {
     uint32_t cast_mode;
     uint32_t epoch_begin, epoch_count;
 };
+
+// frame row of local row L of a launch (see DParams)
+__host__ __device__ inline uint32_t wf_frame_row(const DParams& p, uint32_t L) {
+    const uint32_t l = p.local_row0 + L, si = l / p.strip_rows;
+    return p.row_begin + (si * p.strip_parts + p.strip_part) * p.strip_rows + (l - si * p.strip_rows);
+}
 
 struct DCounters {  // device-side statistics, one 64-bit atomic per CTA at kernel end
     unsigned long long casts, tri_pairs, sph_pairs, confirms, samples, fallbacks;

@@ -445,7 +445,7 @@ struct WfPrimaryIO {
     RT_DI void fetch(uint32_t pid, DRay& r) const {
         const uint32_t pix = pid % wb.n_pixels, e_lane = pid / wb.n_pixels;
         Rng rng;
-        wf_open_sample(cam, p, pix % p.width, p.row_begin + pix / p.width, e_lane, rng, r);
+        wf_open_sample(cam, p, pix % p.width, wf_frame_row(p, pix / p.width), e_lane, rng, r);
     }
     RT_DI bool want_attrs(uint32_t) const { return true; }
     RT_DI bool all_sphere_uv() const { return false; }
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
 
         // pixel of this path: slot e_lane of pixel pix renders samples e_lane, e_lane + epar, ...
         const uint32_t pix = pid % wb.n_pixels, e_lane = pid / wb.n_pixels;
-        const uint32_t px = pix % p.width, py = p.row_begin + pix / p.width;
+        const uint32_t px = pix % p.width, py = wf_frame_row(p, pix / p.width);
 
         // ---- load: only the rows this segment reads -----------------------------------------------------------------
         if (valid && !kIndexed) {
@@ -1039,7 +1039,7 @@ __global__ void wf_combine_kernel(const WfBuffers wb, const DParams p, float4* _
         const float4 v = wb.st[((size_t)e * wb.n_pixels + pix) * kStateRows + ROW_SUM];
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    const size_t at = (size_t)(p.row_begin + pix / p.width) * p.width + pix % p.width;
+    const size_t at = (size_t)wf_frame_row(p, pix / p.width) * p.width + pix % p.width;
     float4 v = accum[at];
     v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
     accum[at] = v;

@@ -224,6 +224,12 @@ int b200rt_render_distributed(b200rt_ctx* ctx, const b200rt_camera* cam, const b
 int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
                                      uint32_t epoch_begin, uint32_t epoch_count, float* d_accum,
                                      void* cuda_stream);
+/* The same for an INTERLEAVED share of the rows: the band params->row_* is cut into strips of strip_rows rows and the call
+ * renders the strips s with s % n_parts == part (wavefront tracer only).  Strips balance a frame whose cost varies from
+ * top to bottom over several GPUs; every pixel sample is what the whole-frame call renders (bitwise). */
+int b200rt_render_distributed_strips_device(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
+                                            uint32_t epoch_begin, uint32_t epoch_count, float* d_accum, void* cuda_stream,
+                                            uint32_t strip_rows, uint32_t n_parts, uint32_t part);
 /* Note: with B200RT_TRACER_WAVEFRONT the call polls a device counter to know when every path has retired, i.e.
  * it synchronises with `cuda_stream` a few times while it enqueues rounds; on return all but the final
  * accumulate kernel have completed.  B200RT_TRACER_MEGAKERNEL enqueues one kernel and returns. */
@@ -296,8 +302,10 @@ int b200rt_group_render_distributed(b200rt_group* group, const b200rt_camera* ca
 /* d_accum_root: device buffer on rank 0's GPU that receives the reduced frame (NULL elsewhere); synchronous. */
 int b200rt_group_render_distributed_device(b200rt_group* group, const b200rt_camera* cam, const b200rt_params* params,
                                            uint32_t epoch_begin, uint32_t epoch_count, float* d_accum_root);
-/* The same frame sharded by ROWS instead (every rank renders all the epochs of its band; the bands are gathered on rank
- * 0): the split for frames of few epochs, e.g. the 10 M one-sample "photons" of a 4000 x 2500 frame. */
+/* The same frame sharded by ROWS instead (every rank renders all the epochs of its rows): the split for frames of few
+ * epochs, e.g. the 10 M one-sample "photons" of a 4000 x 2500 frame.  Rank g takes the 16-row strips
+ * s with s % G == g (interleaved: the cost of a frame varies from top to bottom), and one ncclReduce(sum) of the
+ * accumulators, whose supports are disjoint, assembles the frame on rank 0: bitwise the single-GPU frame. */
 int b200rt_group_render_distributed_rows(b200rt_group* group, const b200rt_camera* cam, const b200rt_params* params,
                                          uint32_t epoch_begin, uint32_t epoch_count, float* out_accum);
 int b200rt_group_render_distributed_rows_device(b200rt_group* group, const b200rt_camera* cam, const b200rt_params* params,

@@ -203,6 +203,9 @@ extern "C" {
                                      epoch_begin: u32, epoch_count: u32, accum: *mut f32) -> c_int;
     pub fn b200rt_render_distributed_device(ctx: *mut b200rt_ctx, cam: *const b200rt_camera, params: *const b200rt_params,
                                             epoch_begin: u32, epoch_count: u32, d_accum: *mut f32, cuda_stream: *mut c_void) -> c_int;
+    pub fn b200rt_render_distributed_strips_device(ctx: *mut b200rt_ctx, cam: *const b200rt_camera, params: *const b200rt_params,
+                                                   epoch_begin: u32, epoch_count: u32, d_accum: *mut f32, cuda_stream: *mut c_void,
+                                                   strip_rows: u32, n_parts: u32, part: u32) -> c_int;
     pub fn b200rt_resolve_device(ctx: *mut b200rt_ctx, d_accum: *const f32, d_out_rgb: *mut f32, n_pixels: usize, cuda_stream: *mut c_void) -> c_int;
     /// post_process, main.rs:748-762
     pub fn b200rt_post_process(ctx: *mut b200rt_ctx, rgb: *mut f32, n_pixels: usize, p98_out: *mut f32) -> c_int;

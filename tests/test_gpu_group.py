@@ -87,3 +87,37 @@ def test_two_gpu_group_matches_one_gpu(b200rt, gpu_ctx, fixture_world):
     t_rgb, _ = g.render_whitted(cam, tiny)
     assert np.array_equal(t_rgb.view(np.uint32), gpu_ctx.render_whitted(cam, tiny)[0].view(np.uint32))
     g.close()
+
+
+def test_row_strips_assemble_the_frame_bitwise(b200rt, gpu_ctx):
+    """b200rt_render_distributed_strips_device: the strips s % 3 == part of three calls fill disjoint rows, and their sum is
+    bitwise the whole-frame render (what a 3-rank row-sharded group reduces on rank 0); ragged last strip, band of rows."""
+    import ctypes as C
+    import torch
+    lib = b200rt.load_library()
+    cam = b200rt.fixture_camera()
+    for (w, h, band) in ((200, 77, None), (160, 120, (13, 90))):
+        p = b200rt.default_params(width=w, height=h, seed=9)
+        if band:
+            p = b200rt.copy_params(p, row_begin=band[0], row_count=band[1])
+        ref = gpu_ctx.render_distributed(cam, p, 1, 2)
+        total = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+        seen = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+        for part in range(3):
+            d = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+            rc = lib.b200rt_render_distributed_strips_device(gpu_ctx._h, C.byref(cam), C.byref(p), 1, 2, C.c_void_p(d.data_ptr()),
+                                                             C.c_void_p(torch.cuda.current_stream().cuda_stream), 16, 3, part)
+            assert rc == 0, rc
+            torch.cuda.synchronize()
+            rows = (d[..., 3] != 0).any(dim=1)
+            seen += (d != 0).any(dim=2).to(torch.int32)
+            r0 = band[0] if band else 0
+            idx = torch.nonzero(rows).flatten().cpu().numpy()
+            assert all(((int(r) - r0) // 16) % 3 == part for r in idx)          # only its own strips
+            total += d
+        assert int(seen.max()) <= 1
+        assert np.array_equal(total.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    bad = b200rt.default_params(width=64, height=64, tracer=b200rt.TRACER_MEGAKERNEL)
+    d = torch.zeros((64, 64, 4), dtype=torch.float32, device="cuda")
+    assert lib.b200rt_render_distributed_strips_device(gpu_ctx._h, C.byref(cam), C.byref(bad), 0, 1, C.c_void_p(d.data_ptr()), None, 16, 2, 0) == b200rt.ERR_UNSUPPORTED
+    assert lib.b200rt_render_distributed_strips_device(gpu_ctx._h, C.byref(cam), C.byref(p), 0, 1, C.c_void_p(d.data_ptr()), None, 16, 2, 2) == b200rt.ERR_INVALID
