@@ -446,13 +446,128 @@ def run_b200(args):
     return 0
 
 
+# --------------------------------------------------------------------------------------------------------
+def run_k2(args):
+    """K2: World::cast on its own (b200rt_intersect_device / b200rt_intersect): the primary camera rays of the 3840x2160
+    frame of the fixture scene (8.3 M rays, the population the tracers produce), resident AoS rays and hits of the public
+    API.  One step = one cast of every ray; value = casts per second (M rays/s).  With N GPUs the rays are split
+    contiguously over the ranks (no collective: the path has no exchange step)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    b = ge.load_package()
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world_size, device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    W, H = 3840, 2160
+    ctx = b.Context(local_rank)
+    world = b.World.fixture()
+    ctx.upload_scene(world)
+    sc = world.scene()
+    cam = b.fixture_camera()
+    # Camera::shoot (main.rs:84-99) for every pixel, in numpy (test / bench infrastructure: the rays are the INPUT)
+    toward = np.array(cam.toward, dtype=np.float64); toward /= np.linalg.norm(toward)
+    right = np.cross(toward, np.array(cam.up, dtype=np.float64)); right /= np.linalg.norm(right)
+    up2 = np.cross(right, toward); up2 /= np.linalg.norm(up2)
+    t = np.tan(cam.fovy / 2)
+    ys, xs = np.mgrid[0:H, 0:W]
+    d = ((xs - W / 2) / H)[..., None] * (t * right) + ((H / 2 - ys) / H)[..., None] * (t * up2) + toward
+    d /= np.linalg.norm(d, axis=2, keepdims=True)
+    rays = np.zeros(W * H, dtype=b.RAY_DTYPE)
+    rays["origin"] = (np.array(cam.center) + toward * cam.near).astype(np.float32)
+    rays["direction"] = d.reshape(-1, 3).astype(np.float32)
+    rays["exclude_prim"] = -1
+    r0, rn = shard(W * H, rank, world_size)
+    rays = rays[r0:r0 + rn]
+    n = len(rays)
+    h_rays = torch.from_numpy(rays.view(np.uint8).copy()).pin_memory()
+    d_rays = h_rays.to(dev)
+    d_hits = torch.empty(n * b.HIT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    h_hits = np.zeros(n, dtype=b.HIT_DTYPE)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # L2: 8.3 M rays x (36 B in + 48 B out) = 697 MB per step exceed the 126 MB L2
+    for _ in range(max(args.warmup, 3)):
+        ctx.intersect_device(d_rays.data_ptr(), n, d_hits.data_ptr(), b.CAST_TWO_PHASE, stream)
+    barrier()
+    ctx.reset_stats()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler: sampler.start()
+    steps = max(args.steps, 20)            # a step is 0.7 ms: enough of them for the clock sampler to see the load
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        ctx.intersect_device(d_rays.data_ptr(), n, d_hits.data_ptr(), b.CAST_TWO_PHASE, stream)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = max_over_ranks(ev0.elapsed_time(ev1) / steps)
+    st = ctx.stats()
+    total_rays = W * H
+    value = total_rays / (ms_per_step * 1e-3) / 1e6
+    # end to end: host rays in, host hits out
+    ctx.intersect(rays)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        h_hits = ctx.intersect(rays)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / 3)
+    peaks, peak_src = measured_peaks()
+    info = ctx.device_info()
+    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    peak_tflops = info["sm_count"] * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    flops = n * (sc.n_triangles * FLOP_TRI + sc.n_spheres * FLOP_SPH)
+    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s (World::cast calls per second, the intersection kernel on its own)", "value": value, "unit": "Mrays/s",
+            "n_gpus": world_size, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "K2: World::cast of the 8 294 400 primary camera rays of the fixture scene at 3840x2160 (64 triangles + 4 spheres per cast)",
+                       "sharding": "rays", "l2": "697 MB of rays + hits per step exceed L2"},
+            "roofline": {"bound": "fp32", "kernel": "intersect_rl_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tflops, "traffic": None,
+                         "peak_source": f"SMs({info['sm_count']}) x 128 lanes x 2 flop x sm_max_mhz({sm_max_mhz:.0f}, {peak_src} MEASURED_PEAKS.json)",
+                         "exact_tests_per_cast": st["exact_confirms"] / max(st["casts"], 1), "hit_fraction": float((h_hits["prim_id"] >= 0).mean())},
+            "cpu_baseline": None,
+            "e2e": {"value": total_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n * 36, "d2h_bytes_per_step": n * 48,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["k2"])
     ap.add_argument("--width", type=int, default=0, help="dev only: override (marks the line REDUCED)")
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--epochs", type=int, default=0)
@@ -460,6 +575,11 @@ def main():
     ap.add_argument("--tracer", default="wavefront", choices=["wavefront", "megakernel"],
                     help="GPU schedule of the stochastic tracer (same samples, same bits)")
     args = ap.parse_args()
+    if args.workload == "k2":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "k2 is the GPU kernel's own micro-workload; the CPU arm is timed on c1..c5"}), flush=True)
+            return 0
+        return run_k2(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
