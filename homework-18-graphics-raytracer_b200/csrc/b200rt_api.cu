@@ -619,7 +619,8 @@ static int render_distributed_device_impl(b200rt_ctx* ctx, const b200rt_camera* 
     ctx->wf_timing.cast_ms = ctx->wf_timing.logic_ms = ctx->wf_timing.primary_ms = 0.0;
     ctx->wf_timing.cast_launches = 0;
     if (epoch_count) {
-        if (params->tracer == B200RT_TRACER_MEGAKERNEL || params->cast_mode == B200RT_CAST_BRUTE_EXACT) {
+        // (the wavefront's control row packs the pixel in 16 + 16 bits: frames beyond 65535 take the megakernel)
+        if (params->tracer == B200RT_TRACER_MEGAKERNEL || params->cast_mode == B200RT_CAST_BRUTE_EXACT || dp.width > 65535u || dp.height > 65535u) {
             CU(launch_distributed(ctx->scene, dc, dp, d_accum, ctx->d_cnt, st));
             ctx->last_launches = 1;
         } else {

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(TraceCfg<MODE>::kThreads, TraceCfg<MODE>::kMin
                             Pending e;
                             e.o = escape_ray.o; e.d = escape_ray.d; e.faces = escape_ray.face | (escape_ray.ex_face << 2);
                             e.ex_prim = escape_ray.ex_prim; e.depth = depth - 1; e.contribution = contribution * refr_c;
-                            e.throughput = T * (nl_powf(mat.opaque_decay, rf_travel) * refr_c);   // main.rs:508, 518
+                            e.throughput = T * (color_pow(mat.opaque_decay, rf_travel) * refr_c);   // main.rs:508, 518
                             stack[sp++] = e;
                         }
                         if (do_refl) {
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(TraceCfg<MODE>::kThreads, TraceCfg<MODE>::kMin
                         else { sh_on = true; shade_purpose = SH_FINAL; }               // get_shade(&scattered_hit)
                     } else {
                         // probe / decay of the CURRENT material, before the hit is replaced
-                        if (ray_type == 2) { pend_factor.x = nl_powf(mat.opaque_decay, rf_travel); shade_purpose = SH_NEXT_REFR; }
+                        if (ray_type == 2) { pend_factor.x = color_pow(mat.opaque_decay, rf_travel); shade_purpose = SH_NEXT_REFR; }
                         else {
                             // get_diffuse (main.rs:566-570) or get_specular (main.rs:585-589) of the probe
                             probe_pending = true;
@@ -635,6 +635,13 @@ namespace {
 struct ApiRayIO {
     const b200rt_ray* __restrict__ rays;
     b200rt_hit* __restrict__ hits;
+#if RL_PREFETCH
+    static constexpr bool kPrefetch = false;   // consecutive rays: coalesced loads, nothing to gather
+    struct Loc { const uint32_t* list; uint32_t first, count, slot; };
+    RT_DI Loc locate(uint32_t) const { return Loc{nullptr, 0u, 0u, 0u}; }
+    RT_DI uint32_t item_from(uint32_t idx, uint32_t) const { return idx; }
+    RT_DI void touch(uint32_t, uint32_t, void*) const {}
+#endif
     RT_DI uint32_t item(uint32_t idx) const { return idx; }
     RT_DI void fetch(uint32_t tag, DRay& r) const {
         const b200rt_ray in = rays[tag];

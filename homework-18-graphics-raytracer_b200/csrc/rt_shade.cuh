@@ -45,18 +45,9 @@ RT_DI MatEval material_approx(const DMaterial* __restrict__ mats, uint32_t objec
 // materials.rs:40-44
 RT_DI f3 adjust_normal(const MatEval& m, f3 normal) { return rotate(from_arc(mk3(0.0f, 0.0f, 1.0f), normal), m.normal_ts); }
 
-// powf(x, e) of the Phong lobe (materials.rs:63: x = max(R.V, 0) in [0, 1 + ulps], e = 1 / (smoothness + eps) up to 8.4e6)
-// without the libm call where its result is known: x = 0 gives 0, and x^e below 2^-160 - decided on MUFU.LG2, whose
-// absolute error of 2^-22 moves e * log2(x) by less than 2.1 - rounds to +0 in any powf (half the smallest subnormal is
-// 2^-150).  Mirror-like materials (e = 1e5: x^e underflows for every x < 0.9989) skip the ~90 instructions of powf nearly always.
-RT_DI float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-RT_DI float phong_pow(float x, float e) {
-    if (e > 0.0f) {                                     // (any material the builder accepts; otherwise plain powf)
-        if (x == 0.0f) return 0.0f;
-        if (x < 1.0f && e * lg2_approx(x) < -170.0f) return 0.0f;
-    }
-    return nl_powf(x, e);
-}
+// powf(x, e) of the Phong lobe (materials.rs:63: x = max(R.V, 0) in [0, 1 + ulps], e = 1 / (smoothness + eps) up to 8.4e6):
+// a colour (rt_math.cuh: color_pow)
+RT_DI float phong_pow(float x, float e) { return color_pow(x, e); }
 
 // materials.rs:46-53
 RT_DI f3 get_diffuse(const MatEval& m, f3 n, f3 l) {
@@ -113,7 +104,7 @@ RT_DI bool approx_light(const DLight& L, f3 position, DirLight& out) {
         const f3 sd = mk3(L.direction);
         const float angle = fabsf(nl_atan2f(magnitude(cross(sd, offset)), dot(sd, offset)));  // Vector3::angle
         if (angle > L.angle) return false;
-        const float angular = nl_powf(1.0f - angle / L.angle, L.softness + kF32Epsilon);
+        const float angular = color_pow(1.0f - angle / L.angle, L.softness + kF32Epsilon);
         const float dist_att = 1.0f / (magnitude(offset) + kF32Epsilon);
         out.has_origin = true;
         out.origin = origin;
@@ -137,21 +128,24 @@ RT_DI bool approx_light(const DLight& L, f3 position, DirLight& out) {
 // The same Directional as approx_light() for a light that is known to reach `position`, from what the wavefront kept
 // when it requested the shadow ray: its direction (dir = normalize(position - origin), lights.rs:66 / 80) and the spot's
 // angular factor.  Skips the atan2 / powf / normalize of the second evaluation; every value has the bits of the first.
-RT_DI void approx_light_cached(const DLight& L, f3 position, f3 dir, float angular, DirLight& out) {
+RT_DI void approx_light_cached(const DLight& L, f3 position, f3 dir, float angular, DirLight& out, float& dist_to_origin) {
     out.dir = dir;
     out.angular = angular;
     if (L.kind == B200RT_LIGHT_DIRECTIONAL) {
         out.has_origin = L.has_origin != 0u;
         out.origin = mk3(L.origin);
         out.color = mk3(L.color);
+        dist_to_origin = -1.0f;   // not formed here
         return;
     }
     const f3 origin = mk3(L.origin);
     const f3 offset = position - origin;
-    const float dist_att = 1.0f / (magnitude(offset) + kF32Epsilon);
+    const float dist = magnitude(offset);
+    const float dist_att = 1.0f / (dist + kF32Epsilon);
     out.has_origin = true;
     out.origin = origin;
     out.color = L.kind == B200RT_LIGHT_SPOT ? mk3(L.color) * angular * dist_att : mk3(L.color) * dist_att;
+    dist_to_origin = dist;   // = distance(position, origin) bit for bit: |a - b| and |b - a| square the same components
 }
 
 // main.rs:328-341 (normal = hit.at.normal, l = hit.ray.direction)

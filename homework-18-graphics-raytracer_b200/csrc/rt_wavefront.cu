@@ -43,7 +43,7 @@ namespace {
 
 // rows that are written together are neighbours, so every store pair fills one whole 32-byte sector
 enum : int {
-    ROW_CTRL = 0,     // flags, depth, rng draws, sample index (4 x u32)
+    ROW_CTRL = 0,     // flags, depth | rng draws << 16, pixel x | y << 16, sample index (4 x u32)
     ROW_RNG,          // Philox block of the sample stream
     ROW_ACC,          // radiance of the sample so far
     ROW_T,            // throughput: what a unit of radiance at the current hit adds to the sample
@@ -336,6 +336,37 @@ struct WfRayIO {
         const uint32_t i = idx - cur_first;
         return i < cur_count ? (cur_list[i] << 3) | cur_slot : 0xffffffffu;     // (padding of the list: no ray)
     }
+    // prefetching (rt_cast_rl.cuh): where a future block's items lie, the item of an index from its prefetched list entry,
+    // and the rows fetch() will read for a path of ray slot `slot`, pulled into L2 by 16-byte cp.async copies
+#if RL_PREFETCH
+    static constexpr bool kPrefetch = true;
+    struct Loc { const uint32_t* list; uint32_t first, count, slot; };
+    RT_DI Loc locate(uint32_t block) const {
+        const uint32_t k = (block >= work.first_block[1] ? 1u : 0u) + (block >= work.first_block[2] ? 1u : 0u) +
+                           (block >= work.first_block[3] ? 1u : 0u) + (block >= work.first_block[4] ? 1u : 0u);
+        Loc l;
+        l.slot = k;
+        l.first = (k == 0u ? work.first_block[0] : k == 1u ? work.first_block[1] : k == 2u ? work.first_block[2] : k == 3u ? work.first_block[3] : work.first_block[4]) * 128u;
+        l.count = k == 0u ? work.count[0] : k == 1u ? work.count[1] : k == 2u ? work.count[2] : k == 3u ? work.count[3] : work.count[4];
+        l.list = work.lists + (size_t)k * work.n;
+        return l;
+    }
+    RT_DI uint32_t item_from(uint32_t idx, uint32_t list_entry) const {
+        const uint32_t i = idx - cur_first;
+        return i < cur_count ? (list_entry << 3) | cur_slot : 0xffffffffu;
+    }
+    RT_DI void touch(uint32_t pid, uint32_t slot, void* scratch) const {
+        if (slot == 0u) rl_cp_async16(scratch, wb.req + (size_t)pid * WF_REQ_ROWS + REQ_O);      // {origin, meta}{direction}: one sector
+        else {
+#if WF_REQ_HP
+            rl_cp_async16(scratch, wb.req + (size_t)pid * WF_REQ_ROWS + REQ_HP);
+#else
+            rl_cp_async16(scratch, wb.st + (size_t)pid * kStateRows + ROW_HPOS);
+#endif
+            rl_cp_async16(scratch, wb.req + (size_t)pid * WF_REQ_ROWS + req_shadow_row(slot - 1u));
+        }
+    }
+#endif
     RT_DI void fetch(uint32_t tag, DRay& r) const {
         const PathMem pm{wb.st, wb.req, tag >> 3};
         if (cur_slot == 0u) pm.get_ray(r);
@@ -440,6 +471,13 @@ struct WfPrimaryIO {
     WfBuffers wb;
     DCamera cam;
     DParams p;
+#if RL_PREFETCH
+    static constexpr bool kPrefetch = false;   // rays are generated, not gathered
+    struct Loc { const uint32_t* list; uint32_t first, count, slot; };
+    RT_DI Loc locate(uint32_t) const { return Loc{nullptr, 0u, 0u, 0u}; }
+    RT_DI uint32_t item_from(uint32_t idx, uint32_t) const { return idx; }
+    RT_DI void touch(uint32_t, uint32_t, void*) const {}
+#endif
     RT_DI void begin_block(uint32_t) const {}
     RT_DI uint32_t item(uint32_t idx) const { return idx; }
     RT_DI void fetch(uint32_t pid, DRay& r) const {
@@ -584,16 +622,22 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         DRay ray;
         ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.face = kFront; ray.ex_prim = -1; ray.ex_face = kFront;
 
-        // pixel of this path: slot e_lane of pixel pix renders samples e_lane, e_lane + epar, ...
-        const uint32_t pix = pid % wb.n_pixels, e_lane = pid / wb.n_pixels;
-        const uint32_t px = pix % p.width, py = wf_frame_row(p, pix / p.width);
+        // pixel of this path: slot e_lane of pixel pix renders samples e_lane, e_lane + epar, ...  The passes that open a
+        // slot (path id = index) derive the pixel from the index; it then travels in the control row, so that the queued
+        // passes do not pay three integer divisions per path (pid / n_pixels, pix / width, the strip of the row)
+        uint32_t px = 0u, py = 0u;
+        if (kIndexed) {
+            const uint32_t pix = pid % wb.n_pixels;
+            px = pix % p.width; py = wf_frame_row(p, pix / p.width);
+        }
 
         // ---- load: only the rows this segment reads -----------------------------------------------------------------
         if (valid && !kIndexed) {
             constexpr bool kNeedRng = seg == WF_SEG_PRIMARY || seg == WF_SEG_SHADE || (FUSED && seg == WF_SEG_BOUNCE);
             float4 r0, r1 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (kNeedRng) pm.ld2(ROW_CTRL, r0, r1); else r0 = pm.ld(ROW_CTRL);
-            flags = f2u(r0.x); depth = __float_as_int(r0.y); rng.draws = f2u(r0.z); sample_idx = f2u(r0.w);
+            flags = f2u(r0.x); depth = (int32_t)(int16_t)(f2u(r0.y) & 0xffffu); rng.draws = f2u(r0.y) >> 16; sample_idx = f2u(r0.w);
+            px = f2u(r0.z) & 0xffffu; py = f2u(r0.z) >> 16;
             rng.x = px; rng.y = py; rng.epoch = p.epoch_begin + sample_idx;
             if (kNeedRng) { rng.b[0] = f2u(r1.x); rng.b[1] = f2u(r1.y); rng.b[2] = f2u(r1.z); rng.b[3] = f2u(r1.w); }
             if (seg != WF_SEG_PRIMARY) {
@@ -628,7 +672,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
             const MatEval mat = material_approx(sc.materials, h.object, h.uv);
             uint32_t purpose;
             if (ray_type == 2u) {
-                pend = mk3(nl_powf(mat.opaque_decay, rf_travel), 0.f, 0.f);
+                pend = mk3(color_pow(mat.opaque_decay, rf_travel), 0.f, 0.f);
                 purpose = SH_NEXT_REFR;
             } else {
                 pend = ray_type == 0u ? get_diffuse(mat, h.normal, ray.d)                    // main.rs:566-570
@@ -693,7 +737,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
             // the slot's first sample: the round-0 cast generated its camera ray from the index; regenerate it (and the
             // sample's stream) instead of reading what an INIT pass would have stored (main.rs:1133-1155)
             if (valid) {
-                sample_idx = e_lane;
+                sample_idx = pid / wb.n_pixels;         // slot e_lane opens with sample e_lane
                 depth = p.depth; flags = 0u;
                 wf_open_sample(cam, p, px, py, sample_idx, rng, ray);
                 w_rng = true;
@@ -770,14 +814,15 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                     if (!((need >> s) & 1u)) continue;
                     DirLight L;
                     const float4 sd = pm.get_shadow_dir(s);                            // {-L.dir, angular} kept by get_shade's entry
-                    approx_light_cached(sc.lights[li0 + s], h.pos, -mk3(sd), sd.w, L);
+                    float dist_light;
+                    approx_light_cached(sc.lights[li0 + s], h.pos, -mk3(sd), sd.w, L, dist_light);
                     const float2 sr = s == 0u ? make_float2(sr01.x, sr01.y) : s == 1u ? make_float2(sr01.z, sr01.w)
                                     : s == 2u ? make_float2(sr23.x, sr23.y) : make_float2(sr23.z, sr23.w);
                     bool occluded = false;
                     if (__float_as_int(sr.x) >= 0) {
                         if (L.has_origin) {
                             const f3 occ = h.pos + (-L.dir) * sr.y;                    // the shadow ray's hit point
-                            if (distance(h.pos, occ) < distance(h.pos, L.origin)) occluded = true;
+                            if (distance(h.pos, occ) < (dist_light >= 0.0f ? dist_light : distance(h.pos, L.origin))) occluded = true;
                         } else occluded = true;
                     }
                     if (!occluded) {
@@ -921,6 +966,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         if (__any_sync(kFullMask, do_finish)) {
             if (do_finish) {
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t e_lane = pid / wb.n_pixels;
                 if (seg != WF_SEG_INIT) {
                     // (a slot's first sample starts its accumulator: no INIT pass zeroed it when round 0 ran fused)
                     const bool first = wb.fused_primary != 0u && sample_idx == e_lane;
@@ -961,7 +1007,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
         }
         // ---- store what changed and append the path to the next round's queues -------------------------------------------
         if (valid && out != OUT_RETIRE) {
-            const float4 ctrl = make_float4(u2f(flags), __int_as_float(depth), u2f(rng.draws), u2f(sample_idx));
+            const float4 ctrl = make_float4(u2f(flags), u2f(((uint32_t)depth & 0xffffu) | (rng.draws << 16)), u2f(px | (py << 16)), u2f(sample_idx));
             // (the INIT pass streams over consecutive paths: measured faster with 128-bit stores, 8.5 vs 12.4 ms per batch)
             constexpr bool kW = seg != WF_SEG_INIT;   // (the INIT pass streams over consecutive paths)
             const float4 rng_row = make_float4(u2f(rng.b[0]), u2f(rng.b[1]), u2f(rng.b[2]), u2f(rng.b[3]));
