@@ -28,6 +28,7 @@ NORMAL_CONST, NORMAL_SINCOS_U = 0, 1
 LIGHT_DIRECTIONAL, LIGHT_SPOT, LIGHT_POINT = 0, 1, 2
 CAST_TWO_PHASE, CAST_BRUTE_EXACT = 0, 1
 TRACER_WAVEFRONT, TRACER_MEGAKERNEL = 0, 1
+OBJ_USE_TEXCOORDS, OBJ_USE_NORMALS = 1, 2
 MAX_DEPTH = 16
 
 
@@ -134,6 +135,7 @@ EXPORTED_SYMBOLS = [
     "b200rt_world_new", "b200rt_world_free",
     "b200rt_world_push_object", "b200rt_world_push_triangle", "b200rt_world_push_flat_triangle",
     "b200rt_world_push_square", "b200rt_world_push_sphere", "b200rt_world_push_light", "b200rt_world_load_obj",
+    "b200rt_world_load_obj_ex", "b200rt_obj_model_count",
     "b200rt_world_scene", "b200rt_world_fixture", "b200rt_fixture_camera", "b200rt_default_params",
 ]
 
@@ -203,6 +205,8 @@ def load_library() -> C.CDLL:
         "b200rt_world_push_sphere": (C.c_int, [vp, C.c_uint32, f32p, C.c_float]),
         "b200rt_world_push_light": (C.c_int, [vp, C.POINTER(Light)]),
         "b200rt_world_load_obj": (C.c_int, [vp, C.c_uint32, C.c_char_p, C.c_float, f32p]),
+        "b200rt_world_load_obj_ex": (C.c_int, [vp, C.c_uint32, C.c_char_p, C.c_float, f32p, C.c_int32, C.c_uint32]),
+        "b200rt_obj_model_count": (C.c_int, [C.c_char_p]),
         "b200rt_world_scene": (C.c_int, [vp, C.POINTER(Scene)]),
         "b200rt_world_fixture": (C.c_int, [vp, C.c_char_p]),
         "b200rt_fixture_camera": (None, [C.POINTER(Camera)]),
@@ -344,6 +348,14 @@ class ObjectProxy:
         """push_triangles(&load_obj(path)) (main.rs:778-807, 810, 825). Returns the triangle count."""
         return _check(load_library().b200rt_world_load_obj(self.world._h, self.object_index, os.fsencode(path),
                                                           float(scale_div), _f32(offset, 3)), "load_obj")
+
+    def load_obj_ex(self, path: str, scale_div: float = 3.0, offset=(0.7, 1.0, -0.5), model_index: int = 0,
+                    use_texcoords: bool = False, use_normals: bool = False) -> int:
+        """What tobj::load_obj returns beyond models[0].positions (main.rs:786-790): model `model_index` (-1 = all models),
+        the file's `vt` as uv and `vn` as vertex normals.  Returns the triangle count."""
+        flags = (OBJ_USE_TEXCOORDS if use_texcoords else 0) | (OBJ_USE_NORMALS if use_normals else 0)
+        return _check(load_library().b200rt_world_load_obj_ex(self.world._h, self.object_index, os.fsencode(path),
+                                                             float(scale_div), _f32(offset, 3), int(model_index), flags), "load_obj_ex")
 
 
 class World:

@@ -125,53 +125,112 @@ struct ObjMesh {
     std::vector<unsigned> indices;          // triangulated, 0-based, first model only
 };
 
-bool parse_obj(FILE* f, ObjMesh& mesh) {
+// A Wavefront OBJ file as tobj 0.1.6 (Cargo.toml:14) reads it: `v` / `vt` / `vn` pools shared by the whole file, and one
+// MODEL per run of faces between `o` / `g` statements (a new name closes the model that has faces).  Faces are
+// triangulated as fans (quads: (0,1,2),(0,2,3)); a corner is `v`, `v/vt`, `v//vn` or `v/vt/vn`, 1-based or negative
+// (relative to the pool's size at that line).  The reference takes models[0].mesh.positions / indices and nothing else
+// (main.rs:787-790); the extended entry point below also offers the other models, `vt` and `vn`.
+struct ObjCorner { int v, vt, vn; };        // 0-based, -1 = absent
+struct ObjModel {
+    std::string name;
+    std::vector<ObjCorner> corners;         // 3 per triangle
+};
+struct ObjFile {
+    std::vector<float> positions, texcoords, normals;   // xyz, uv, xyz
+    std::vector<ObjModel> models;
+};
+
+bool parse_floats(char* q, int n, std::vector<float>& out) {
+    for (int k = 0; k < n; ++k) {
+        char* end = nullptr;
+        const float val = std::strtof(q, &end);          // correctly rounded, like Rust's str::parse::<f32>
+        if (end == q) return false;
+        out.push_back(val);
+        q = end;
+    }
+    return true;
+}
+
+bool resolve_index(long raw, size_t pool, int& out) {
+    const long n = (long)pool;
+    const long c = raw < 0 ? n + raw : raw - 1;
+    if (c < 0 || c >= n) return false;
+    out = (int)c;
+    return true;
+}
+
+bool parse_obj_file(FILE* f, ObjFile& obj) {
     char line[4096];
-    bool first_model_closed = false;
-    bool have_faces = false;
+    ObjModel cur;
+    cur.name = "unnamed_object";                         // tobj's name for faces before any o / g
+    auto is_sep = [](char c) { return c == ' ' || c == '\t'; };
+    auto is_end = [](char c) { return c == '\0' || c == '\n' || c == '\r'; };
     while (std::fgets(line, sizeof line, f)) {
         char* p = line;
-        while (*p == ' ' || *p == '\t') ++p;
-        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) {
-            char* q = p + 1;
-            for (int k = 0; k < 3; ++k) {
-                char* end = nullptr;
-                float val = std::strtof(q, &end);  // correctly rounded, like Rust's str::parse::<f32>
-                if (end == q) return false;
-                mesh.positions.push_back(val);
-                q = end;
-            }
-        } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
-            if (first_model_closed) continue;
-            std::vector<long> corner;
+        while (is_sep(*p)) ++p;
+        if (p[0] == 'v' && is_sep(p[1])) {
+            if (!parse_floats(p + 1, 3, obj.positions)) return false;
+        } else if (p[0] == 'v' && p[1] == 't' && is_sep(p[2])) {
+            if (!parse_floats(p + 2, 2, obj.texcoords)) return false;
+        } else if (p[0] == 'v' && p[1] == 'n' && is_sep(p[2])) {
+            if (!parse_floats(p + 2, 3, obj.normals)) return false;
+        } else if (p[0] == 'f' && is_sep(p[1])) {
+            std::vector<ObjCorner> corner;
             char* q = p + 1;
             for (;;) {
-                while (*q == ' ' || *q == '\t') ++q;
-                if (*q == '\0' || *q == '\n' || *q == '\r' || *q == '#') break;
+                while (is_sep(*q)) ++q;
+                if (is_end(*q) || *q == '#') break;
+                ObjCorner c{-1, -1, -1};
                 char* end = nullptr;
-                long vi = std::strtol(q, &end, 10);
-                if (end == q) return false;
-                corner.push_back(vi);
+                const long vi = std::strtol(q, &end, 10);
+                if (end == q || !resolve_index(vi, obj.positions.size() / 3, c.v)) return false;
                 q = end;
-                while (*q != '\0' && *q != ' ' && *q != '\t' && *q != '\n' && *q != '\r') ++q;  // skip /vt/vn
+                if (*q == '/') {
+                    ++q;
+                    if (*q != '/' && !is_sep(*q) && !is_end(*q)) {
+                        const long ti = std::strtol(q, &end, 10);
+                        if (end == q || !resolve_index(ti, obj.texcoords.size() / 2, c.vt)) return false;
+                        q = end;
+                    }
+                    if (*q == '/') {
+                        ++q;
+                        if (!is_sep(*q) && !is_end(*q)) {
+                            const long ni = std::strtol(q, &end, 10);
+                            if (end == q || !resolve_index(ni, obj.normals.size() / 3, c.vn)) return false;
+                            q = end;
+                        }
+                    }
+                }
+                if (!is_sep(*q) && !is_end(*q)) return false;
+                corner.push_back(c);
             }
             if (corner.size() < 3) return false;
-            const long nv = (long)(mesh.positions.size() / 3);
-            for (long& c : corner) {
-                c = c < 0 ? nv + c : c - 1;
-                if (c < 0 || c >= nv) return false;
-            }
             for (size_t i = 1; i + 1 < corner.size(); ++i) {
-                mesh.indices.push_back((unsigned)corner[0]);
-                mesh.indices.push_back((unsigned)corner[i]);
-                mesh.indices.push_back((unsigned)corner[i + 1]);
+                cur.corners.push_back(corner[0]);
+                cur.corners.push_back(corner[i]);
+                cur.corners.push_back(corner[i + 1]);
             }
-            have_faces = true;
-        } else if ((p[0] == 'g' || p[0] == 'o') && (p[1] == ' ' || p[1] == '\t' || p[1] == '\n' || p[1] == '\r')) {
-            if (have_faces) first_model_closed = true;
+        } else if ((p[0] == 'g' || p[0] == 'o') && (is_sep(p[1]) || is_end(p[1]))) {
+            if (!cur.corners.empty()) { obj.models.push_back(cur); cur.corners.clear(); }
+            char* q = p + 1;
+            while (is_sep(*q)) ++q;
+            char* e = q;
+            while (!is_end(*e)) ++e;
+            while (e > q && is_sep(e[-1])) --e;
+            cur.name.assign(q, e);
         }
     }
-    return have_faces;
+    if (!cur.corners.empty()) obj.models.push_back(cur);
+    return !obj.models.empty();
+}
+
+// the reference's view of the file: models[0], positions through the face's `v` indices
+bool parse_obj(FILE* f, ObjMesh& mesh) {
+    ObjFile obj;
+    if (!parse_obj_file(f, obj)) return false;
+    mesh.positions = obj.positions;
+    for (const ObjCorner& c : obj.models[0].corners) mesh.indices.push_back((unsigned)c.v);
+    return true;
 }
 
 // Built-in copy of the reference mesh as data: 20 unit vertices of a regular dodecahedron and its
@@ -247,6 +306,67 @@ int b200rt_world_load_obj(b200rt_world* w, uint32_t object_index, const char* pa
     std::fclose(f);
     if (!ok) return B200RT_ERR_IO;
     return push_mesh(w, object_index, mesh, scale_div, offset);
+}
+
+// The whole file behind the same transform: any model (or all of them, in file order), and - on request - the file's own
+// texture coordinates (`vt`) and vertex normals (`vn`) instead of uv = (0,0) and the flat normal of triangle()
+// (main.rs:730-739).  A corner without `vt` / `vn` keeps the reference's value.  Normals are not transformed: the
+// reference's placement is a uniform scale and a translation (main.rs:802).
+int b200rt_world_load_obj_ex(b200rt_world* w, uint32_t object_index, const char* path, float scale_div,
+                             const float offset[3], int32_t model_index, uint32_t flags) {
+    if (!w || !path || !offset || object_index >= w->materials.size()) return B200RT_ERR_INVALID;
+    if (flags & ~(uint32_t)(B200RT_OBJ_USE_TEXCOORDS | B200RT_OBJ_USE_NORMALS)) return B200RT_ERR_INVALID;
+    FILE* f = std::fopen(path, "r");
+    if (!f) return B200RT_ERR_IO;
+    ObjFile obj;
+    const bool ok = parse_obj_file(f, obj);
+    std::fclose(f);
+    if (!ok) return B200RT_ERR_IO;
+    if (model_index >= (int32_t)obj.models.size() || model_index < -1) return B200RT_ERR_INVALID;
+    const V3 off = v3(offset);
+    int n = 0;
+    for (size_t m = 0; m < obj.models.size(); ++m) {
+        if (model_index >= 0 && (size_t)model_index != m) continue;
+        const std::vector<ObjCorner>& cs = obj.models[m].corners;
+        for (size_t t = 0; t + 2 < cs.size(); t += 3) {
+            float pos[3][3], uv[3][2];
+            bool own_normals = (flags & B200RT_OBJ_USE_NORMALS) != 0u;
+            for (int k = 0; k < 3; ++k) {
+                const ObjCorner& c = cs[t + k];
+                store(pos[k], v3(&obj.positions[3 * (size_t)c.v]) / scale_div + off);          // main.rs:802
+                const bool has_uv = (flags & B200RT_OBJ_USE_TEXCOORDS) && c.vt >= 0;
+                uv[k][0] = has_uv ? obj.texcoords[2 * (size_t)c.vt] : 0.0f;                     // main.rs:797-799
+                uv[k][1] = has_uv ? obj.texcoords[2 * (size_t)c.vt + 1] : 0.0f;
+                if (c.vn < 0) own_normals = false;
+            }
+            int rc;
+            if (own_normals) {
+                b200rt_vertex v[3];
+                for (int k = 0; k < 3; ++k) {
+                    std::memcpy(v[k].position, pos[k], sizeof(float) * 3);
+                    std::memcpy(v[k].normal, &obj.normals[3 * (size_t)cs[t + k].vn], sizeof(float) * 3);
+                    v[k].uv[0] = uv[k][0]; v[k].uv[1] = uv[k][1];
+                }
+                rc = b200rt_world_push_triangle(w, object_index, v);
+            } else {
+                rc = b200rt_world_push_flat_triangle(w, object_index, pos, uv);
+            }
+            if (rc != B200RT_OK) return rc;
+            ++n;
+        }
+    }
+    return n;
+}
+
+// number of models tobj::load_obj would return for the file (runs of faces between o / g statements), or < 0
+int b200rt_obj_model_count(const char* path) {
+    if (!path) return B200RT_ERR_INVALID;
+    FILE* f = std::fopen(path, "r");
+    if (!f) return B200RT_ERR_IO;
+    ObjFile obj;
+    const bool ok = parse_obj_file(f, obj);
+    std::fclose(f);
+    return ok ? (int)obj.models.size() : B200RT_ERR_IO;
 }
 
 void b200rt_fixture_camera(b200rt_camera* cam) {

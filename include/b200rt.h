@@ -338,6 +338,16 @@ int b200rt_world_push_light(b200rt_world* w, const b200rt_light* light);
  * (the reference hard-codes /3.0 + (0.7,1.0,-0.5), main.rs:802). Returns #triangles or <0. */
 int b200rt_world_load_obj(b200rt_world* w, uint32_t object_index, const char* path,
                           float scale_div, const float offset[3]);
+/* The rest of what tobj::load_obj (tobj 0.1.6, Cargo.toml:14) returns and load_obj drops (main.rs:786-790): the other
+ * models of the file (model_index = k, or -1 for all of them in file order; a model is a run of faces between o / g
+ * statements) and, with the flags, the file's own `vt` as uv and `vn` as vertex normals for the corners that name them
+ * (the others keep uv = (0,0) / the flat normal of triangle(), main.rs:730-739, 797-799).  flags = 0, model_index = 0
+ * is b200rt_world_load_obj.  Returns #triangles or <0. */
+#define B200RT_OBJ_USE_TEXCOORDS 1u
+#define B200RT_OBJ_USE_NORMALS   2u
+int b200rt_world_load_obj_ex(b200rt_world* w, uint32_t object_index, const char* path, float scale_div,
+                             const float offset[3], int32_t model_index, uint32_t flags);
+int b200rt_obj_model_count(const char* path);   /* models in the file (>= 1), or <0 */
 int b200rt_world_scene(const b200rt_world* w, b200rt_scene* out);   /* view, valid until next push/free */
 /* The scene literal of main() (main.rs:810-1075) and its camera (main.rs:1077-1083).
  * obj_path NULL = use the built-in dodecahedron mesh (same 20 v / 36 f as dodecahedron.obj). */

@@ -31,6 +31,8 @@ pub const B200RT_CAST_TWO_PHASE: u32 = 0;
 pub const B200RT_CAST_BRUTE_EXACT: u32 = 1;
 pub const B200RT_TRACER_WAVEFRONT: u32 = 0;
 pub const B200RT_TRACER_MEGAKERNEL: u32 = 1;
+pub const B200RT_OBJ_USE_TEXCOORDS: u32 = 1;
+pub const B200RT_OBJ_USE_NORMALS: u32 = 2;
 
 /// `PositionNormalUV`, geometric.rs:43-47
 #[repr(C)]
@@ -255,6 +257,9 @@ extern "C" {
     pub fn b200rt_world_push_sphere(w: *mut b200rt_world, object_index: u32, center: *const f32, radius: f32) -> c_int;
     pub fn b200rt_world_push_light(w: *mut b200rt_world, light: *const b200rt_light) -> c_int;
     pub fn b200rt_world_load_obj(w: *mut b200rt_world, object_index: u32, path: *const c_char, scale_div: f32, offset: *const f32) -> c_int;
+    pub fn b200rt_world_load_obj_ex(w: *mut b200rt_world, object_index: u32, path: *const c_char, scale_div: f32, offset: *const f32,
+                                    model_index: i32, flags: u32) -> c_int;
+    pub fn b200rt_obj_model_count(path: *const c_char) -> c_int;
     pub fn b200rt_world_scene(w: *const b200rt_world, out: *mut b200rt_scene) -> c_int;
     pub fn b200rt_world_fixture(w: *mut b200rt_world, obj_path: *const c_char) -> c_int;
     pub fn b200rt_fixture_camera(cam: *mut b200rt_camera);

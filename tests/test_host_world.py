@@ -111,6 +111,72 @@ def test_obj_import(b200rt, tmp_path):
     assert tri_array(b200rt, w2.scene())[0, 8:11].tolist() == [1, 0, 0]
 
 
+OBJ_FULL = """# two models, texture coordinates and normals (what tobj::load_obj returns and load_obj drops)
+o first
+v 0 0 0
+v 3 0 0
+v 3 3 0
+v 0 3 0
+vt 0.25 0.5
+vt 1 0
+vt 1 1
+vn 0 0 1
+vn 0 1 0
+f 1/1/1 2/2/1 3/3/2
+f 1//1 3//1 4//1
+g second
+v 0 0 3
+f 1/1 2/2 5/-1
+f -1 -2 -3 -4
+"""
+
+
+def test_obj_import_models_texcoords_normals(b200rt, tmp_path):
+    """N3: the tobj behaviours beyond models[0].positions - model selection, `vt`, `vn`, mixed corner forms."""
+    path = tmp_path / "full.obj"
+    path.write_text(OBJ_FULL)
+    lib = b200rt.load_library()
+    assert lib.b200rt_obj_model_count(str(path).encode()) == 2
+    ident = dict(scale_div=1.0, offset=(0, 0, 0))
+    # flags = 0, model 0 is load_obj
+    wa, wb = b200rt.World(), b200rt.World()
+    oa, ob = wa.push_object(b200rt.color_material()), wb.push_object(b200rt.color_material())
+    assert oa.load_obj(str(path)) == 2 and ob.load_obj_ex(str(path)) == 2
+    assert np.array_equal(tri_array(b200rt, wa.scene()), tri_array(b200rt, wb.scene()))
+    # model 1 alone: its triangle and the quad (a fan of two) over the last four vertices
+    w1 = b200rt.World()
+    o1 = w1.push_object(b200rt.color_material())
+    assert o1.load_obj_ex(str(path), model_index=1, **ident) == 3
+    t = tri_array(b200rt, w1.scene())
+    assert t[0, 16:19].tolist() == [0, 0, 3]                                  # corner 5 = the vertex pushed in `second`
+    assert t[1, 0:3].tolist() == [0, 0, 3] and t[1, 8:11].tolist() == [0, 3, 0] and t[1, 16:19].tolist() == [3, 3, 0]   # -1 -2 -3
+    assert t[2, 16:19].tolist() == [3, 0, 0]                                  # fan: (-1, -3, -4)
+    # all models, with the file's uv and normals
+    w2 = b200rt.World()
+    o2 = w2.push_object(b200rt.color_material())
+    assert o2.load_obj_ex(str(path), model_index=-1, use_texcoords=True, use_normals=True, **ident) == 5
+    t = tri_array(b200rt, w2.scene())
+    assert t[0, 6:8].tolist() == [0.25, 0.5] and t[0, 14:16].tolist() == [1, 0] and t[0, 22:24].tolist() == [1, 1]
+    assert t[0, 3:6].tolist() == [0, 0, 1] and t[0, 19:22].tolist() == [0, 1, 0]      # per-corner vn
+    assert np.all(t[1, [6, 7, 14, 15, 22, 23]] == 0) and t[1, 3:6].tolist() == [0, 0, 1]   # a//c: no uv, own normal
+    assert t[2, 22:24].tolist() == [1, 1]                                     # vt -1 = the last vt
+    flat = tri_array(b200rt, w1.scene())
+    assert np.array_equal(t[2, 3:6], flat[0, 3:6])                            # no vn on a corner: triangle()'s flat normal
+    # the reference's transform applies to every model alike
+    w3 = b200rt.World()
+    o3 = w3.push_object(b200rt.color_material())
+    assert o3.load_obj_ex(str(path), model_index=1) == 3
+    f32 = np.float32
+    assert tri_array(b200rt, w3.scene())[0, 16:19].tolist() == [float(f32(0.7)), float(f32(1.0)), float(f32(3) / f32(3) + f32(-0.5))]
+    with pytest.raises(b200rt.B200rtError):
+        o3.load_obj_ex(str(path), model_index=2)
+    assert lib.b200rt_world_load_obj_ex(w3._h, 0, str(path).encode(), 1.0, (C.c_float * 3)(0, 0, 0), 0, 4) == b200rt.ERR_INVALID
+    bad = tmp_path / "badvt.obj"
+    bad.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1/1 2/1 3/1\n")            # vt index without any vt
+    with pytest.raises(b200rt.B200rtError):
+        o3.load_obj_ex(str(bad))
+
+
 def test_obj_errors(b200rt, tmp_path):
     w = b200rt.World()
     o = w.push_object(b200rt.color_material())
