@@ -26,7 +26,7 @@ MATERIAL_COLOR, MATERIAL_GENERATIVE = 0, 1
 DIFFUSE_CONST, DIFFUSE_STRIPE_V, DIFFUSE_CHECKER_UPV = 0, 1, 2
 NORMAL_CONST, NORMAL_SINCOS_U = 0, 1
 LIGHT_DIRECTIONAL, LIGHT_SPOT, LIGHT_POINT = 0, 1, 2
-CAST_TWO_PHASE, CAST_BRUTE_EXACT = 0, 1
+CAST_TWO_PHASE, CAST_BRUTE_EXACT, CAST_BVH = 0, 1, 2
 TRACER_WAVEFRONT, TRACER_MEGAKERNEL = 0, 1
 OBJ_USE_TEXCOORDS, OBJ_USE_NORMALS = 1, 2
 MAX_DEPTH = 16
@@ -117,7 +117,7 @@ HIT_DTYPE = np.dtype([("prim_id", "<i4"), ("object_index", "<u4"), ("face_direct
 assert RAY_DTYPE.itemsize == C.sizeof(Ray) and HIT_DTYPE.itemsize == C.sizeof(Hit)
 
 # include/b200rt_dev.h: development micro-benchmarks (not part of the product ABI)
-DEV_SYMBOLS = ["b200rt_filter_bench", "b200rt_pipe_bench"]
+DEV_SYMBOLS = ["b200rt_filter_bench", "b200rt_pipe_bench", "b200rt_dev_build_bvh"]
 
 # every symbol include/b200rt.h declares
 EXPORTED_SYMBOLS = [
@@ -181,6 +181,8 @@ def load_library() -> C.CDLL:
         "b200rt_measure_fp32_peak": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "b200rt_filter_bench": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
         "b200rt_pipe_bench": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
+        "b200rt_dev_build_bvh": (C.c_int, [C.POINTER(Scene), C.c_int, f32p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                           C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "b200rt_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
         "b200rt_group_unique_id": (C.c_int, [vp, C.c_size_t]),
         "b200rt_group_create_rank": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(vp)]),

@@ -17,6 +17,7 @@
 #include "b200rt_dev.h"
 #include "hvec.h"
 #include "rt_types.h"
+#include "rt_bvh_build.h"
 #include "rt_wavefront.h"
 
 using namespace b200rt;
@@ -43,6 +44,8 @@ struct b200rt_ctx {
     float scene_radius = 0.0f;   // max |vertex|, max |centre| + r
     float max_edge = 0.0f;
     void* d_filter = nullptr;  size_t d_filter_bytes = 0;
+    void* d_bvh = nullptr;     size_t d_bvh_bytes = 0;      // B200RT_CAST_BVH: nodes, then the triangle permutation
+    uint32_t bvh_depth = 0, bvh_leaves = 0;
     RlTileParam h_tile0{};     // tile 0 of the rays-in-lanes filter records, passed to the cast kernels by value
 
     // device scratch for the host-buffer entry points
@@ -202,6 +205,52 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
     ctx->scene.filter_As_runs = up(A + 2.0 * a_runs) * kRlPlaneScale;
     ctx->scene.h_tile0 = &ctx->h_tile0;
     ctx->scene.filter_g = 3.814697265625e-6f;   // 2^-18
+    ctx->scene.filter_B = up(B);
+    return B200RT_OK;
+}
+
+// the exact record of a triangle {n, d} {v0, obj} {v1} {v2}: Triangle::face_normal (primitives.rs:37-42) and d = n . v0
+// (main.rs:203) in the reference's arithmetic, once per triangle instead of once per pair
+void exact_record(const b200rt_triangle& t, float4* out) {
+    const V3 v0 = v3(t.vertices[0].position), v1 = v3(t.vertices[1].position), v2 = v3(t.vertices[2].position);
+    const V3 a = v1 - v0, b = v2 - v1;
+    const V3 n = normalize(cross(a, b));
+    const float d = dot(n, v0);
+    float obj_bits;
+    std::memcpy(&obj_bits, &t.object_index, 4);
+    out[0] = make_float4(n.x, n.y, n.z, d);
+    out[1] = make_float4(v0.x, v0.y, v0.z, obj_bits);
+    out[2] = make_float4(v1.x, v1.y, v1.z, 0.0f);
+    out[3] = make_float4(v2.x, v2.y, v2.z, 0.0f);
+}
+
+// B200RT_CAST_BVH: the hierarchy over the scene's triangles (host build, rt_bvh_build.h), uploaded behind the scene
+int build_and_upload_bvh(b200rt_ctx* ctx) {
+    DScene& sc = ctx->scene;
+    sc.bvh_nodes = sc.nbvh_nodes = nullptr; sc.bvh_tris = sc.nbvh_tris = nullptr; sc.bvh_n_nodes = sc.nbvh_n_nodes = 0u;
+    ctx->bvh_depth = ctx->bvh_leaves = 0u;
+    if (sc.n_tris == 0u) return B200RT_OK;
+    BvhBuild bvh;
+    build_bvh(ctx->h_tri_exact.data(), sc.n_tris, bvh);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b0 = bvh.nodes.size() * sizeof(float4), b1 = bvh.nnodes.size() * sizeof(float4);
+    const size_t b2 = bvh.tri_index.size() * sizeof(uint32_t), b3 = bvh.ntri_index.size() * sizeof(uint32_t);
+    const size_t o1 = al(b0), o2 = o1 + al(b1), o3 = o2 + al(b2);
+    int rc = ensure(ctx, &ctx->d_bvh, &ctx->d_bvh_bytes, o3 + al(b3) + 256);
+    if (rc != B200RT_OK) return rc;
+    char* base = (char*)ctx->d_bvh;
+    if (b0) CU(cudaMemcpyAsync(base, bvh.nodes.data(), b0, cudaMemcpyHostToDevice, ctx->stream));
+    if (b1) CU(cudaMemcpyAsync(base + o1, bvh.nnodes.data(), b1, cudaMemcpyHostToDevice, ctx->stream));
+    if (b2) CU(cudaMemcpyAsync(base + o2, bvh.tri_index.data(), b2, cudaMemcpyHostToDevice, ctx->stream));
+    if (b3) CU(cudaMemcpyAsync(base + o3, bvh.ntri_index.data(), b3, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    sc.bvh_nodes = reinterpret_cast<const float4*>(base);
+    sc.nbvh_nodes = reinterpret_cast<const float4*>(base + o1);
+    sc.bvh_tris = reinterpret_cast<const uint32_t*>(base + o2);
+    sc.nbvh_tris = reinterpret_cast<const uint32_t*>(base + o3);
+    sc.bvh_n_nodes = (uint32_t)(bvh.nodes.size() / 3);
+    sc.nbvh_n_nodes = (uint32_t)(bvh.nnodes.size() / 2);
+    ctx->bvh_depth = std::max(bvh.max_depth, bvh.nmax_depth); ctx->bvh_leaves = bvh.n_leaves;
     return B200RT_OK;
 }
 
@@ -232,7 +281,7 @@ int make_params(const b200rt_params& p, uint32_t epoch_begin, uint32_t epoch_cou
     if (p.width == 0 || p.height == 0) return B200RT_ERR_INVALID;
     if (p.depth < 0 || p.depth > B200RT_MAX_DEPTH) return B200RT_ERR_UNSUPPORTED;
     if (p.row_count && (p.row_begin >= p.height || p.row_count > p.height - p.row_begin)) return B200RT_ERR_INVALID;   // (no u32 wrap)
-    if (p.cast_mode > B200RT_CAST_BRUTE_EXACT) return B200RT_ERR_INVALID;
+    if (p.cast_mode > B200RT_CAST_BVH) return B200RT_ERR_INVALID;
     if (p.tracer > B200RT_TRACER_MEGAKERNEL) return B200RT_ERR_INVALID;
     o.width = p.width; o.height = p.height;
     o.row_begin = p.row_count ? p.row_begin : 0u;
@@ -328,6 +377,7 @@ int b200rt_destroy(b200rt_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d_scene_blob) cudaFree(ctx->d_scene_blob);
     if (ctx->d_filter) cudaFree(ctx->d_filter);
+    if (ctx->d_bvh) cudaFree(ctx->d_bvh);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_aux) cudaFree(ctx->d_aux);
     if (ctx->d_cnt) cudaFree(ctx->d_cnt);
@@ -387,17 +437,7 @@ int b200rt_upload_scene(b200rt_ctx* ctx, const b200rt_scene* s) {
     std::vector<DLight> lights(std::max(nl, 1u));
     for (uint32_t i = 0; i < nt; ++i) {
         const b200rt_triangle& t = s->triangles[i];
-        const V3 v0 = v3(t.vertices[0].position), v1 = v3(t.vertices[1].position), v2 = v3(t.vertices[2].position);
-        // Triangle::face_normal, primitives.rs:37-42, and d = n . v0, main.rs:203
-        const V3 a = v1 - v0, b = v2 - v1;
-        const V3 n = normalize(cross(a, b));
-        const float d = dot(n, v0);
-        float obj_bits;
-        std::memcpy(&obj_bits, &t.object_index, 4);
-        tri_exact[4 * (size_t)i + 0] = make_float4(n.x, n.y, n.z, d);
-        tri_exact[4 * (size_t)i + 1] = make_float4(v0.x, v0.y, v0.z, obj_bits);
-        tri_exact[4 * (size_t)i + 2] = make_float4(v1.x, v1.y, v1.z, 0.0f);
-        tri_exact[4 * (size_t)i + 3] = make_float4(v2.x, v2.y, v2.z, 0.0f);
+        exact_record(t, &tri_exact[4 * (size_t)i]);
         const b200rt_vertex* v = t.vertices;
         tri_attr[4 * (size_t)i + 0] = make_float4(v[0].normal[0], v[0].normal[1], v[0].normal[2], v[0].uv[0]);
         tri_attr[4 * (size_t)i + 1] = make_float4(v[1].normal[0], v[1].normal[1], v[1].normal[2], v[0].uv[1]);
@@ -518,6 +558,8 @@ int b200rt_upload_scene(b200rt_ctx* ctx, const b200rt_scene* s) {
     ctx->h_sph = sph;
     // every secondary ray starts on a primitive, i.e. within scene_radius (+ rounding); cameras further out re-pack
     rc = pack_filter(ctx, (float)(4.0 * rad + 8.0));
+    if (rc != B200RT_OK) return rc;
+    rc = build_and_upload_bvh(ctx);
     if (rc != B200RT_OK) return rc;
     ctx->have_scene = true;
     return B200RT_OK;
@@ -742,7 +784,7 @@ int b200rt_intersect_device(b200rt_ctx* ctx, const b200rt_ray* d_rays, size_t n,
                             void* cuda_stream) {
     if (!ctx || (n && (!d_rays || !d_hits))) return B200RT_ERR_INVALID;
     if (!ctx->have_scene) return B200RT_ERR_NO_SCENE;
-    if (cast_mode > B200RT_CAST_BRUTE_EXACT) return B200RT_ERR_INVALID;
+    if (cast_mode > B200RT_CAST_BVH) return B200RT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the CUDA default stream
     CU(cudaEventRecord(ctx->ev0, st));
@@ -799,6 +841,30 @@ int b200rt_reset_stats(b200rt_ctx* ctx) {
     CU(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(DCounters), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     std::memset(&ctx->stats, 0, sizeof ctx->stats);
+    return B200RT_OK;
+}
+
+// dev / test entry (b200rt_dev.h): the acceleration structure of a scene, built on the host exactly as
+// b200rt_upload_scene builds it (no GPU needed)
+int b200rt_dev_build_bvh(const b200rt_scene* s, int which, float* nodes_out, uint32_t max_nodes, uint32_t* tri_index_out,
+                         uint32_t* n_nodes, uint32_t* n_indexed, uint32_t* depth, uint32_t* n_leaves) {
+    if (!s || !n_nodes || (s->n_triangles && !s->triangles) || which < 0 || which > 1) return B200RT_ERR_INVALID;
+    std::vector<float4> ex(4 * (size_t)std::max(s->n_triangles, 1u));
+    for (uint32_t i = 0; i < s->n_triangles; ++i) exact_record(s->triangles[i], &ex[4 * (size_t)i]);
+    BvhBuild bvh;
+    build_bvh(ex.data(), s->n_triangles, bvh);
+    const std::vector<float4>& nodes = which == 0 ? bvh.nodes : bvh.nnodes;
+    const std::vector<uint32_t>& index = which == 0 ? bvh.tri_index : bvh.ntri_index;
+    const size_t per = which == 0 ? 3 : 2;
+    *n_nodes = (uint32_t)(nodes.size() / per);
+    if (n_indexed) *n_indexed = (uint32_t)index.size();
+    if (depth) *depth = which == 0 ? bvh.max_depth : bvh.nmax_depth;
+    if (n_leaves) *n_leaves = which == 0 ? bvh.n_leaves : bvh.nn_leaves;
+    if (nodes_out) {
+        if (max_nodes < *n_nodes) return B200RT_ERR_INVALID;
+        if (!nodes.empty()) std::memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(float4));
+    }
+    if (tri_index_out && !index.empty()) std::memcpy(tri_index_out, index.data(), index.size() * sizeof(uint32_t));
     return B200RT_OK;
 }
 

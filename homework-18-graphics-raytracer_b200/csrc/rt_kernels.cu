@@ -17,6 +17,7 @@
 
 #include "rt_cast.cuh"
 #include "rt_cast_rl.cuh"
+#include "rt_bvh.cuh"
 #include "rt_shade.cuh"
 #include "rt_types.h"
 
@@ -63,6 +64,8 @@ RT_DI void cast_warp(const DScene& sc, float4* s_rays, const TriPair& tile0, uin
     if (CAST == B200RT_CAST_BRUTE_EXACT) {
         h.prim = -1;
         if (active) { cast_brute_exact(sc, r, h); cs.casts += 1ull; }
+    } else if (CAST == B200RT_CAST_BVH) {
+        bvh_warp_cast(sc, lane, active, r, h, cs);
     } else {
         warp_cast(sc, s_rays, tile0, lane, active, r, h, cs);
     }
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(TraceCfg<MODE>::kThreads, TraceCfg<MODE>::kMin
     __shared__ float4 s_rays_all[kTraceWarps][kCastSlotFloat4];     // per-warp ray staging slot of the transposed filter
     float4* s_rays = s_rays_all[warp];
     TriPair tile0;                                     // this lane's two triangles of tile 0: register resident
-    if (CAST != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
+    if (CAST == B200RT_CAST_TWO_PHASE && sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
     else zero_tripair(tile0);
 
     const f3 cam_toward = mk3(cam.toward), cam_x = mk3(cam.x), cam_y = mk3(cam.y);
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(128, 4) intersect_kernel(const DScene sc, cons
     __shared__ float4 s_rays_all[4][kCastSlotFloat4];
     float4* s_rays = s_rays_all[warp];
     TriPair tile0;
-    if (CAST != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
+    if (CAST == B200RT_CAST_TWO_PHASE && sc.n_tris_padded) load_tripair(sc.tri_filter, 0, lane, tile0);
     else zero_tripair(tile0);
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
@@ -761,6 +764,8 @@ cudaError_t launch_whitted(const DScene& sc, const DCamera& cam, const DParams& 
                            DCounters* d_cnt, cudaStream_t stream) {
     if (p.cast_mode == B200RT_CAST_BRUTE_EXACT)
         trace_kernel<kModeWhitted, B200RT_CAST_BRUTE_EXACT><<<grid_tiles<kModeWhitted>(p), TraceCfg<kModeWhitted>::kThreads, 0, stream>>>(sc, cam, p, d_rgb, d_prim, d_cnt);
+    else if (p.cast_mode == B200RT_CAST_BVH)
+        trace_kernel<kModeWhitted, B200RT_CAST_BVH><<<grid_tiles<kModeWhitted>(p), TraceCfg<kModeWhitted>::kThreads, 0, stream>>>(sc, cam, p, d_rgb, d_prim, d_cnt);
     else
         trace_kernel<kModeWhitted, B200RT_CAST_TWO_PHASE><<<grid_tiles<kModeWhitted>(p), TraceCfg<kModeWhitted>::kThreads, 0, stream>>>(sc, cam, p, d_rgb, d_prim, d_cnt);
     return cudaGetLastError();
@@ -770,6 +775,8 @@ cudaError_t launch_distributed(const DScene& sc, const DCamera& cam, const DPara
                                DCounters* d_cnt, cudaStream_t stream) {
     if (p.cast_mode == B200RT_CAST_BRUTE_EXACT)
         trace_kernel<kModeDistributed, B200RT_CAST_BRUTE_EXACT><<<grid_tiles<kModeDistributed>(p), TraceCfg<kModeDistributed>::kThreads, 0, stream>>>(sc, cam, p, d_accum, nullptr, d_cnt);
+    else if (p.cast_mode == B200RT_CAST_BVH)
+        trace_kernel<kModeDistributed, B200RT_CAST_BVH><<<grid_tiles<kModeDistributed>(p), TraceCfg<kModeDistributed>::kThreads, 0, stream>>>(sc, cam, p, d_accum, nullptr, d_cnt);
     else
         trace_kernel<kModeDistributed, B200RT_CAST_TWO_PHASE><<<grid_tiles<kModeDistributed>(p), TraceCfg<kModeDistributed>::kThreads, 0, stream>>>(sc, cam, p, d_accum, nullptr, d_cnt);
     return cudaGetLastError();
@@ -781,6 +788,10 @@ cudaError_t launch_intersect(const DScene& sc, const b200rt_ray* d_rays, size_t 
     const unsigned blocks = (unsigned)((n + 127) / 128);
     // one-tile scenes: rays in lanes (B200RT_INTERSECT=transposed keeps the warp-transposed kernel: measurement)
     const char* sel = getenv("B200RT_INTERSECT");
+    if (cast_mode == B200RT_CAST_BVH) {
+        intersect_kernel<B200RT_CAST_BVH><<<blocks, 128, 0, stream>>>(sc, d_rays, n, d_hits, d_cnt);
+        return cudaGetLastError();
+    }
     if (cast_mode != B200RT_CAST_BRUTE_EXACT && sc.n_tris_padded >= (uint32_t)kTileTris && sc.tri_filter_plain &&
         n < 0xffffffffull && !(sel && sel[0] == 't')) {
         int dev = 0, sms = 0;

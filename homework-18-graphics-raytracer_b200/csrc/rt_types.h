@@ -85,6 +85,14 @@ struct DScene {
     float filter_As_runs;    // ... for the loop over RlTileParam, whose coplanar runs share the plane of their first triangle
     const struct RlTileParam* h_tile0;   // HOST pointer (launchers only): tile 0 of the scene as a kernel parameter
     float filter_g;          // |n.dir| below this always passes the filter (2^-18)
+    float filter_B;          // the absolute slack folded into the filter's edge offsets (128u * 2S)
+    // B200RT_CAST_BVH (rt_bvh_build.h / rt_bvh.cuh): the spatial tree (3 float4 per node) and the tree over the normals
+    // (2 float4 per node), root = node 0, leaves index bvh_tris / nbvh_tris
+    const float4* bvh_nodes;
+    const uint32_t* bvh_tris;
+    const float4* nbvh_nodes;
+    const uint32_t* nbvh_tris;
+    uint32_t bvh_n_nodes, nbvh_n_nodes;
 };
 
 // Camera::shoot hoisted per frame (main.rs:85-92): computed on the host with the same libm tanf

@@ -33,6 +33,7 @@
 
 #include "rt_cast.cuh"
 #include "rt_cast_rl.cuh"
+#include "rt_bvh.cuh"
 #include "rt_shade.cuh"
 #include "rt_types.h"
 #include "rt_wavefront.h"
@@ -534,6 +535,49 @@ __global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_TILED_MIN_BLOCKS) wf_ca
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
     const WfPrimaryIO io{wb, cam, p};
     cast_rays_in_lanes_tiled(sc, io, wb.n, sh, cs);
+    wf_cast_tail(sc, cs, wb.n, cnt);
+}
+
+// ---- cast through the acceleration structure (B200RT_CAST_BVH, rt_bvh.cuh): one ray per lane -----------------------------------
+namespace {
+template <class IO>
+RT_DI void wf_cast_rays_bvh(const DScene& sc, IO io, const uint32_t n_work, CastStats& cs) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_chunks = (n_work + 31u) >> 5;
+    for (uint32_t chunk = warp0; chunk < n_chunks; chunk += n_warps) {
+        const uint32_t idx = chunk * 32u + lane;
+        io.begin_block(idx & ~127u);                       // (the lists are padded to 128-index blocks: warp-uniform)
+        const uint32_t tag = idx < n_work ? io.item(idx) : kRlNoRay;
+        DRay r;
+        r.o = mk3(0.f, 0.f, 0.f); r.d = mk3(0.f, 0.f, 1.f); r.face = kFront; r.ex_prim = -1; r.ex_face = kFront;
+        if (tag != kRlNoRay) io.fetch(tag, r);
+        DHit h;
+        h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
+        bvh_warp_cast(sc, lane, tag != kRlNoRay, r, h, cs, tag != kRlNoRay && io.want_attrs(tag), io.all_sphere_uv());
+        if (tag != kRlNoRay) io.store(tag, h);
+    }
+}
+}  // namespace
+__global__ void __launch_bounds__(128, 4) wf_cast_bvh_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf, DCounters* __restrict__ cnt) {
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
+    const WfWork wk = wf_work(wb, buf);
+    const uint32_t n_work = wk.n_real();
+    if (n_work == 0u) return;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    WfRayIO io;
+    io.wb = wb; io.work = wk;
+    wf_cast_rays_bvh(sc, io, wk.n_virtual(), cs);
+    wf_cast_tail(sc, cs, n_work, cnt);
+}
+__global__ void __launch_bounds__(128, 4) wf_cast_bvh_primary_kernel(const DScene sc, const DCamera cam, const DParams p, const WfBuffers wb,
+                                                                     const uint32_t buf, DCounters* __restrict__ cnt) {
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    const WfPrimaryIO io{wb, cam, p};
+    wf_cast_rays_bvh(sc, io, wb.n, cs);
     wf_cast_tail(sc, cs, wb.n, cnt);
 }
 
@@ -1148,8 +1192,9 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     // B200RT_WF_CAST = rl (default: rays in lanes, tiles by TMA for larger scenes) | fused (warp-transposed): measurement
     const char* cast_env = getenv("B200RT_WF_CAST");
     const std::string cast_sel = cast_env ? cast_env : "";
-    const bool rays_in_lanes = n_tiles == 1 && (cast_sel.empty() || cast_sel == "rl");
-    const bool rays_in_lanes_tiled = n_tiles > 1 && (cast_sel.empty() || cast_sel == "rl");
+    const bool bvh = p.cast_mode == B200RT_CAST_BVH && sc.bvh_n_nodes != 0u;      // the acceleration structure (rt_bvh.cuh)
+    const bool rays_in_lanes = bvh || (n_tiles == 1 && (cast_sel.empty() || cast_sel == "rl"));   // (bvh: the same round-0 flow)
+    const bool rays_in_lanes_tiled = !bvh && n_tiles > 1 && (cast_sel.empty() || cast_sel == "rl");
     // fused levels (one light chunk): a hit's shadow rays and the next level's ray are cast in the same round, and one
     // kernel pass per level consumes both (B200RT_WF_FUSED_LEVELS=0: one pass per cast, as for scenes of > 4 lights)
     const char* fused_env = getenv("B200RT_WF_FUSED_LEVELS");
@@ -1181,7 +1226,10 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                 ev_b = timing->pool[2 * (round - first_round_of_group) + 1];
                 cudaEventRecord(ev_a, stream);
             }
-            if (round == 0u && fused_primary) {
+            if (bvh) {
+                if (round == 0u && fused_primary) wf_cast_bvh_primary_kernel<<<sm_count * 8, 128, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+                else wf_cast_bvh_kernel<<<sm_count * 8, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+            } else if (round == 0u && fused_primary) {
                 if (rays_in_lanes) wf_cast_rl_primary_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, cam, p, wb, buf, d_cnt);
                 else wf_cast_rl_tiled_primary_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
             } else if (rays_in_lanes) {

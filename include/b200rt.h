@@ -152,7 +152,11 @@ typedef struct b200rt_hit {
 #define B200RT_MAX_DEPTH 16
 enum {
     B200RT_CAST_TWO_PHASE = 0,   /* FMA filter over packed plane records + exact confirm (default) */
-    B200RT_CAST_BRUTE_EXACT = 1  /* every pair through the exact reference-order test              */
+    B200RT_CAST_BRUTE_EXACT = 1, /* every pair through the exact reference-order test              */
+    /* the same hits (bit for bit: id, face, distance, position, normal, uv) through a bounding-volume
+     * hierarchy over the triangles, built at b200rt_upload_scene.  Not the brute-force walk of main.rs:183 any more, so
+     * not the workload the FP32-roofline figure is quoted on: a mode for scenes of 1e4+ triangles (rt_bvh.cuh). */
+    B200RT_CAST_BVH = 2
 };
 /* How b200rt_render_distributed* schedules the stochastic tracer on the GPU (same samples, same bits):
  * WAVEFRONT keeps every path's state in HBM and alternates one cast kernel with one shading kernel per

@@ -20,6 +20,15 @@ int b200rt_filter_bench(b200rt_ctx* ctx, int variant, int blocks_per_sm, int ite
 /* Pipe calibration loops (dev tool): returns warp-instructions per clock per SM sub-partition at sm_mhz. */
 int b200rt_pipe_bench(b200rt_ctx* ctx, int variant, float* kernel_ms, double* inst_per_clk_per_smsp);
 
+/* The acceleration structure of B200RT_CAST_BVH as b200rt_upload_scene builds it, on the host (no GPU;
+ * csrc/rt_bvh_build.h).  which = 0: the spatial tree, 12 floats per node {bmin.xyz, rho_geom}{bmax.xyz, -}{u32 left |
+ * first, u32 right | 0x80000000 + count, u32 axis, -}; which = 1: the tree over the triangles' unit normals, 8 floats per
+ * node {nmin.xyz, u32 left | first}{nmax.xyz, u32 right | 0x80000000 + count}.  tri_index_out receives the n_indexed
+ * triangle ids the leaves index (every triangle for the normal tree, the well-shaped ones for the spatial tree).
+ * nodes_out / tri_index_out may be NULL. */
+int b200rt_dev_build_bvh(const b200rt_scene* scene, int which, float* nodes_out, uint32_t max_nodes, uint32_t* tri_index_out,
+                         uint32_t* n_nodes, uint32_t* n_indexed, uint32_t* depth, uint32_t* n_leaves);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,7 @@ pub const B200RT_LIGHT_SPOT: u32 = 1;
 pub const B200RT_LIGHT_POINT: u32 = 2;
 pub const B200RT_CAST_TWO_PHASE: u32 = 0;
 pub const B200RT_CAST_BRUTE_EXACT: u32 = 1;
+pub const B200RT_CAST_BVH: u32 = 2;
 pub const B200RT_TRACER_WAVEFRONT: u32 = 0;
 pub const B200RT_TRACER_MEGAKERNEL: u32 = 1;
 pub const B200RT_OBJ_USE_TEXCOORDS: u32 = 1;
