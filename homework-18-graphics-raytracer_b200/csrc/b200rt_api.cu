@@ -206,6 +206,7 @@ int pack_filter(b200rt_ctx* ctx, float origin_bound) {
     ctx->scene.h_tile0 = &ctx->h_tile0;
     ctx->scene.filter_g = 3.814697265625e-6f;   // 2^-18
     ctx->scene.filter_B = up(B);
+    ctx->scene.scene_extent = up((double)ctx->scene_radius + (double)ctx->max_edge);
     return B200RT_OK;
 }
 

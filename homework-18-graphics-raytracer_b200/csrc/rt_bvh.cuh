@@ -5,7 +5,7 @@
 // One ray per lane, two passes (the argument is in rt_bvh_build.h):
 //   1. the NORMAL tree: every triangle whose normal may satisfy |n.dir| < g - where main.rs:204 can overflow or divide
 //      0 by 0 and the reference registers hits at t = +inf / NaN wherever the triangle lies - goes through the exact test;
-//   2. the SPATIAL tree: a node is skipped when the ray's line misses its box inflated by rho = rho_geom + 8 B, or meets
+//   2. the SPATIAL tree: a node is skipped when the ray's line misses its box inflated by rho_geom + the ray's rounding slack, or meets
 //      it only at parameters below zero (main.rs:205) or beyond the nearest hit so far (main.rs:229-233); the triangles
 //      of the leaves reached go through the exact test.
 // The exact test is the reference's own (tri_exact_eval = main.rs:184-227 verbatim).  The nearest rule of the walk, "skip
@@ -77,7 +77,13 @@ RT_DI void bvh_cast_triangles(const DScene& sc, const DRay& ray, Best& best, boo
                 }
                 const uint32_t count = w2 & ~kBvhLeafBit;
 #pragma unroll 1
-                for (uint32_t k = 0; k < count; ++k) bvh_try_triangle(sc, sc.nbvh_tris[w1 + k], ray, best, nan_seen, tested);
+                for (uint32_t k = 0; k < count; ++k) {
+                    // of the leaf's triangles only those that ARE nearly parallel (the reference's own n.dir), and those the
+                    // spatial tree does not hold (flagged), are this pass's business; NaN normals compare false and stay
+                    const uint32_t e = sc.nbvh_tris[w1 + k], i = e & ~kBvhLeafBit;
+                    if (!(e & kBvhLeafBit) && fabsf(dot(mk3(sc.tri_exact[4 * (size_t)i]), ray.d)) >= kBvhBand) continue;
+                    bvh_try_triangle(sc, i, ray, best, nan_seen, tested);
+                }
             }
             if (sp == 0) break;
             node = stack[--sp];
@@ -86,7 +92,9 @@ RT_DI void bvh_cast_triangles(const DScene& sc, const DRay& ray, Best& best, boo
     // ---- pass 2: triangles near the ray's line --------------------------------------------------------------------
     if (sc.bvh_n_nodes == 0u) return;
     const float ix = 1.0f / ray.d.x, iy = 1.0f / ray.d.y, iz = 1.0f / ray.d.z;
-    const float slack = 8.0f * sc.filter_B;
+    // what separates the reference's plane point from the line and from the plane (rt_bvh_build.h), for THIS ray: with
+    // |o|, |t| <= 2 |o| + V and u = 2^-24 it is below u (10 V + 25 |o|); four times that, plus the slab arithmetic's own rounding
+    const float slack = 5.9604645e-8f * (40.0f * sc.scene_extent + 100.0f * ((fabsf(ray.o.x) + fabsf(ray.o.y)) + fabsf(ray.o.z)));
     int sp = 0;
     uint32_t node = 0u;
     for (;;) {

@@ -8,11 +8,13 @@
 //   * |n.dir| >= g = 2^-18: t is finite, and the test accepts only if the plane point p = o + t dir it forms - a point of
 //     the ray's line, to rounding - projects into the triangle or within 32 u kappa E' of it (u = 2^-24, E' = the
 //     triangle's diameter): an edge function (e x (p - v)).n carries a rounding error of at most 8 u |e| |p - v|, and
-//     outside the triangle at distance D one of the three is below -|e| D / kappa.  p is also within ~1e-5 S of the plane
-//     (the error of t scales with 1 / |n.dir|, but it moves p ALONG the line).  So the LINE passes within
-//         rho = 1e-4 kappa E' + 8 B
-//     of the triangle (B = the absolute slack of the two-phase filter, 128 u 2 (O + V + E): here only a generous unit), at
-//     a parameter t that lies in the line's parameter range inside the triangle's bounding box inflated by rho.
+//     outside the triangle at distance D one of the three is below -|e| D / kappa.  p is also within u (10 V + 25 |o|) of
+//     the plane and of the line (the error of t scales with 1 / |n.dir|, but it moves p ALONG the line: off the plane it
+//     is |d_plane| u + 4 u |n.o| from the numerator and 5.2 u |t| from the rounding of n.dir, |t| <= 2 |o| + V for a point
+//     near the triangle; p = o + t dir adds 3.5 u (|o| + |t|)).  So the LINE passes within
+//         rho = 1e-4 kappa E' + 4 u (10 (V + E) + 25 |o|)
+//     of the triangle, at a parameter t that lies in the line's parameter range inside the triangle's bounding box
+//     inflated by rho (50x and 4x the bounds).
 //   * |n.dir| < g: the division of main.rs:204 may overflow or be 0/0 - the reference then registers hits at t = +inf or
 //     NaN whatever the triangle's position (main.rs:205, 224, 229-231 reject nothing on inf / NaN).  Such pairs must
 //     reach the exact test wherever the triangle lies.
@@ -29,6 +31,7 @@
 // Both are binary trees built by binned SAH (16 bins on the longest centroid axis) with leaves of <= 4 triangles:
 //   spatial node (48 B)  {bmin.xyz, rho_geom} {bmax.xyz, -} {u32 left | first, u32 right | 0x80000000 + count, u32 axis, -}
 //   normal node  (32 B)  {nmin.xyz, u32 left | first} {nmax.xyz, u32 right | 0x80000000 + count}
+// (the normal tree's index entries carry 0x80000000 for the triangles that are not in the spatial tree)
 // The left child holds the smaller centroids along `axis`.  Triangle order inside the trees is free: the traversal applies
 // the reference's nearest / tie rule (main.rs:229-233) in its order-independent form.
 #pragma once
@@ -213,6 +216,12 @@ inline void build_bvh(const float4* tri_exact, uint32_t n_tris, BvhBuild& out) {
     out.ntri_index.resize(n_tris);
     for (uint32_t i = 0; i < n_tris; ++i) out.ntri_index[i] = i;
     build_tree(np, out.ntri_index, tn, out.nmax_depth, out.nn_leaves);
+    // (a triangle that is not well shaped is not in the spatial tree: its entry carries a flag, and every ray tests it)
+    {
+        std::vector<uint8_t> in_spatial(n_tris, 0);
+        for (uint32_t i : sp_ids) in_spatial[i] = 1;
+        for (uint32_t& e : out.ntri_index) if (!in_spatial[e]) e |= kBvhLeafFlag;
+    }
     out.nnodes.resize(2 * tn.size());
     for (size_t k = 0; k < tn.size(); ++k) {
         const TreeNode& t = tn[k];

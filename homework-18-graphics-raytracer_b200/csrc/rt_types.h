@@ -86,6 +86,7 @@ struct DScene {
     const struct RlTileParam* h_tile0;   // HOST pointer (launchers only): tile 0 of the scene as a kernel parameter
     float filter_g;          // |n.dir| below this always passes the filter (2^-18)
     float filter_B;          // the absolute slack folded into the filter's edge offsets (128u * 2S)
+    float scene_extent;      // V + E: largest vertex norm + longest edge
     // B200RT_CAST_BVH (rt_bvh_build.h / rt_bvh.cuh): the spatial tree (3 float4 per node) and the tree over the normals
     // (2 float4 per node), root = node 0, leaves index bvh_tris / nbvh_tris
     const float4* bvh_nodes;

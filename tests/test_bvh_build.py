@@ -106,7 +106,10 @@ def check_trees(b200rt, world):
     assert sorted(st["tris"]) == np.where(regular)[0].tolist() and st["leaves"] == s_leaves
 
     n_nodes, n_perm, n_depth, n_leaves = build(b200rt, world, 1)
+    flagged = (n_perm & 0x80000000) != 0                                        # not in the spatial tree: tested by every ray
+    n_perm = n_perm & 0x7fffffff
     assert sorted(n_perm.tolist()) == list(range(n)) and n_depth <= 62        # every triangle, each once
+    assert sorted(n_perm[flagged].tolist()) == np.where(~regular)[0].tolist()
 
     def normal_leaf(tris, lo, hi, rho):
         for i in tris:
