@@ -423,6 +423,10 @@ RT_DI unsigned long long tile_candidates(const DScene& sc, uint32_t tile, uint2 
     return ((unsigned long long)c_hi << 32) | (unsigned long long)c_lo;
 }
 
+// (Round 2 measured this pre-filter in packed form inside the rays-in-lanes loop - the same operations on ray pairs, FFMA2 /
+// FMUL2, the spheres beside the tile in the kernel parameter: the cast of a 16-epoch 4K batch took 66.6 ms against 63.4.  A
+// packed instruction occupies the FMA pipe for two issue slots: on an issue-bound kernel it saves nothing, and the four
+// spheres leave it two dependent chains where this loop has four.  Not built.)
 // spheres (main.rs:264-324): a conservative pre-filter of main.rs:265-268 in fused arithmetic for 32 spheres at a
 // time — squared line-sphere distance |disp|^2 |dir|^2 - (disp.dir)^2 against r^2 with a 64u (r^2 + |disp|^2)
 // slack (both sides' rounding is <= 13u of that; NaNs pass) — then the exact test of the survivors in index
@@ -442,6 +446,12 @@ RT_DI void cast_spheres(const DScene& sc, const DRay& ray, bool trust, float dd,
             const float bound = __fmaf_rn(3.8146973e-6f, r2 + e2, r2);
             if (!(trust && d2 > bound)) smask |= 1u << j;
         }
+        // a sphere the ray's own exclusion always rules out (main.rs:286-296: the only face a Front / Back ray can see of it
+        // is the excluded one - every shadow ray that starts on a sphere) never changes `best`: sphere_exact_test returns
+        // at or before its exclusion test
+        const int32_t es = ray.ex_prim - (int32_t)(sc.n_tris + j0);
+        if (es >= 0 && es < 32 && ((ray.face == kFront && ray.ex_face == kFront) || (ray.face == kBack && ray.ex_face == kBack) || ray.ex_face == kBoth))
+            smask &= ~(1u << es);
 #pragma unroll 1
         while (smask) {
             const uint32_t j = (uint32_t)__ffs((int)smask) - 1u;
