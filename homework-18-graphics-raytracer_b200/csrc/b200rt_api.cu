@@ -309,12 +309,12 @@ int fetch_counters(b200rt_ctx* ctx) {
     ctx->stats.exact_confirms = h.confirms;
     ctx->stats.samples = h.samples;
     ctx->stats.certify_fallbacks = h.fallbacks;
-    ctx->stats.wavefront_rounds = ctx->last_rounds;
+    ctx->stats.wavefront_rounds = ctx->last_rounds + (uint32_t)h.rounds;       // host-enqueued rounds + the device loop's
     ctx->stats.cast_kernel_ms = (float)ctx->wf_timing.cast_ms;
     ctx->stats.logic_kernel_ms = (float)ctx->wf_timing.logic_ms;
     ctx->stats.cast_kernel_launches = (uint32_t)ctx->wf_timing.cast_launches;
     ctx->stats.primary_kernel_ms = (float)ctx->wf_timing.primary_ms;
-    ctx->stats.kernel_launches = ctx->last_launches;
+    ctx->stats.kernel_launches = ctx->last_launches + (uint32_t)h.launches;
     return B200RT_OK;
 }
 
@@ -659,6 +659,7 @@ static int render_distributed_device_impl(b200rt_ctx* ctx, const b200rt_camera* 
     CU(cudaEventRecord(ctx->ev0, st));
     ctx->last_rounds = 0;
     ctx->last_launches = 0;
+    CU(cudaMemsetAsync(&ctx->d_cnt->rounds, 0, 2 * sizeof(unsigned long long), st));   // the device loop's counters are per call
     ctx->wf_timing.cast_ms = ctx->wf_timing.logic_ms = ctx->wf_timing.primary_ms = 0.0;
     ctx->wf_timing.cast_launches = 0;
     if (epoch_count) {

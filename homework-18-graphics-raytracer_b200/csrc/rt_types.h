@@ -130,6 +130,7 @@ __host__ __device__ inline uint32_t wf_frame_row(const DParams& p, uint32_t L) {
 
 struct DCounters {  // device-side statistics, one 64-bit atomic per CTA at kernel end
     unsigned long long casts, tri_pairs, sph_pairs, confirms, samples, fallbacks;
+    unsigned long long rounds, launches;   // of the wavefront's device-side round loop, since the last render call began
 };
 
 constexpr int kTileTris = 64;  // triangles per shared-memory tile (64 x 64 B = 4 KB)

@@ -1135,6 +1135,15 @@ __global__ void wf_combine_kernel(const WfBuffers wb, const DParams p, float4* _
     accum[at] = v;
 }
 
+// the condition of the round loop's WHILE node (launch_distributed_wavefront): go on while a slot has samples left
+__global__ void wf_loop_kernel(cudaGraphConditionalHandle handle, const WfControl* __restrict__ ctl, uint32_t n_paths,
+                               DCounters* __restrict__ cnt, uint32_t launches) {
+    const bool more = ctl->retired < n_paths;
+    if (cnt) { cnt->rounds += 2ull; cnt->launches += (unsigned long long)launches; }
+    // (every path retires after <= epochs * (depth + 1) * (14 + lights) rounds; the cap only guards a corrupted counter)
+    cudaGraphSetConditional(handle, (more && (!cnt || cnt->rounds < (1ull << 22))) ? 1u : 0u);
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------
 size_t wf_workspace_bytes_per_path() {
     return (size_t)kStateRows * 16 + WF_REQ_ROWS * 16 + 32 + 32 + 2 * WF_SEG_COUNT * 4 + 2 * WF_WORK_PER_PATH * 4;
@@ -1208,7 +1217,93 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     wb.fused_primary = fused_primary ? 1u : 0u;
     if (!fused_primary)
         wf_logic_kernel<WF_SEG_INIT, false><<<logic_blocks(LogicCfg<WF_SEG_INIT>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, 1u, d_cnt);
-    uint32_t round = 0, buf = 0;
+    // one round on `stream`: the cast of the rays requested in the round before, then the passes that consume it
+    auto launch_round = [&](uint32_t round, uint32_t buf) {
+        if (bvh) {
+            if (round == 0u && fused_primary) wf_cast_bvh_primary_kernel<<<sm_count * 8, 128, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            else wf_cast_bvh_kernel<<<sm_count * 8, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+        } else if (round == 0u && fused_primary) {
+            if (rays_in_lanes) wf_cast_rl_primary_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, cam, p, wb, buf, d_cnt);
+            else wf_cast_rl_tiled_primary_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+        } else if (rays_in_lanes) {
+            wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, wb, buf, d_cnt);
+        } else if (rays_in_lanes_tiled) {
+            wf_cast_rl_tiled_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
+        } else {
+            wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+        }
+    };
+    auto launch_round_logic = [&](uint32_t round, uint32_t buf) {
+        if (round == 0u && fused_primary)
+            wf_logic_kernel<WF_SEG_PRIMARY0, false><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY0>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+        wf_logic_kernel<WF_SEG_PRIMARY, false><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+        if (fused) {
+            wf_logic_kernel<WF_SEG_SHADE, true><<<logic_blocks(LogicCfg<WF_SEG_SHADE, true>::kMinBlocks), LogicCfg<WF_SEG_SHADE, true>::kThreads, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            wf_logic_kernel<WF_SEG_BOUNCE, true><<<logic_blocks(LogicCfg<WF_SEG_BOUNCE, true>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+        } else {
+            wf_logic_kernel<WF_SEG_SHADE, false><<<logic_blocks(LogicCfg<WF_SEG_SHADE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            wf_logic_kernel<WF_SEG_BOUNCE, false><<<logic_blocks(LogicCfg<WF_SEG_BOUNCE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+        }
+        wf_logic_kernel<WF_SEG_REFR, false><<<logic_blocks(LogicCfg<WF_SEG_REFR>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+        if (p.depth <= 0)   // get_shade of depth-0 primary hits (the only source of this segment)
+            wf_logic_kernel<WF_SEG_SHB, false><<<logic_blocks(LogicCfg<WF_SEG_SHB>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+    };
+    const uint32_t launches_per_round = p.depth <= 0 ? 6u : 5u;
+
+    // The round loop ON THE DEVICE: a CUDA graph whose WHILE node repeats {round on buffer 1, round on buffer 0, "any
+    // path left?"} until every slot has retired (wf_loop_kernel sets the node's condition from the retired counter).  The
+    // host enqueues round 0, the graph and the combine pass and returns: no polling, the *_device entry points are
+    // asynchronous.  Not on the legacy default stream (it cannot be captured), not when the per-kernel timing of the
+    // roofline pass is on, and B200RT_WF_GRAPH=0 keeps the host loop (measurement).
+    const char* graph_env = getenv("B200RT_WF_GRAPH");
+    const bool use_graph = timing == nullptr && stream != nullptr && stream != cudaStreamLegacy && !(graph_env && graph_env[0] == '0');
+    bool round0_done = false;
+    if (use_graph) {
+        launch_round(0u, 0u);
+        launch_round_logic(0u, 0u);
+        round0_done = true;
+        cudaGraph_t graph = nullptr, body = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphConditionalHandle handle;
+        cudaGraphNode_t node;
+        cudaGraphNodeParams np = {};
+        bool captured = false;
+        e = cudaGraphCreate(&graph, 0);
+        if (e == cudaSuccess) e = cudaGraphConditionalHandleCreate(&handle, graph, 1u, cudaGraphCondAssignDefault);
+        if (e == cudaSuccess) {
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = handle;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            e = cudaGraphAddNode(&node, graph, nullptr, 0, &np);
+        }
+        if (e == cudaSuccess) {
+            body = np.conditional.phGraph_out[0];
+            e = cudaStreamBeginCaptureToGraph(stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+        }
+        if (e == cudaSuccess) {
+            captured = true;
+            launch_round(1u, 1u); launch_round_logic(1u, 1u);
+            launch_round(2u, 0u); launch_round_logic(2u, 0u);
+            wf_loop_kernel<<<1, 1, 0, stream>>>(handle, wb.ctl, n_paths, d_cnt, 2u * launches_per_round + 1u);
+            cudaGraph_t out = nullptr;
+            e = cudaStreamEndCapture(stream, &out);
+        }
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+        if (e == cudaSuccess) e = cudaGraphLaunch(exec, stream);
+        if (exec) cudaGraphExecDestroy(exec);      // (in flight: freed when the launch completes)
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            if (captured) return e;                // the stream's state is the capture's: report
+            (void)cudaGetLastError();              // (no conditional-node support: the host loop below takes over after round 0)
+        } else {
+            wf_combine_kernel<<<(n_pixels + 255) / 256, 256, 0, stream>>>(wb, p, reinterpret_cast<float4*>(d_accum));
+            if (rounds_out) *rounds_out = 1u;      // round 0; the loop's rounds and launches are counted on the device (DCounters)
+            if (launches_out) *launches_out += 2u + launches_per_round;
+            return cudaGetLastError();
+        }
+    }
+    uint32_t round = round0_done ? 1u : 0u, buf = round0_done ? 1u : 0u;
     uint32_t group = 8;
     for (;;) {
         const uint32_t first_round_of_group = round;
@@ -1226,33 +1321,9 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
                 ev_b = timing->pool[2 * (round - first_round_of_group) + 1];
                 cudaEventRecord(ev_a, stream);
             }
-            if (bvh) {
-                if (round == 0u && fused_primary) wf_cast_bvh_primary_kernel<<<sm_count * 8, 128, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-                else wf_cast_bvh_kernel<<<sm_count * 8, 128, 0, stream>>>(sc, wb, buf, d_cnt);
-            } else if (round == 0u && fused_primary) {
-                if (rays_in_lanes) wf_cast_rl_primary_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, cam, p, wb, buf, d_cnt);
-                else wf_cast_rl_tiled_primary_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-            } else if (rays_in_lanes) {
-                wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, wb, buf, d_cnt);
-            } else if (rays_in_lanes_tiled) {
-                wf_cast_rl_tiled_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
-            } else {
-                wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
-            }
+            launch_round(round, buf);
             if (timing) cudaEventRecord(ev_b, stream);
-            if (round == 0u && fused_primary)
-                wf_logic_kernel<WF_SEG_PRIMARY0, false><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY0>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-            wf_logic_kernel<WF_SEG_PRIMARY, false><<<logic_blocks(LogicCfg<WF_SEG_PRIMARY>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-            if (fused) {
-                wf_logic_kernel<WF_SEG_SHADE, true><<<logic_blocks(LogicCfg<WF_SEG_SHADE, true>::kMinBlocks), LogicCfg<WF_SEG_SHADE, true>::kThreads, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-                wf_logic_kernel<WF_SEG_BOUNCE, true><<<logic_blocks(LogicCfg<WF_SEG_BOUNCE, true>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-            } else {
-                wf_logic_kernel<WF_SEG_SHADE, false><<<logic_blocks(LogicCfg<WF_SEG_SHADE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-                wf_logic_kernel<WF_SEG_BOUNCE, false><<<logic_blocks(LogicCfg<WF_SEG_BOUNCE>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-            }
-            wf_logic_kernel<WF_SEG_REFR, false><<<logic_blocks(LogicCfg<WF_SEG_REFR>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-            if (p.depth <= 0)   // get_shade of depth-0 primary hits (the only source of this segment)
-                wf_logic_kernel<WF_SEG_SHB, false><<<logic_blocks(LogicCfg<WF_SEG_SHB>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            launch_round_logic(round, buf);
         }
         e = cudaMemcpyAsync(h_pinned_retired, &wb.ctl->retired, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess) return e;

@@ -234,9 +234,12 @@ int b200rt_render_distributed_device(b200rt_ctx* ctx, const b200rt_camera* cam, 
 int b200rt_render_distributed_strips_device(b200rt_ctx* ctx, const b200rt_camera* cam, const b200rt_params* params,
                                             uint32_t epoch_begin, uint32_t epoch_count, float* d_accum, void* cuda_stream,
                                             uint32_t strip_rows, uint32_t n_parts, uint32_t part);
-/* Note: with B200RT_TRACER_WAVEFRONT the call polls a device counter to know when every path has retired, i.e.
- * it synchronises with `cuda_stream` a few times while it enqueues rounds; on return all but the final
- * accumulate kernel have completed.  B200RT_TRACER_MEGAKERNEL enqueues one kernel and returns. */
+/* Note: the *_device calls are ASYNCHRONOUS on a stream the caller created: with B200RT_TRACER_WAVEFRONT the rounds of
+ * the tracer repeat on the device (a CUDA graph WHILE node that ends when every path has retired), the call enqueues
+ * round 0, that graph and the accumulate kernel and returns; B200RT_TRACER_MEGAKERNEL enqueues one kernel and returns.
+ * On the legacy default stream (cuda_stream = NULL: it cannot be captured into a graph), and while per-kernel timing
+ * is on (b200rt_set_kernel_timing), the wavefront call enqueues its rounds from the host and synchronises with the
+ * stream a few times to read the retired-paths counter; on return all but the accumulate kernel have completed. */
 
 /* photon.rs:18-21 into_rgb_internal: out_rgb[i] = weight_sum < EPSILON ? 0 : sum / weight_sum */
 int b200rt_resolve_device(b200rt_ctx* ctx, const float* d_accum, float* d_out_rgb, size_t n_pixels,
