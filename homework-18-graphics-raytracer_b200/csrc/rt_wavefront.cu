@@ -606,6 +606,11 @@ template <> struct LogicCfg<WF_SEG_REFR, false> { static constexpr int kMinBlock
 // shade + arrival + next level in one pass
 template <> struct LogicCfg<WF_SEG_SHADE, true> { static constexpr int kMinBlocks = WF_FUSED_SHADE_MIN_BLOCKS, kThreads = WF_FUSED_SHADE_THREADS; };
 
+// (Round 2 also measured pulling the rows a fused SHADE pass reads late - the ray and hit that travelled with the shadow
+// rays, the shadow directions: a third dependent round trip - into L2 with 16-byte cp.async copies while the state rows are
+// in flight: 74.5 ms of shading kernels per 16-epoch 4K batch against 74.7; and the queue entry of the warp's next chunk
+// one iteration ahead (WF_LOGIC_PREFETCH = 2): 75.3.  These kernels wait on dependent arithmetic, instruction fetch and
+// branches as much as on memory (ncu: long scoreboard 36 % of the stall samples, wait 22 %, no-instruction 14 %).)
 #ifndef WF_LOGIC_PREFETCH
 #define WF_LOGIC_PREFETCH 0   // measured on B200: pulling the next chunk's rows into L2 one iteration ahead is SLOWER (94.7 vs 89.2 ms per batch)
 #endif

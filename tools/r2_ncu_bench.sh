@@ -2,6 +2,7 @@
 # launch list of the bench command (device time of every launch; cold-cache, serialised: compare SHARES) and one --set full
 # capture of the fused shading kernel, each after the same command exited 0 without ncu.
 cd "$(dirname "$0")/.."
+export B200RT_WF_GRAPH=0   # ncu does not profile kernel nodes of conditional graphs: the rounds are enqueued from the host (same kernels)
 mkdir -p gpurun_out
 T=${1:-r2}
 CMD="python bench.py --steps 2 --warmup 1 --epochs 16 --no-cpu-baseline"

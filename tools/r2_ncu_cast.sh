@@ -3,6 +3,7 @@
 #   1. --set full of one large wf_cast_rl_kernel launch (tools/wf_profile_run.py 3840x2160x4, third cast launch)
 #   2. DRAM / time / pipe metrics of every cast launch of one 16-epoch 4K batch (the bench's batch size)
 cd "$(dirname "$0")/.."
+export B200RT_WF_GRAPH=0   # ncu does not profile kernel nodes of conditional graphs: the rounds are enqueued from the host (same kernels)
 mkdir -p gpurun_out
 T=${1:-r2a}
 python tools/wf_profile_run.py 3840x2160x4 > gpurun_out/${T}_plain.log 2>&1 &&
