@@ -26,6 +26,7 @@
 //   sres[n][4]   float2 {prim, t} per shadow ray                                        32 B
 //   q   [2][6][n] path ids per consumer segment (double buffered by round parity)       48 B
 //   work[2][5][n] cast work: one list of path ids per ray slot (path ray, 4 shadow rays)  40 B
+//   sums[n]      every slot's PhotonAccumulator {sum.rgb, weight_sum}, dense [slot][pixel]   16 B
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdlib>
@@ -55,13 +56,13 @@ enum : int {
     ROW_PEND,         // pending factor (BRDF probe value or decay^distance); w = get_refract travel distance
     ROW_NADJ,         // adjust_normal(hit.at.normal) of the current hit, between get_shade's entry and its sum
     ROW_HI_POS,       // get_refract: previous inside hit position, retry count | get_shade: sum of earlier light chunks
-    ROW_SUM,          // this slot's PhotonAccumulator {sum.rgb, weight_sum} (photon.rs:9-12)
+    ROW_SPARE2,       // (the slot's PhotonAccumulator lived here; it is a dense array of its own now: WfBuffers::sums)
     kStateRows
 };
 static_assert(kStateRows == WF_STATE_ROWS, "state rows");
 static_assert(ROW_CTRL % 2 == 0 && ROW_RNG == ROW_CTRL + 1 && ROW_ACC % 2 == 0 && ROW_T == ROW_ACC + 1 && ROW_HPOS % 2 == 0 &&
               ROW_HNORMAL == ROW_HPOS + 1 && ROW_HDIR % 2 == 0 && ROW_HDIR0 == ROW_HDIR + 1 && ROW_PEND % 2 == 0 &&
-              ROW_NADJ == ROW_PEND + 1 && ROW_HI_POS % 2 == 0 && ROW_SUM == ROW_HI_POS + 1, "rows that travel together share a sector");
+              ROW_NADJ == ROW_PEND + 1 && ROW_HI_POS % 2 == 0 && ROW_SPARE2 == ROW_HI_POS + 1, "rows that travel together share a sector");
 #if WF_REQ_HP
 enum : int { REQ_O = 0, REQ_D = 1, REQ_SD3 = 2, REQ_HP = 4, REQ_SD0 = 5 };
 RT_DI int req_shadow_row(uint32_t s) { return s < 3u ? REQ_SD0 + (int)s : REQ_SD3; }
@@ -1019,17 +1020,17 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 if (seg != WF_SEG_INIT) {
                     // (a slot's first sample starts its accumulator: no INIT pass zeroed it when round 0 ran fused)
                     const bool first = wb.fused_primary != 0u && sample_idx == e_lane;
-                    if (!first) sum = pm.ld(ROW_SUM);
+                    if (!first) sum = wb.sums[pid];
                     const bool accepted = is_normal_f32(acc.x) && is_normal_f32(acc.y) && is_normal_f32(acc.z);   // main.rs:1157-1160
                     if (accepted) {
                         sum.x += acc.x; sum.y += acc.y; sum.z += acc.z; sum.w += 1.0f;            // photon.rs:30-31
                         n_samples += 1ull;
                     }
-                    if (accepted || first) pm.sv(ROW_SUM, sum);
+                    if (accepted || first) wb.sums[pid] = sum;
                     sample_idx += wb.epar;
                 } else {
                     sample_idx = e_lane;
-                    pm.template sv2<false>(ROW_HI_POS, sum, sum);   // the whole 32-byte sector: no read-modify-write in DRAM
+                    wb.sums[pid] = sum;
                 }
                 if (sample_idx >= n_epochs) out = OUT_RETIRE;
                 else {
@@ -1129,9 +1130,9 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
 __global__ void wf_combine_kernel(const WfBuffers wb, const DParams p, float4* __restrict__ accum) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= wb.n_pixels) return;
-    float4 s = wb.st[(size_t)pix * kStateRows + ROW_SUM];
+    float4 s = wb.sums[pix];
     for (uint32_t e = 1; e < wb.epar; ++e) {
-        const float4 v = wb.st[((size_t)e * wb.n_pixels + pix) * kStateRows + ROW_SUM];
+        const float4 v = wb.sums[(size_t)e * wb.n_pixels + pix];      // (dense per slot: coalesced over the pixels of a warp)
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     const size_t at = (size_t)wf_frame_row(p, pix / p.width) * p.width + pix % p.width;
@@ -1151,10 +1152,10 @@ __global__ void wf_loop_kernel(cudaGraphConditionalHandle handle, const WfContro
 
 // ---- host side -----------------------------------------------------------------------------------------------
 size_t wf_workspace_bytes_per_path() {
-    return (size_t)kStateRows * 16 + WF_REQ_ROWS * 16 + 32 + 32 + 2 * WF_SEG_COUNT * 4 + 2 * WF_WORK_PER_PATH * 4;
+    return (size_t)kStateRows * 16 + WF_REQ_ROWS * 16 + 32 + 32 + 2 * WF_SEG_COUNT * 4 + 2 * WF_WORK_PER_PATH * 4 + 16;
 }
 size_t wf_workspace_bytes(uint32_t n_paths) {
-    return sizeof(WfControl) + 256 + (size_t)n_paths * wf_workspace_bytes_per_path() + 16 * 64;
+    return sizeof(WfControl) + 256 + (size_t)n_paths * wf_workspace_bytes_per_path() + 16 * 256;   // (every array starts on a 256-byte boundary)
 }
 
 // Epochs rendered at once: every epoch of a batch has its own path slot per pixel, so no slot ever renders two samples
@@ -1188,6 +1189,7 @@ static WfBuffers wf_carve(void* workspace, uint32_t n_paths, uint32_t n_pixels, 
     wb.sres = reinterpret_cast<float2*>(b + off);              off = align(off + n * 32);
     wb.q = reinterpret_cast<uint32_t*>(b + off);               off = align(off + n * 2 * WF_SEG_COUNT * 4);
     wb.work = reinterpret_cast<uint32_t*>(b + off);            off = align(off + n * 2 * WF_WORK_PER_PATH * 4);
+    wb.sums = reinterpret_cast<float4*>(b + off);              off = align(off + n * 16);
     wb.n = n_paths; wb.n_pixels = n_pixels; wb.epar = epar; wb.fused_primary = 0u;
     return wb;
 }

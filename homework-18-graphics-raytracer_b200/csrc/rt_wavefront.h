@@ -60,6 +60,7 @@ struct WfBuffers {
     float2* sres;            // [n][4]
     uint32_t* q;             // [2][WF_SEG_COUNT][n]
     uint32_t* work;          // [2][WF_WORK_PER_PATH][n]: one list of path ids per ray slot
+    float4* sums;            // [n] = [slot][pixel]: every slot's PhotonAccumulator {sum.rgb, weight_sum} (photon.rs:9-12), dense
     uint32_t n, n_pixels, epar;
     uint32_t fused_primary;  // round 0 ran without an INIT pass: a slot's first sample starts its accumulator row
 };
