@@ -221,7 +221,8 @@ def run_b200(args):
                    sc.n_materials * ctypes.sizeof(b.Material) + sc.n_lights * ctypes.sizeof(b.Light))
     cam = b.fixture_camera()
     tracer_id = b.TRACER_WAVEFRONT if args.tracer == "wavefront" else b.TRACER_MEGAKERNEL
-    params = b.default_params(width=W, height=H, depth=depth, seed=0, tracer=tracer_id)
+    cast_id = b.CAST_BVH if args.cast == "bvh" else b.CAST_TWO_PHASE
+    params = b.default_params(width=W, height=H, depth=depth, seed=0, tracer=tracer_id, cast_mode=cast_id)
 
     # ---- the device group: one rank per process, NCCL inside the library (include/b200rt.h, "device groups") -------------
     # The id of the NCCL communicator is made on rank 0 and handed to the other ranks (here: a torch broadcast).
@@ -426,7 +427,8 @@ def run_b200(args):
             "config": {"workload": desc + (" [REDUCED SIZE: dev run]" if reduced else ""), "width": W, "height": H,
                        "depth": depth, "epochs": epochs, "sharding": ("rows" if (by_rows or tracer != "distributed") else "epochs"),
                        "collective": "NCCL inside libb200rt.so (b200rt_group_*): " + ("ncclSend/ncclRecv gather of row bands to rank 0" if (by_rows or tracer != "distributed") else "one ncclReduce(sum) of the accumulators to rank 0"),
-                       "cast_mode": "two_phase", "tracer": args.tracer if tracer == "distributed" else "megakernel",
+                       "cast_mode": "two_phase" if args.cast != "bvh" else "bvh (SURVEY 8f N1: the same hits through the acceleration structure - NOT the brute-force walk the roofline figure is defined on; roofline.frac of this line counts the pairs the reference would test)",
+                       "tracer": args.tracer if tracer == "distributed" else "megakernel",
                        "timing": "per step: CUDA events on the launching stream around accumulator clear + render + collective (b200rt_group_last_render_ms), max over ranks",
                        "l2": "path state + ray buffers (%.1f GB per 16-epoch batch) and the accumulation buffer (%.1f MB) exceed L2; scene records stay in the constant bank / shared memory" % (W * H * 16 * 440 / 1e9, W * H * 16 / 1e6)},
             "accepted_samples_per_s": accepted / (ms_per_step * 1e-3) / 1e6,
@@ -572,6 +574,8 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--epochs", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cast", default="two_phase", choices=["two_phase", "bvh"],
+                    help="World::cast: the reference's brute-force walk (two-phase cast; the headline) or the acceleration structure (same hits)")
     ap.add_argument("--tracer", default="wavefront", choices=["wavefront", "megakernel"],
                     help="GPU schedule of the stochastic tracer (same samples, same bits)")
     args = ap.parse_args()
