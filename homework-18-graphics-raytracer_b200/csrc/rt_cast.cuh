@@ -270,8 +270,11 @@ RT_DI uint2* cast_slot_masks(float4* s_rays) { return reinterpret_cast<uint2*>(s
 //   shared-memory copy of the plain filter records, whose first row holds the same bits (degenerate triangles are
 //   all-zero there: n.dir = 0, set U).
 //   exact: the exact records {n,d}{v0,obj}{v1}{v2} of the tile's triangles (sc.tri_exact + 4 * base, or a shared-memory copy).
+//   nan_out (optional): set when a NaN distance was accepted on the way - the result then depends on the nearest-so-far
+//   the walk STARTED from (a caller that folds the results of separate triangle ranges must not use this one).
 RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand, bool certify, const DRay& ray,
-                        Best& best, CastStats& cs, const float4* __restrict__ planes, const float4* __restrict__ exact) {
+                        Best& best, CastStats& cs, const float4* __restrict__ planes, const float4* __restrict__ exact,
+                        bool* nan_out = nullptr) {
     if (cand == 0ull) return;
     unsigned long long todo = cand;
     bool fast = false;
@@ -324,6 +327,7 @@ RT_DI void confirm_tile(const DScene& sc, uint32_t base, unsigned long long cand
             tri_exact_test(exact + 4 * (size_t)i, (int32_t)(base + i), ray, best);
             nan_seen |= best.t != best.t;
         }
+        if (nan_out && nan_seen) *nan_out = true;
         if (!fast) break;
         // certified: every survivor that was not tested is strictly farther than the nearest hit so far
         if (!nan_seen && (lo2 == CUDART_INF_F || (best.prim >= 0 && lo2 > best.t))) break;

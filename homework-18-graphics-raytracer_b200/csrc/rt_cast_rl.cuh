@@ -458,7 +458,7 @@ RT_DI void rl_best_load(const RlTiledShared& sh, int j, uint32_t tid, const DRay
 // in index order, by all lanes alike.  32x the speed of one lane walking 64 exact tests, same result as the walk for
 // any distances (inf and NaN included).  Warp-collective: every lane calls it with the SAME ray and the owner's best.
 RT_DI void rl_coop_exact_tile(const DScene& sc, uint32_t tile, const DRay& r, uint32_t lane, bool& best_valid, float& best_t,
-                              Best& winner, bool& changed, CastStats& cs) {
+                              Best& winner, bool& changed, CastStats& cs, bool* nan_out = nullptr) {
     const uint32_t base = tile * kTileTris;
     Best ba, bb;
     best_init(ba); best_init(bb);
@@ -474,6 +474,7 @@ RT_DI void rl_coop_exact_tile(const DScene& sc, uint32_t tile, const DRay& r, ui
         const float t = __shfl_sync(kFullMask, ba.t, l);
         if (best_valid && best_t < t) continue;     // main.rs:229-233
         best_valid = true; best_t = t; win = l;
+        if (nan_out && t != t) *nan_out = true;     // (an accepted NaN: the walk is order-dependent from here)
     }
 #pragma unroll 1
     while (mb) {
@@ -482,6 +483,7 @@ RT_DI void rl_coop_exact_tile(const DScene& sc, uint32_t tile, const DRay& r, ui
         const float t = __shfl_sync(kFullMask, bb.t, l);
         if (best_valid && best_t < t) continue;
         best_valid = true; best_t = t; win = 32 + l;
+        if (nan_out && t != t) *nan_out = true;
     }
     if (lane == 0u) cs.confirms += (unsigned long long)min(kTileTris, (int)(sc.n_tris - base));
     if (win >= 0) {
@@ -663,6 +665,228 @@ RT_DI void cast_rays_in_lanes_tiled(const DScene& sc, IO io, const uint32_t n_wo
             cs.casts += 1ull;
             io.store(tag, h);
         }
+    }
+}
+
+// ---- scenes of more than one tile, FEW rays: the tile range of a ray block split over the warps of a CTA ----------------
+// A unit of work of cast_rays_in_lanes_tiled is 128 rays x ALL tiles by one warp (8 ms on the 1570 tiles of C5): a round of
+// a few ten thousand rays - the later rounds of a frame, every round of an eighth of a frame on one of 8 GPUs - keeps a
+// fraction of the SMs busy for that long whatever its size.  Here a CTA takes ONE block of 128 rays and its four warps walk
+// a quarter of the tiles each, every warp with its own two-deep TMA ring (lane 0 issues, an mbarrier per buffer,
+// __syncwarp between tiles), and the four partial results of a ray are folded in tile order with the reference's own rule,
+// "skip if best.t < t" (main.rs:229-233) - which is the walk's result, because a range's winner is the last of its nearest
+// triangles and a later range only wins with t <= the earlier one's.  The one exception is a NaN distance accepted inside a
+// range (a ray lying in a triangle's plane, main.rs:204): it makes the walk depend on the nearest-so-far the range started
+// from.  confirm_tile / rl_coop_exact_tile flag it, and such a ray takes the ordered walk over every triangle by the whole
+// warp.  Spheres, attributes and the result follow as in the unsplit cast: warp w finishes ray w of every lane.
+struct RlSplitShared {                              // 51 KB per CTA
+    alignas(128) float4 tile[4][2][4 * kTileTris];  // per warp: TMA destinations
+    unsigned long long bar[4][2];
+    float4 ro[4][32];                               // the block's rays [j][lane] (every warp stages the same values)
+    float4 rd[4][32];
+    uint2 mk[4][4][32];                             // per warp: candidate masks of the current tile [warp][j][lane]
+    float4 best[4][4][32];                          // per warp: nearest of its tile range [warp][j][lane]
+    float best_a2[4][4][32];
+    uint32_t bad[4][32];                            // per warp: bit j = a NaN distance was accepted for ray j in this range
+};
+
+template <class IO>
+RT_DI void cast_rays_in_lanes_tiled_split(const DScene& sc, IO io, const uint32_t n_work, RlSplitShared& sh, CastStats& cs) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = sc.n_tris_padded / kTileTris;
+    if (n_work == 0u || n_tiles == 0u) return;
+    if (lane == 0u) { rl_mbar_init(&sh.bar[warp][0], 1u); rl_mbar_init(&sh.bar[warp][1], 1u); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t parity0 = 0u, parity1 = 0u;
+    const P2 As2 = p2_bc(sc.filter_As);
+    const P2 one2 = p2_bc(__fmaf_rn(sc.filter_g, 0.0f, 1.0f));   // see cast_rays_in_lanes
+    const uint32_t n_blocks = (n_work + 127u) / 128u;
+    const uint32_t t0 = (warp * n_tiles) / 4u, t1 = ((warp + 1u) * n_tiles) / 4u;      // this warp's tiles
+    auto best_store = [&](int j, const Best& b) {
+        sh.best[warp][j][lane] = make_float4(__uint_as_float(((uint32_t)(b.prim + 1) << 1) | (b.bf & 1u)), b.t, b.a0, b.a1);
+        sh.best_a2[warp][j][lane] = b.a2;
+    };
+    auto best_load = [&](uint32_t w, int j, uint32_t l, const DRay& r, Best& b) {
+        const float4 v = sh.best[w][j][l];
+        const uint32_t u = __float_as_uint(v.x);
+        b.prim = (int32_t)(u >> 1) - 1; b.bf = u & 1u; b.t = v.y; b.a0 = v.z; b.a1 = v.w; b.a2 = sh.best_a2[w][j][l];
+        b.pos = b.prim >= 0 ? r.o + r.d * b.t : mk3(0.f, 0.f, 0.f);                   // main.rs:210
+    };
+    auto ray_of = [&](int j, uint32_t l, DRay& r, uint32_t& tag) {
+        const float4 a = sh.ro[j][l], b = sh.rd[j][l];
+        const uint32_t meta = __float_as_uint(a.w);
+        r.o = mk3(a); r.d = mk3(b);
+        r.face = meta & 3u; r.ex_face = (meta >> 2) & 3u; r.ex_prim = (int32_t)(meta >> 4) - 1;
+        tag = __float_as_uint(b.w);
+    };
+    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        if (lane == 0u && t0 < t1) {
+            rl_tma_load_tile(sh.tile[warp][0], sc.tri_filter_plain + (size_t)t0 * 4u * kTileTris, &sh.bar[warp][0]);
+            if (t0 + 1u < t1) rl_tma_load_tile(sh.tile[warp][1], sc.tri_filter_plain + (size_t)(t0 + 1u) * 4u * kTileTris, &sh.bar[warp][1]);
+        }
+        const uint32_t base = blk * 128u;
+        io.begin_block(base);
+        P2 ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], cf[2];
+        uint32_t valid4 = 0u, trust4 = 0u, nan4 = 0u;
+        uint32_t have_front = 0u, have_back = 0u, have_both = 0u;
+        uint32_t tags[4];
+        DRay rays4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t idx = base + lane + 32u * (uint32_t)j;
+            tags[j] = idx < n_work ? io.item(idx) : kRlNoRay;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            rays4[j].o = mk3(0.f, 0.f, 0.f); rays4[j].d = mk3(0.f, 0.f, 1.f); rays4[j].face = kFront; rays4[j].ex_prim = -1; rays4[j].ex_face = kFront;
+            if (tags[j] != kRlNoRay) io.fetch(tags[j], rays4[j]);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            DRay (&r)[2] = reinterpret_cast<DRay (&)[2]>(rays4[2 * k]);
+            float c[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * k + h;
+                const uint32_t tag = tags[j];
+                c[h] = rl_cull_factor(r[h].face);
+                float dd;
+                if (tag != kRlNoRay) {
+                    have_front |= r[h].face == kFront; have_back |= r[h].face == kBack; have_both |= r[h].face > kBack;
+                    valid4 |= 1u << j;
+                    if (ray_trusted(sc, r[h], dd)) trust4 |= 1u << j;
+                    else if (ray_has_nan(r[h])) nan4 |= 1u << j;
+                }
+                if (warp == 0u) {       // (the four warps hold the same rays: one of them stages them for the per-ray passes)
+                    sh.ro[j][lane] = make_float4(r[h].o.x, r[h].o.y, r[h].o.z, __uint_as_float(rl_pack_ray_meta(r[h].face, r[h].ex_prim, r[h].ex_face)));
+                    sh.rd[j][lane] = make_float4(r[h].d.x, r[h].d.y, r[h].d.z, __uint_as_float(tag));
+                }
+                Best b0;
+                best_init(b0);
+                best_store(j, b0);
+            }
+            ox[k] = p2_mul(p2_pack(r[0].o.x, r[1].o.x), one2); oy[k] = p2_mul(p2_pack(r[0].o.y, r[1].o.y), one2);
+            oz[k] = p2_mul(p2_pack(r[0].o.z, r[1].o.z), one2);
+            dx[k] = p2_mul(p2_pack(r[0].d.x, r[1].d.x), one2); dy[k] = p2_mul(p2_pack(r[0].d.y, r[1].d.y), one2);
+            dz[k] = p2_mul(p2_pack(r[0].d.z, r[1].d.z), one2);
+            cf[k] = p2_mul(p2_pack(c[0], c[1]), one2);
+        }
+        uint32_t bad4 = 0u;
+        const int mode = rl_block_mode(have_front, have_back, have_both);
+        __syncthreads();                                            // the staged rays are visible to every warp
+#pragma unroll 1
+        for (uint32_t tile = t0; tile < t1; ++tile) {
+            const uint32_t buf = (tile - t0) & 1u;
+            if (buf == 0u) { rl_mbar_wait(&sh.bar[warp][0], parity0); parity0 ^= 1u; }
+            else           { rl_mbar_wait(&sh.bar[warp][1], parity1); parity1 ^= 1u; }
+            const float4* __restrict__ recs = sh.tile[warp][buf];
+            uint32_t keep[4][2];
+            rl_filter_tile_mode(mode, RlRecShared{recs}, ox, oy, oz, dx, dy, dz, cf, As2, keep);
+            // untrusted rays without NaNs: the whole warp tests the tile for each of them (rl_coop_exact_tile)
+            const uint32_t coop4 = valid4 & ~trust4 & ~nan4;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                unsigned owners = __ballot_sync(kFullMask, (coop4 >> j) & 1u);
+#pragma unroll 1
+                while (owners) {
+                    const int l = __ffs((int)owners) - 1;
+                    owners &= owners - 1u;
+                    DRay r;
+                    uint32_t tag;
+                    ray_of(j, (uint32_t)l, r, tag);
+                    Best cur;
+                    best_load(warp, j, (uint32_t)l, r, cur);
+                    bool bvalid = cur.prim >= 0, changed = false, nan_here = false;
+                    float bt = cur.t;
+                    Best winner = cur;
+                    rl_coop_exact_tile(sc, tile, r, lane, bvalid, bt, winner, changed, cs, &nan_here);
+                    if (lane == (uint32_t)l) { if (changed) best_store(j, winner); if (nan_here) bad4 |= 1u << j; }
+                    __syncwarp();
+                }
+            }
+            // phase 2 of this tile, for the trusted rays that have candidates in it
+            uint32_t todo4 = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (((valid4 & trust4) >> j) & 1u) { if ((keep[j][0] | keep[j][1]) != 0u) todo4 |= 1u << j; }
+            if (todo4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sh.mk[warp][j][lane] = make_uint2(keep[j][0], keep[j][1]);
+#pragma unroll 1
+                while (todo4) {
+                    const int j = __ffs((int)todo4) - 1;
+                    todo4 &= todo4 - 1u;
+                    DRay r;
+                    uint32_t tag;
+                    ray_of(j, lane, r, tag);
+                    Best best;
+                    best_load(warp, j, lane, r, best);
+                    const uint2 km = sh.mk[warp][j][lane], cm = io.culled(sc, tag, tile);
+                    bool nan_here = false;
+                    confirm_tile(sc, tile * kTileTris, tile_candidates(sc, tile, make_uint2(km.x & ~cm.x, km.y & ~cm.y), true),
+                                 true, r, best, cs, sc.tri_exact + 4 * (size_t)(tile * kTileTris),
+                                 sc.tri_exact + 4 * (size_t)(tile * kTileTris), &nan_here);
+                    best_store(j, best);
+                    if (nan_here) bad4 |= 1u << j;
+                }
+            }
+            __syncwarp();                                           // every lane is done with this buffer
+            if (lane == 0u && tile + 2u < t1)
+                rl_tma_load_tile(sh.tile[warp][buf], sc.tri_filter_plain + (size_t)(tile + 2u) * 4u * kTileTris, &sh.bar[warp][buf]);
+        }
+        sh.bad[warp][lane] = bad4;
+        __syncthreads();                                            // the four partial results of every ray are in shared memory
+        // warp w finishes ray w of every lane: fold the ranges in tile order, then spheres, attributes, result
+        {
+            const int j = (int)warp;
+            DRay r;
+            uint32_t tag;
+            ray_of(j, lane, r, tag);
+            const bool valid = tag != kRlNoRay;
+            float dd = 1.0f;
+            const bool trust = valid && ray_trusted(sc, r, dd);
+            const bool has_nan = valid && !trust && ray_has_nan(r);
+            Best best;
+            best_init(best);
+            bool bad = false;
+            if (valid && !has_nan) {
+#pragma unroll 1
+                for (uint32_t w = 0; w < 4u; ++w) {
+                    bad |= ((sh.bad[w][lane] >> j) & 1u) != 0u;
+                    Best part;
+                    best_load(w, j, lane, r, part);
+                    if (part.prim >= 0 && !(best.prim >= 0 && best.t < part.t)) best = part;      // main.rs:229-233
+                }
+            }
+            // an accepted NaN somewhere: the ordered walk over every triangle, one ray at a time, by the whole warp
+            unsigned redo = __ballot_sync(kFullMask, bad);
+#pragma unroll 1
+            while (redo) {
+                const int l = __ffs((int)redo) - 1;
+                redo &= redo - 1u;
+                DRay rr;
+                uint32_t tg;
+                ray_of(j, (uint32_t)l, rr, tg);
+                Best w;
+                best_init(w);
+                bool bvalid = false, changed = false;
+                float bt = 0.0f;
+#pragma unroll 1
+                for (uint32_t tile = 0; tile < n_tiles; ++tile) rl_coop_exact_tile(sc, tile, rr, lane, bvalid, bt, w, changed, cs);
+                if ((int)lane == l) { best_init(best); if (changed) best = w; cs.fallbacks += 1ull; }
+            }
+            if (valid) {
+                if (has_nan) cast_nan_ray_triangles(sc, r, best, cs);
+                cast_spheres(sc, r, trust, dd, best);
+                DHit h;
+                h.prim = -1; h.face = 0; h.object = 0; h.t = 0.f; h.pos = h.normal = mk3(0.f, 0.f, 0.f); h.uv.x = h.uv.y = 0.f;
+                finalize_hit(sc, best, h, io.want_attrs(tag));
+                cs.casts += 1ull;
+                io.store(tag, h);
+            }
+        }
+        __syncthreads();                                            // shared memory is free for the next block
     }
 }
 

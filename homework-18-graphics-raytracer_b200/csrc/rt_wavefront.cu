@@ -435,21 +435,57 @@ __global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_MIN_BLOCKS) wf_cast_rl_
 #ifndef WF_CAST_RL_TILED_MIN_BLOCKS
 #define WF_CAST_RL_TILED_MIN_BLOCKS 5
 #endif
+// Rounds of few rays (at most split_below blocks of 128) go to wf_cast_rl_tiled_split_kernel instead, which is launched right
+// after this one: the work counters live on the device, so both kernels are enqueued every round and one of them returns.
 __global__ void __launch_bounds__(kRlThreads, WF_CAST_RL_TILED_MIN_BLOCKS) wf_cast_rl_tiled_kernel(const DScene sc, const WfBuffers wb,
                                                                                                   const uint32_t buf,
-                                                                                                  DCounters* __restrict__ cnt) {
+                                                                                                  DCounters* __restrict__ cnt,
+                                                                                                  const uint32_t split_below) {
     __shared__ RlTiledShared sh;
     const uint32_t lane = threadIdx.x & 31u;
     if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
     const WfWork wk = wf_work(wb, buf);
     const uint32_t n_work = wk.n_real();
     if (n_work == 0u) return;
+    if ((wk.n_virtual() >> 7) <= split_below) return;
     CastStats cs;
     cs.casts = cs.confirms = cs.fallbacks = 0ull;
     WfRayIO io;
     io.wb = wb; io.work = wk;
     cast_rays_in_lanes_tiled(sc, io, wk.n_virtual(), sh, cs);
     if (cnt) {
+        unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_conf += __shfl_xor_sync(0xffffffffu, n_conf, o);
+            n_fb += __shfl_xor_sync(0xffffffffu, n_fb, o);
+        }
+        if (lane == 0u && n_conf) atomicAdd(&cnt->confirms, n_conf);
+        if (lane == 0u && n_fb) atomicAdd(&cnt->fallbacks, n_fb);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicAdd(&cnt->casts, (unsigned long long)n_work);
+            atomicAdd(&cnt->tri_pairs, (unsigned long long)n_work * sc.n_tris);
+            atomicAdd(&cnt->sph_pairs, (unsigned long long)n_work * sc.n_sph);
+        }
+    }
+}
+
+// the same cast for rounds of few rays: one block of 128 rays per CTA, the tile range split over its four warps
+// (rt_cast_rl.cuh: cast_rays_in_lanes_tiled_split).  51 KB of dynamic shared memory.
+__global__ void __launch_bounds__(kRlThreads, 4) wf_cast_rl_tiled_split_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf,
+                                                                              DCounters* __restrict__ cnt, const uint32_t split_below) {
+    extern __shared__ __align__(128) unsigned char wf_split_smem[];
+    RlSplitShared& sh = *reinterpret_cast<RlSplitShared*>(wf_split_smem);
+    const WfWork wk = wf_work(wb, buf);
+    const uint32_t n_work = wk.n_real();
+    if (n_work == 0u || (wk.n_virtual() >> 7) > split_below) return;
+    CastStats cs;
+    cs.casts = cs.confirms = cs.fallbacks = 0ull;
+    WfRayIO io;
+    io.wb = wb; io.work = wk;
+    cast_rays_in_lanes_tiled_split(sc, io, wk.n_virtual(), sh, cs);
+    if (cnt) {
+        const uint32_t lane = threadIdx.x & 31u;
         unsigned long long n_conf = cs.confirms, n_fb = cs.fallbacks;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -1224,6 +1260,18 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     wb.fused_primary = fused_primary ? 1u : 0u;
     if (!fused_primary)
         wf_logic_kernel<WF_SEG_INIT, false><<<logic_blocks(LogicCfg<WF_SEG_INIT>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, 1u, d_cnt);
+    // Scenes of many tiles: rounds of at most split_below 128-ray blocks take the split form of the cast (a block per CTA,
+    // the tile range over its warps).  The unsplit kernel fills the GPU with sm_count x 5 x 4 blocks; below half of that the
+    // split form is faster (B200RT_WF_SPLIT_BELOW overrides, 0 = never).
+    uint32_t split_below = 0u;
+    if (rays_in_lanes_tiled) {
+        split_below = (uint32_t)sm_count * WF_CAST_RL_TILED_MIN_BLOCKS * 2u;
+        if (const char* sb = getenv("B200RT_WF_SPLIT_BELOW")) split_below = (uint32_t)strtoul(sb, nullptr, 10);
+        if (split_below) {
+            e = cudaFuncSetAttribute(wf_cast_rl_tiled_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RlSplitShared));
+            if (e != cudaSuccess) return e;
+        }
+    }
     // one round on `stream`: the cast of the rays requested in the round before, then the passes that consume it
     auto launch_round = [&](uint32_t round, uint32_t buf) {
         if (bvh) {
@@ -1235,7 +1283,8 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
         } else if (rays_in_lanes) {
             wf_cast_rl_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, wb, buf, d_cnt);
         } else if (rays_in_lanes_tiled) {
-            wf_cast_rl_tiled_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt);
+            wf_cast_rl_tiled_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, wb, buf, d_cnt, split_below);
+            if (split_below) wf_cast_rl_tiled_split_kernel<<<sm_count * 4, kRlThreads, sizeof(RlSplitShared), stream>>>(sc, wb, buf, d_cnt, split_below);
         } else {
             wf_cast_kernel<<<cast_blocks, 128, 0, stream>>>(sc, wb, buf, d_cnt);
         }
@@ -1255,7 +1304,7 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
         if (p.depth <= 0)   // get_shade of depth-0 primary hits (the only source of this segment)
             wf_logic_kernel<WF_SEG_SHB, false><<<logic_blocks(LogicCfg<WF_SEG_SHB>::kMinBlocks), 256, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
     };
-    const uint32_t launches_per_round = p.depth <= 0 ? 6u : 5u;
+    const uint32_t launches_per_round = (p.depth <= 0 ? 6u : 5u) + ((rays_in_lanes_tiled && split_below) ? 1u : 0u);
 
     // The round loop ON THE DEVICE: a CUDA graph whose WHILE node repeats {round on buffer 1, round on buffer 0, "any
     // path left?"} until every slot has retired (wf_loop_kernel sets the node's condition from the retired counter).  The
