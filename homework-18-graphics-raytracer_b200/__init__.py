@@ -117,7 +117,7 @@ HIT_DTYPE = np.dtype([("prim_id", "<i4"), ("object_index", "<u4"), ("face_direct
 assert RAY_DTYPE.itemsize == C.sizeof(Ray) and HIT_DTYPE.itemsize == C.sizeof(Hit)
 
 # include/b200rt_dev.h: development micro-benchmarks (not part of the product ABI)
-DEV_SYMBOLS = ["b200rt_filter_bench", "b200rt_pipe_bench", "b200rt_dev_build_bvh"]
+DEV_SYMBOLS = ["b200rt_filter_bench", "b200rt_pipe_bench", "b200rt_dev_build_bvh", "b200rt_dev_color_pow"]
 
 # every symbol include/b200rt.h declares
 EXPORTED_SYMBOLS = [
@@ -181,6 +181,7 @@ def load_library() -> C.CDLL:
         "b200rt_measure_fp32_peak": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "b200rt_filter_bench": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
         "b200rt_pipe_bench": (C.c_int, [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
+        "b200rt_dev_color_pow": (C.c_int, [vp, f32p, f32p, f32p, C.c_size_t]),
         "b200rt_dev_build_bvh": (C.c_int, [C.POINTER(Scene), C.c_int, f32p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "b200rt_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),

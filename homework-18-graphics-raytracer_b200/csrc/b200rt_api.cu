@@ -920,6 +920,24 @@ int b200rt_filter_bench(b200rt_ctx* ctx, int variant, int blocks_per_sm, int ite
     return B200RT_OK;
 }
 
+// dev / test entry (b200rt_dev.h): out[i] = color_pow(x[i], e[i]) on the device
+int b200rt_dev_color_pow(b200rt_ctx* ctx, const float* x, const float* e, float* out, size_t n) {
+    if (!ctx || !x || !e || !out) return B200RT_ERR_INVALID;
+    if (n == 0) return B200RT_OK;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, &ctx->d_aux, &ctx->d_aux_bytes, 2 * n * sizeof(float));
+    if (rc != B200RT_OK) return rc;
+    rc = ensure(ctx, &ctx->d_out, &ctx->d_out_bytes, n * sizeof(float));
+    if (rc != B200RT_OK) return rc;
+    float* d_x = (float*)ctx->d_aux;
+    CU(cudaMemcpyAsync(d_x, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_x + n, e, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_color_pow(d_x, d_x + n, (float*)ctx->d_out, n, ctx->stream));
+    CU(cudaMemcpyAsync(out, ctx->d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200RT_OK;
+}
+
 int b200rt_pipe_bench(b200rt_ctx* ctx, int variant, float* kernel_ms, double* inst_per_clk_per_smsp) {
     if (!ctx || !kernel_ms || !inst_per_clk_per_smsp) return B200RT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));

@@ -135,4 +135,15 @@ cudaError_t launch_encode_srgb8(const float* d_rgb, size_t n_values, uint8_t* d_
     return cudaGetLastError();
 }
 
+// dev / test: color_pow (rt_math.cuh) element by element, so that its error bound can be measured against f64 pow
+__global__ void color_pow_kernel(const float* __restrict__ x, const float* __restrict__ e, float* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = color_pow(x[i], e[i]);
+}
+cudaError_t launch_color_pow(const float* d_x, const float* d_e, float* d_out, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    color_pow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_x, d_e, d_out, n);
+    return cudaGetLastError();
+}
+
 }  // namespace b200rt

@@ -156,6 +156,7 @@ cudaError_t launch_fp32_peak(float* d_sink, int blocks, int threads, int iters, 
 // rt_image.cu
 size_t post_process_workspace_bytes();
 cudaError_t launch_post_process(float* d_rgb, size_t n_pixels, void* d_workspace, float* d_p98_out, int sm_count, cudaStream_t stream);
+cudaError_t launch_color_pow(const float* d_x, const float* d_e, float* d_out, size_t n, cudaStream_t stream);
 cudaError_t launch_encode_srgb8(const float* d_rgb, size_t n_values, uint8_t* d_out, int sm_count, cudaStream_t stream);
 
 }  // namespace b200rt

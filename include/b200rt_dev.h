@@ -29,6 +29,10 @@ int b200rt_pipe_bench(b200rt_ctx* ctx, int variant, float* kernel_ms, double* in
 int b200rt_dev_build_bvh(const b200rt_scene* scene, int which, float* nodes_out, uint32_t max_nodes, uint32_t* tri_index_out,
                          uint32_t* n_nodes, uint32_t* n_indexed, uint32_t* depth, uint32_t* n_leaves);
 
+/* out[i] = color_pow(x[i], e[i]) on the device (csrc/rt_math.cuh): the power the shading code uses where the result is only
+ * ever a colour - Phong lobe, spot cone, opaque decay - so that its error bound is measured, not asserted. */
+int b200rt_dev_color_pow(b200rt_ctx* ctx, const float* x, const float* e, float* out, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,3 +136,47 @@ def test_render_main_progressive_renormalisation(b200rt, oracle, gpu_ctx, fixtur
     assert (err > 1e-3).mean() < 2e-3
     assert np.array_equal(np.asarray(Image.open(out).convert("RGB")), frames[3])
 
+
+
+def test_color_pow_error_bound(b200rt, gpu_ctx):
+    """color_pow (csrc/rt_math.cuh) - the power behind the Phong lobe (materials.rs:63), the spot cone (lights.rs:62-64) and
+    the opaque decay (main.rs:508 / 605), whose results are only ever colours - against f64 pow: absolute error <= 2.5e-7,
+    relative error <= 3e-7 max(1, |e log2 x|) over every exponent of the fixture scene and the extremes the builder
+    accepts; subnormal results are kept (the is_normal filter sees what the reference sees), and the arguments outside
+    its fast path fall through to powf."""
+    import ctypes as C
+    lib = b200rt.load_library()
+    rng = np.random.default_rng(5)
+    f32p = C.POINTER(C.c_float)
+
+    def dev(x, e):
+        x = np.ascontiguousarray(x, dtype=np.float32); e = np.ascontiguousarray(np.broadcast_to(np.float32(e), x.shape), dtype=np.float32)
+        out = np.zeros_like(x)
+        rc = lib.b200rt_dev_color_pow(gpu_ctx._h, x.ctypes.data_as(f32p), e.ctypes.data_as(f32p), out.ctypes.data_as(f32p), x.size)
+        assert rc == b200rt.OK
+        return out
+
+    eps = np.finfo(np.float32).eps
+    exps = [1 / (s + eps) for s in (1.0, 0.7, 0.2, 0.01, 0.001, 1e-5)] + [1.0 + eps, 0.5, 3.0, 2.5e-3, 8.4e6, 37.5]
+    worst_abs = worst_rel = 0.0
+    for e in exps:
+        e = np.float32(e)
+        x = np.concatenate([rng.random(1 << 16), 1.0 - rng.random(1 << 16) * min(1.0, 60.0 / float(e)),
+                            [1.0, np.nextafter(np.float32(1), np.float32(2)), 0.5, 0.25, 1e-20, 1e-37, 3e-38]]).astype(np.float32)
+        got = dev(x, e).astype(np.float64)
+        want = np.power(x.astype(np.float64), float(e))
+        y = np.abs(float(e) * np.log2(x.astype(np.float64)))
+        big = want >= 2.0 ** -126
+        worst_abs = max(worst_abs, float(np.abs(got - want).max()))
+        rel = np.abs(got[big] - want[big]) / want[big] / np.maximum(1.0, y[big])
+        worst_rel = max(worst_rel, float(rel.max()))
+        sub = (want < 2.0 ** -126) & (want >= 2.0 ** -149)
+        if sub.any():    # subnormal results survive (MUFU.EX2 alone would flush them)
+            assert (got[sub] > 0).all() and np.abs(got[sub] - want[sub]).max() <= 2.0 ** -140, float(e)
+        assert (got[want < 2.0 ** -151] == 0).all()
+    print(f"color_pow: max abs err {worst_abs:.2e}, max rel err / max(1, |e log2 x|) {worst_rel:.2e}")
+    assert worst_abs <= 2.5e-7 and worst_rel <= 3e-7
+    # outside the fast path: the libm answers
+    assert dev([0.0, 0.0, 0.5, 2.0, np.inf], [2.0, 0.0, 0.0, 0.0, 2.0]).tolist() == [0.0, 1.0, 1.0, 1.0, np.inf]
+    assert np.isnan(dev([np.nan], 2.0))[0] and np.isnan(dev([-0.5], 0.5))[0]
+    assert dev([0.25], 0.5)[0] == 0.5 and dev([1.0], 1e5)[0] == 1.0
