@@ -648,6 +648,16 @@ template <> struct LogicCfg<WF_SEG_SHADE, true> { static constexpr int kMinBlock
 // in flight: 74.5 ms of shading kernels per 16-epoch 4K batch against 74.7; and the queue entry of the warp's next chunk
 // one iteration ahead (WF_LOGIC_PREFETCH = 2): 75.3.  These kernels wait on dependent arithmetic, instruction fetch and
 // branches as much as on memory (ncu: long scoreboard 36 % of the stall samples, wait 22 %, no-instruction 14 %).)
+#ifndef WF_SHADE_SUM_UNROLL
+// the light loops of get_shade (its sum, its entry): unrolled copies measured on B200 - shading kernels of a 16-epoch 4K
+// batch 74.9 ms rolled; sum x2 75.4, sum x4 76.6, entry x4 78.0, both x4 78.9 (code size: these kernels already wait on
+// instruction fetch)
+#define WF_SHADE_SUM_UNROLL 1
+#endif
+#ifndef WF_SHADE_BEGIN_UNROLL
+#define WF_SHADE_BEGIN_UNROLL 1
+#endif
+constexpr int kShadeSumUnroll = WF_SHADE_SUM_UNROLL, kShadeBeginUnroll = WF_SHADE_BEGIN_UNROLL;
 #ifndef WF_LOGIC_PREFETCH
 #define WF_LOGIC_PREFETCH 0   // measured on B200: pulling the next chunk's rows into L2 one iteration ahead is SLOWER (94.7 vs 89.2 ms per batch)
 #endif
@@ -895,7 +905,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 // the four shadow results of the path: one 32-byte sector, read before the loop
                 float4 sr01, sr23;
                 ld_rows2(reinterpret_cast<const float4*>(wb.sres) + (size_t)pid * 2u, sr01, sr23);
-#pragma unroll 1
+#pragma unroll kShadeSumUnroll
                 for (uint32_t s = 0; s < 4u; ++s) {
                     if (!((need >> s) & 1u)) continue;
                     DirLight L;
@@ -1021,7 +1031,7 @@ __global__ void __launch_bounds__(LogicCfg<SEG, FUSED>::kThreads, LogicCfg<SEG, 
                 uint32_t need = 0u;
                 // chunks without any shadow ray are skipped here (their lights contribute nothing, main.rs:418-421)
                 for (;;) {
-#pragma unroll 1
+#pragma unroll kShadeBeginUnroll
                     for (uint32_t s = 0; s < 4u && li0 + s < sc.n_lights; ++s) {
                         DirLight L;
                         if (!approx_light(sc.lights[li0 + s], h.pos, L)) continue;
