@@ -204,3 +204,51 @@ def test_c4_4k_epoch_properties(b200rt, oracle, gpu_ctx, fixture_world):
     assert np.array_equal(g[1040:1088, :, 3], o_acc[1040:1088, :, 3])
     assert np.array_equal(g[1040:1088].view(np.uint32), a[1040:1088].view(np.uint32))     # band == same rows of the full frame
     assert_stochastic_agreement(g[1040:1088], o_acc[1040:1088], "C4 band 3840x48 x 4 epochs", 4)
+
+
+def test_split_tile_range_cast_bitwise(b200rt, mesh_ctx):
+    """Rounds of few rays on a scene of many tiles take the split form of the tiled cast (a 128-ray block per CTA, the tile
+    range over its four warps, partial results folded in tile order): the same bits as the unsplit cast, for trusted rays,
+    rays from infinity and NaN rays alike (the stochastic tracer produces all three on this scene)."""
+    import os
+    ctx, world, _ = mesh_ctx
+    cam = b200rt.fixture_camera()
+    p = b200rt.default_params(width=400, height=250, seed=9)
+    out = {}
+    for name, sb in (("split", None), ("unsplit", "0"), ("always", "1000000")):
+        if sb is None:
+            os.environ.pop("B200RT_WF_SPLIT_BELOW", None)
+        else:
+            os.environ["B200RT_WF_SPLIT_BELOW"] = sb
+        try:
+            ctx.reset_stats()
+            out[name] = (ctx.render_distributed(cam, p, 0, 2), ctx.stats())
+        finally:
+            os.environ.pop("B200RT_WF_SPLIT_BELOW", None)
+    ref = out["unsplit"][0]
+    assert (ref[..., 3] > 0).mean() > 0.5
+    for name in ("split", "always"):
+        assert np.array_equal(out[name][0].view(np.uint32), ref.view(np.uint32)), name
+        assert out[name][1]["casts"] == out["unsplit"][1]["casts"]
+
+
+def test_device_round_loop_matches_host_rounds(b200rt, gpu_ctx):
+    """The wavefront's rounds repeated on the device (CUDA graph WHILE node) and enqueued from the host: the same bits, the
+    same casts; the device loop reports its rounds and launches through the device counters."""
+    import os
+    cam = b200rt.fixture_camera()
+    p = b200rt.default_params(width=640, height=360, seed=21)
+    gpu_ctx.reset_stats()
+    a = gpu_ctx.render_distributed(cam, p, 0, 5)
+    sa = gpu_ctx.stats()
+    os.environ["B200RT_WF_GRAPH"] = "0"
+    try:
+        gpu_ctx.reset_stats()
+        h = gpu_ctx.render_distributed(cam, p, 0, 5)
+        sh = gpu_ctx.stats()
+    finally:
+        del os.environ["B200RT_WF_GRAPH"]
+    assert np.array_equal(a.view(np.uint32), h.view(np.uint32))
+    assert sa["casts"] == sh["casts"] and sa["samples"] == sh["samples"]
+    assert sa["wavefront_rounds"] >= 15 and sa["wavefront_rounds"] % 2 == 1        # round 0 + pairs of rounds
+    assert sa["kernel_launches"] > 5 * sa["wavefront_rounds"] // 2
