@@ -430,7 +430,8 @@ RT_DI unsigned long long tile_candidates(const DScene& sc, uint32_t tile, uint2 
 // (Round 2 measured this pre-filter in packed form inside the rays-in-lanes loop - the same operations on ray pairs, FFMA2 /
 // FMUL2, the spheres beside the tile in the kernel parameter: the cast of a 16-epoch 4K batch took 66.6 ms against 63.4.  A
 // packed instruction occupies the FMA pipe for two issue slots: on an issue-bound kernel it saves nothing, and the four
-// spheres leave it two dependent chains where this loop has four.  Not built.)
+// spheres leave it two dependent chains where this loop has four.  Not built.  Nor is one test against a sphere around all
+// the scene's spheres ahead of the loop: 64.1 ms against 63.1 - most rays of the fixture room pass the enclosure.)
 // spheres (main.rs:264-324): a conservative pre-filter of main.rs:265-268 in fused arithmetic for 32 spheres at a
 // time — squared line-sphere distance |disp|^2 |dir|^2 - (disp.dir)^2 against r^2 with a 64u (r^2 + |disp|^2)
 // slack (both sides' rounding is <= 13u of that; NaNs pass) — then the exact test of the survivors in index
