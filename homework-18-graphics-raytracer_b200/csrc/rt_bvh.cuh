@@ -67,8 +67,9 @@ RT_DI bool bvh_filter_pair(const DScene& sc, uint32_t i, const DRay& ray) {
 }
 
 // main.rs:229-233 over the accepted triangles in index order == the smallest t, the later index on a tie (no NaN)
+template <bool FILTER = true>
 RT_DI void bvh_try_triangle(const DScene& sc, uint32_t i, const DRay& ray, Best& best, bool& nan_seen, uint32_t& tested) {
-    if (!bvh_filter_pair(sc, i, ray)) return;
+    if (FILTER && !bvh_filter_pair(sc, i, ray)) return;
     Best cand;
     tested += 1u;
     if (!tri_exact_eval(sc.tri_exact + 4 * (size_t)i, (int32_t)i, ray, cand)) return;
@@ -103,8 +104,13 @@ RT_DI void bvh_cast_triangles(const DScene& sc, const DRay& ray, Best& best, boo
                     // of the leaf's triangles only those that ARE nearly parallel (the reference's own n.dir), and those the
                     // spatial tree does not hold (flagged), are this pass's business; NaN normals compare false and stay
                     const uint32_t e = sc.nbvh_tris[w1 + k], i = e & ~kBvhLeafBit;
-                    if (!(e & kBvhLeafBit) && fabsf(dot(mk3(sc.tri_exact[4 * (size_t)i]), ray.d)) >= kBvhBand) continue;
-                    bvh_try_triangle(sc, i, ray, best, nan_seen, tested);
+                    const float nd = dot(mk3(sc.tri_exact[4 * (size_t)i]), ray.d);        // the reference's own n.dir (primitives.rs:45)
+                    if (!(e & kBvhLeafBit) && fabsf(nd) >= kBvhBand) continue;
+                    // main.rs:185-188 decided here (the exact test starts with the same comparison on the same bits): a light
+                    // that lies in the plane of a thousand triangles sends every one of its shadow rays through this loop
+                    const bool bf = nd > 0.0f;
+                    if ((bf && ray.face == kFront) || (!bf && ray.face == kBack)) continue;
+                    bvh_try_triangle<false>(sc, i, ray, best, nan_seen, tested);        // (near-parallel pairs pass the filter anyway)
                 }
             }
             if (sp == 0) break;
