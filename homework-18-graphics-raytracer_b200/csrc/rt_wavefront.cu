@@ -596,7 +596,12 @@ RT_DI void wf_cast_rays_bvh(const DScene& sc, IO io, const uint32_t n_work, Cast
     }
 }
 }  // namespace
-__global__ void __launch_bounds__(128, 4) wf_cast_bvh_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf, DCounters* __restrict__ cnt) {
+// the traversal chases pointers through L2 (a few hundred dependent node loads per ray): it wants warps, not registers.
+// Measured on B200, C5 frame: 4 CTAs of 128 threads per SM 1146 ms, 6: 947, 8: 815, 10: 778, 12: 976, 16: 899
+#ifndef WF_BVH_MIN_BLOCKS
+#define WF_BVH_MIN_BLOCKS 10
+#endif
+__global__ void __launch_bounds__(128, WF_BVH_MIN_BLOCKS) wf_cast_bvh_kernel(const DScene sc, const WfBuffers wb, const uint32_t buf, DCounters* __restrict__ cnt) {
     if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
     const WfWork wk = wf_work(wb, buf);
     const uint32_t n_work = wk.n_real();
@@ -608,7 +613,7 @@ __global__ void __launch_bounds__(128, 4) wf_cast_bvh_kernel(const DScene sc, co
     wf_cast_rays_bvh(sc, io, wk.n_virtual(), cs);
     wf_cast_tail(sc, cs, n_work, cnt);
 }
-__global__ void __launch_bounds__(128, 4) wf_cast_bvh_primary_kernel(const DScene sc, const DCamera cam, const DParams p, const WfBuffers wb,
+__global__ void __launch_bounds__(128, WF_BVH_MIN_BLOCKS) wf_cast_bvh_primary_kernel(const DScene sc, const DCamera cam, const DParams p, const WfBuffers wb,
                                                                      const uint32_t buf, DCounters* __restrict__ cnt) {
     if (blockIdx.x == 0 && threadIdx.x < sizeof(WfCounters) / 4) reinterpret_cast<uint32_t*>(&wb.ctl->c[buf ^ 1u])[threadIdx.x] = 0u;
     CastStats cs;
@@ -1285,8 +1290,8 @@ cudaError_t launch_distributed_wavefront(const DScene& sc, const DCamera& cam, c
     // one round on `stream`: the cast of the rays requested in the round before, then the passes that consume it
     auto launch_round = [&](uint32_t round, uint32_t buf) {
         if (bvh) {
-            if (round == 0u && fused_primary) wf_cast_bvh_primary_kernel<<<sm_count * 8, 128, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
-            else wf_cast_bvh_kernel<<<sm_count * 8, 128, 0, stream>>>(sc, wb, buf, d_cnt);
+            if (round == 0u && fused_primary) wf_cast_bvh_primary_kernel<<<sm_count * 2 * WF_BVH_MIN_BLOCKS, 128, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
+            else wf_cast_bvh_kernel<<<sm_count * 2 * WF_BVH_MIN_BLOCKS, 128, 0, stream>>>(sc, wb, buf, d_cnt);
         } else if (round == 0u && fused_primary) {
             if (rays_in_lanes) wf_cast_rl_primary_kernel<<<sm_count * WF_CAST_RL_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, *sc.h_tile0, cam, p, wb, buf, d_cnt);
             else wf_cast_rl_tiled_primary_kernel<<<sm_count * WF_CAST_RL_TILED_MIN_BLOCKS, kRlThreads, 0, stream>>>(sc, cam, p, wb, buf, d_cnt);
