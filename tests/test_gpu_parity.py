@@ -306,3 +306,59 @@ def test_wavefront_fused_levels_light_counts(b200rt, gpu_ctx, extra):
                 assert st["casts"] == st_m["casts"]          # > 4 lights: the megakernel's casts exactly
     finally:
         ctx.close()
+
+
+def test_obj_mesh_with_texcoords_and_normals_renders_like_the_oracle(b200rt, oracle, tmp_path):
+    """N3 through the hot path: a two-model OBJ with `vt` and `vn` (a smooth-shaded dome over a textured ground plate)
+    loaded with b200rt_world_load_obj_ex - interpolated vertex normals (main.rs:248-251) and interpolated uv feeding a
+    procedural texture (main.rs:252, materials.rs:85-103) - renders the oracle's frame: identical hit ids, colours to 1e-4."""
+    n = 12
+    lines, vid = ["o dome"], {}
+    for j in range(n + 1):
+        for i in range(n + 1):
+            u, v = i / n, j / n
+            x, z = 2 * u - 1, 2 * v - 1
+            y = 0.6 * (1 - x * x) * (1 - z * z)
+            nx, nz = 1.2 * x * (1 - z * z), 1.2 * z * (1 - x * x)           # -dy/dx, -dy/dz
+            nl = (nx * nx + 1 + nz * nz) ** 0.5
+            lines += [f"v {x:.6f} {y:.6f} {z:.6f}", f"vt {u:.6f} {v:.6f}", f"vn {nx / nl:.6f} {1 / nl:.6f} {nz / nl:.6f}"]
+            vid[(i, j)] = len(vid) + 1
+    for j in range(n):
+        for i in range(n):
+            a, b_, c, d = vid[(i, j)], vid[(i + 1, j)], vid[(i + 1, j + 1)], vid[(i, j + 1)]
+            lines.append(f"f {a}/{a}/{a} {d}/{d}/{d} {c}/{c}/{c} {b_}/{b_}/{b_}")   # a quad: fan of two, facing +y
+    lines += ["g plate", "v -3 -0.01 -3", "v 3 -0.01 -3", "v 3 -0.01 3", "v -3 -0.01 3", "vt 0 0", "vt 1 0", "vt 1 1", "vt 0 1",
+              "f -4/-4 -1/-1 -2/-2 -3/-3"]
+    path = tmp_path / "dome.obj"
+    path.write_text("\n".join(lines) + "\n")
+    w = b200rt.World()
+    dome = w.push_object(b200rt.generative_material(diffuse_fn=b200rt.DIFFUSE_CHECKER_UPV, freq=8.0, c0=(1.0, 0.2, 0.2), c1=(0.2, 0.2, 1.0),
+                                                    shiness=0.3, smoothness=0.05))
+    plate = w.push_object(b200rt.generative_material(diffuse_fn=b200rt.DIFFUSE_STRIPE_V, freq=12.0, c0=(0.9, 0.9, 0.9), c1=(0.3, 0.5, 0.3),
+                                                     shiness=0.4, smoothness=0.3))
+    ident = dict(scale_div=1.0, offset=(0, 0, 0), use_texcoords=True, use_normals=True)
+    assert dome.load_obj_ex(str(path), model_index=0, **ident) == 2 * n * n
+    assert plate.load_obj_ex(str(path), model_index=1, **ident) == 2
+    w.push_light(b200rt.directional_light([-0.4, -1.0, -0.3], [1.0, 0.95, 0.9]))
+    w.push_light(b200rt.point_light([1.5, 2.0, 1.5], [0.6, 0.6, 0.8]))
+    cam = b200rt.fixture_camera()
+    ctx = b200rt.Context(0)
+    ctx.upload_scene(w)
+    for cm in (b200rt.CAST_TWO_PHASE, b200rt.CAST_BVH):
+        rgb, prim, _ = check_whitted(b200rt, oracle, ctx, w, b200rt.default_params(width=320, height=240, cast_mode=cm), cam)
+    assert (prim >= 0).mean() > 0.3 and (prim < 2 * n * n).mean() > 0.05 and (prim >= 2 * n * n).any()
+    # flat shading of the same file gives another frame: the normals of the file are really used
+    w2 = b200rt.World()
+    d2 = w2.push_object(b200rt.color_material(shiness=0.3, smoothness=0.05))
+    d2.load_obj_ex(str(path), model_index=0, scale_div=1.0, offset=(0, 0, 0))
+    w2.push_light(b200rt.directional_light([-0.4, -1.0, -0.3], [1.0, 0.95, 0.9]))
+    ctx.upload_scene(w2)
+    flat, _ = ctx.render_whitted(cam, b200rt.default_params(width=320, height=240))
+    w3 = b200rt.World()
+    d3 = w3.push_object(b200rt.color_material(shiness=0.3, smoothness=0.05))
+    d3.load_obj_ex(str(path), model_index=0, scale_div=1.0, offset=(0, 0, 0), use_normals=True)
+    w3.push_light(b200rt.directional_light([-0.4, -1.0, -0.3], [1.0, 0.95, 0.9]))
+    ctx.upload_scene(w3)
+    smooth, _ = ctx.render_whitted(cam, b200rt.default_params(width=320, height=240))
+    assert np.abs(flat - smooth).max() > 0.02
+    ctx.close()
